@@ -1,0 +1,43 @@
+/* ns_scenario.h — binary "scenario script" format shared by the three executors of the
+ * netsim flow/event hot path:
+ *   1. the UNMODIFIED reference core (/root/reference, built into oracle/_ref/) driven by
+ *      oracle/ref_scenario.c, a behaviour module written against the reference's module API
+ *      (sim.h:14-23, data.h:124-136);
+ *   2. the CPU restatement oracle/ns_oracle.c;
+ *   3. the sm_100a CUDA engine netsim_b200/csrc/ (through include/netsim_b200.h).
+ * A scenario is everything a behaviour module would do to the core, written down as data:
+ * nodes with their capacities (modules/p2p.c:144-170 writes node->maximum_bandwidth the same way),
+ * resources (sim_node_new_resource / sim_node_add_resource, sim.c:129-154), and groups of
+ * operations that run at init, at scheduled USER events (event.h:56-74) or when a given flow
+ * completes (a HNDR_USER handler on FLOW_DONE, like modules/test04.c:23-35).
+ * All integers little-endian, doubles IEEE-754 binary64.
+ */
+#ifndef NS_SCENARIO_H
+#define NS_SCENARIO_H
+#include <stdint.h>
+
+#define NS_SC_MAGIC   0x4353534eu /* "NSSC" */
+#define NS_SC_VERSION 1u
+
+enum ns_op_kind {
+	NS_OP_CREATE = 1, /* sim_establish_flow(rid[c], start, node[a], node[b]); bwcalc -> x, dlycalc -> y */
+	NS_OP_SCHED  = 2, /* event_add(event_new(c ? now+x : x, USER, group a)) */
+	NS_OP_CLOSE  = 3, /* flow_close(flow created by the a-th executed CREATE), if still alive */
+	NS_OP_END    = 4, /* sim_end(): the event loop stops before the next pop (main.c:51-52) */
+};
+
+struct ns_sc_header {
+	uint32_t magic, version;
+	uint32_t seed;       /* srandom(seed) before anything else; 1 == glibc default state */
+	uint32_t flags;      /* reserved, 0 */
+	int32_t n_nodes, n_resources, n_copies, n_groups, n_ops, n_ondone;
+	int32_t pad[2];
+};                           /* 48 bytes, followed by the arrays below in this order */
+/* double max_up[n_nodes];  double max_down[n_nodes];          node->maximum_bandwidth[0|1] */
+struct ns_sc_resource { int32_t owner; int32_t bit_rate; int64_t len; };   /* sim_node_new_resource */
+struct ns_sc_copy     { int32_t node;  int32_t res; };                    /* sim_node_add_resource */
+/* int32_t group_off[n_groups+1];   group g = ops[group_off[g] .. group_off[g+1]); group 0 runs at init */
+struct ns_sc_op { int32_t kind, a, b, c; int64_t start; double x, y; };  /* 40 bytes */
+struct ns_sc_ondone { int32_t flow_ord; int32_t group; };                /* sorted by flow_ord, unique */
+
+#endif

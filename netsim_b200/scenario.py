@@ -1,0 +1,317 @@
+"""Scenario scripts: the workload description shared by the reference core, the CPU oracle and the
+CUDA engine (binary layout: include/ns_scenario.h).
+
+A scenario writes down, as data, what a netsim behaviour module does to the core through its API:
+nodes and their capacities (modules/p2p.c:144-170), resources (sim.c:129-154), flows established at
+init or from USER events (sim.c:42-94, modules/test02.c:31-33), flows started when another flow
+completes (modules/test04.c:23-35), explicit closes (flow.c:241) and the end of simulation
+(modules/p2p.c:50-53).  `reference_tests()` restates the reference's own scenario modules
+test00..test05 in this form; `swarm()`/`churn()` are the synthetic configs of SURVEY.md §8d.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+MAGIC = 0x4353534E
+VERSION = 1
+OP_CREATE, OP_SCHED, OP_CLOSE, OP_END = 1, 2, 3, 4
+
+OP_DTYPE = np.dtype([("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"),
+                     ("start", "<i8"), ("x", "<f8"), ("y", "<f8")])
+RES_DTYPE = np.dtype([("owner", "<i4"), ("bit_rate", "<i4"), ("len", "<i8")])
+COPY_DTYPE = np.dtype([("node", "<i4"), ("res", "<i4")])
+ONDONE_DTYPE = np.dtype([("flow_ord", "<i4"), ("group", "<i4")])
+
+
+def create(src: int, dst: int, res: int, start: int, ub: float, delay: float):
+    return (OP_CREATE, src, dst, res, start, float(ub), float(delay))
+
+
+def sched(group: int, time: float, relative: bool = False):
+    return (OP_SCHED, group, 0, 1 if relative else 0, 0, float(time), 0.0)
+
+
+def close(flow_ord: int):
+    return (OP_CLOSE, flow_ord, 0, 0, 0, 0.0, 0.0)
+
+
+def end():
+    return (OP_END, 0, 0, 0, 0, 0.0, 0.0)
+
+
+@dataclass
+class Scenario:
+    max_up: np.ndarray
+    max_down: np.ndarray
+    resources: np.ndarray                      # RES_DTYPE
+    copies: np.ndarray                         # COPY_DTYPE
+    groups: List[Sequence[tuple]] = field(default_factory=list)   # group 0 = init
+    ondone: Dict[int, int] = field(default_factory=dict)          # flow ordinal -> group
+    seed: int = 1
+    # optional pre-packed op table (big generators build numpy directly)
+    _ops: np.ndarray | None = None
+    _group_off: np.ndarray | None = None
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.max_up.shape[0])
+
+    def packed_ops(self) -> Tuple[np.ndarray, np.ndarray]:
+        if self._ops is not None:
+            return self._ops, self._group_off
+        off = np.zeros(len(self.groups) + 1, dtype="<i4")
+        rows = []
+        for g, ops in enumerate(self.groups):
+            rows.extend(ops)
+            off[g + 1] = len(rows)
+        arr = np.zeros(len(rows), dtype=OP_DTYPE)
+        for i, r in enumerate(rows):
+            arr[i] = r
+        return arr, off
+
+    def n_creates(self) -> int:
+        ops, _ = self.packed_ops()
+        return int((ops["kind"] == OP_CREATE).sum())
+
+    def to_bytes(self) -> bytes:
+        ops, off = self.packed_ops()
+        od = np.zeros(len(self.ondone), dtype=ONDONE_DTYPE)
+        for i, (k, v) in enumerate(sorted(self.ondone.items())):
+            od[i] = (k, v)
+        n_groups = len(off) - 1
+        hdr = struct.pack("<IIII6i2i", MAGIC, VERSION, self.seed & 0xFFFFFFFF, 0,
+                          self.n_nodes, len(self.resources), len(self.copies), n_groups,
+                          len(ops), len(od), 0, 0)
+        return b"".join([
+            hdr,
+            np.ascontiguousarray(self.max_up, dtype="<f8").tobytes(),
+            np.ascontiguousarray(self.max_down, dtype="<f8").tobytes(),
+            np.ascontiguousarray(self.resources, dtype=RES_DTYPE).tobytes(),
+            np.ascontiguousarray(self.copies, dtype=COPY_DTYPE).tobytes(),
+            np.ascontiguousarray(off, dtype="<i4").tobytes(),
+            np.ascontiguousarray(ops, dtype=OP_DTYPE).tobytes(),
+            od.tobytes(),
+        ])
+
+    def write(self, path: str) -> None:
+        with open(path, "wb") as f:
+            f.write(self.to_bytes())
+
+
+def _mk(max_bw: Sequence[Tuple[float, float]], resources, copies=(), groups=(), ondone=None, seed=1):
+    mu = np.array([m[0] for m in max_bw], dtype="<f8")
+    md = np.array([m[1] for m in max_bw], dtype="<f8")
+    res = np.zeros(len(resources), dtype=RES_DTYPE)
+    for i, r in enumerate(resources):
+        res[i] = (r[0], r[2] if len(r) > 2 else 0, r[1])
+    cp = np.zeros(len(copies), dtype=COPY_DTYPE)
+    for i, c in enumerate(copies):
+        cp[i] = c
+    return Scenario(mu, md, res, cp, [list(g) for g in groups], dict(ondone or {}), seed)
+
+
+# --------------------------------------------------------------------------------------------
+# The reference's own scenario modules, restated (node order == sim_create_node call order).
+# --------------------------------------------------------------------------------------------
+def reference_tests() -> Dict[str, Scenario]:
+    L = 5000000
+    t = {}
+    # modules/test00.c:22-40 — server(5000) -> client(1000), ub 500, delay .2
+    t["test00"] = _mk([(5000, 5000), (1000, 1000)], [(0, L)], groups=[[create(0, 1, 0, 0, 500, 0.2)]])
+    # modules/test01.c:22-41 — same with ub 500000 (node-limited)
+    t["test01"] = _mk([(5000, 5000), (1000, 1000)], [(0, L)], groups=[[create(0, 1, 0, 0, 500000, 0.2)]])
+    # modules/test02.c:38-63 — second flow (USER @5000) after the first has closed
+    t["test02"] = _mk([(5000, 5000), (1000, 1000), (1000, 1000)], [(0, L)],
+                      groups=[[create(0, 1, 0, 0, 500000, 0.2), sched(1, 5000)],
+                              [create(0, 2, 0, 0, 500000, 0.2)]])
+    # modules/test03.c:38-63 — second flow (USER @2000) throttles the first (server max 1000)
+    t["test03"] = _mk([(1000, 1000)] * 3, [(0, L)],
+                      groups=[[create(0, 1, 0, 0, 500000, 0.2), sched(1, 2000)],
+                              [create(0, 2, 0, 0, 500000, 0.2)]])
+    # modules/test04.c:23-73 / test05.c:24-75 — s1->s2; when it completes: s1->c1 @0 and a USER
+    # event .1 s later that starts s1->c2 @0 and s2->c1 @10000 (relay source, range merge).
+    # nodes: 0=s1 1=s2 2=c1 3=c2
+    t["test04"] = _mk([(1000, 1000)] * 4, [(0, L)],
+                      groups=[[create(0, 1, 0, 0, 500000, 0.2)],
+                              [create(0, 2, 0, 0, 500000, 0.2), sched(2, 0.1, relative=True)],
+                              [create(0, 3, 0, 0, 500000, 0.2), create(1, 2, 0, 10000, 500000, 0.2)]],
+                      ondone={0: 1})
+    t["test05"] = t["test04"]
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# Synthetic generators
+# --------------------------------------------------------------------------------------------
+def _tz(i: np.ndarray, n: int) -> np.ndarray:
+    """time zone of node i of n, as modules/p2p.c:146,155,171 (24*i/n, integer division)."""
+    return (24 * i.astype(np.int64)) // max(n, 1)
+
+
+def _ub_delay(tz_a: np.ndarray, tz_b: np.ndarray):
+    """distance_based_bw / distance_based_delay, modules/p2p_common.h:181-189,214-221."""
+    d = np.abs(tz_a - tz_b)
+    return (4000 - 100 * d).astype("<f8"), 0.02 * d.astype("<f8") + 0.1
+
+
+def swarm(n_peers: int, n_hubs: int, n_catalogue: int = 16, seeds_per_peer: int = 4,
+          mean_strips: float = 9.0, max_strips: int = 32, hub_frac: float = 0.1,
+          res_len: int = 600000, arrival_window: float = 0.0, arrival_quantum: float = 0.01,
+          seed: int = 12345, end_time: float | None = None, rearm: bool = False) -> Scenario:
+    """SURVEY.md §8d config 3 as a script: `n_hubs` seeders (160000/160000 Kbit/s, hold the whole
+    catalogue) and `n_peers` peers (8000 up / 40000 down) that each seed `seeds_per_peer` catalogue
+    entries and fetch one they do not hold, in 1+Poisson(mean_strips) (<= max_strips) strips from
+    distinct holders (Zipf(1) over hubs with probability `hub_frac`, uniform seeding peers
+    otherwise).  ub/delay follow p2p_common.h distance rules.  Arrivals are at t=0 (init) when
+    arrival_window == 0, else USER events on an `arrival_quantum` grid inside the window.
+    """
+    rng = np.random.default_rng(seed)
+    n = n_hubs + n_peers
+    idx = np.arange(n)
+    is_hub = idx < n_hubs
+    tz = np.where(is_hub, _tz(idx, n_hubs), _tz(idx - n_hubs, n_peers))
+    mu = np.where(is_hub, 160000.0, 8000.0)
+    md = np.where(is_hub, 160000.0, 40000.0)
+    res = np.zeros(n_catalogue, dtype=RES_DTYPE)
+    res["owner"] = rng.integers(0, n_hubs, n_catalogue)
+    res["len"] = res_len
+    res["bit_rate"] = 2000
+    # catalogue copies: every hub holds everything; each peer seeds a few
+    holders: List[List[int]] = [[] for _ in range(n_catalogue)]
+    cp = []
+    for r in range(n_catalogue):
+        for h in range(n_hubs):
+            if h != res["owner"][r]:
+                cp.append((h, r))
+    seeds = np.stack([rng.permutation(n_catalogue)[:seeds_per_peer + 1] for _ in range(n_peers)]) \
+        if n_peers else np.zeros((0, seeds_per_peer + 1), dtype=np.int64)
+    for p in range(n_peers):
+        for r in seeds[p, :seeds_per_peer]:
+            cp.append((n_hubs + p, int(r)))
+            holders[int(r)].append(n_hubs + p)
+    holders_np = [np.array(h, dtype=np.int64) for h in holders]
+    zipf_w = 1.0 / np.arange(1, n_hubs + 1)
+    zipf_w /= zipf_w.sum()
+    ops = []
+    per_peer_ops: List[List[tuple]] = []
+    for p in range(n_peers):
+        node = n_hubs + p
+        want = int(seeds[p, seeds_per_peer])          # a catalogue entry this peer does not seed
+        k = int(min(max_strips, 1 + rng.poisson(mean_strips)))
+        srcs: List[int] = []
+        tries = 0
+        while len(srcs) < k and tries < 8 * k:
+            tries += 1
+            if rng.random() < hub_frac or len(holders_np[want]) == 0:
+                s = int(rng.choice(n_hubs, p=zipf_w))
+            else:
+                s = int(holders_np[want][rng.integers(0, len(holders_np[want]))])
+            if s != node and s not in srcs:
+                srcs.append(s)
+        k = len(srcs)
+        strip = res_len // k
+        ub, dl = _ub_delay(tz[np.array(srcs)], np.full(k, tz[node]))
+        per_peer_ops.append([create(srcs[i], node, want, i * strip, ub[i], dl[i]) for i in range(k)])
+    groups: List[List[tuple]] = [[]]
+    if arrival_window <= 0:
+        for o in per_peer_ops:
+            groups[0].extend(o)
+    else:
+        t_arr = np.floor(rng.random(n_peers) * arrival_window / arrival_quantum) * arrival_quantum
+        order = np.argsort(t_arr, kind="stable")
+        for p in order:
+            groups.append(per_peer_ops[p])
+            groups[0].append(sched(len(groups) - 1, float(t_arr[p])))
+    if end_time is not None:
+        groups.append([end()])
+        groups[0].append(sched(len(groups) - 1, end_time))
+    sc = Scenario(mu.astype("<f8"), md.astype("<f8"), res, np.array(cp, dtype=COPY_DTYPE).reshape(-1),
+                  groups, {}, seed=1)
+    return sc
+
+
+def random_small(seed: int, n_nodes: int = 8, n_flows: int = 12, relay: bool = False,
+                 closes: bool = True) -> Scenario:
+    """Small randomized scripts for differential testing: a few sources holding full copies and
+    "downloads" (one destination fetching one resource in 1..4 strips from distinct sources, all
+    strips established together like client_new_play1, client_behaviour.c:382-385) started at
+    init, from USER events on a coarse time grid (equal-time batches) or when another flow
+    completes; optional explicit closes from USER events; optional relay (a download whose source
+    is itself still being filled, exercising FLOW_SPEED_THROTTLE, flow.c:408-423)."""
+    rng = np.random.default_rng(seed)
+    caps = [(float(rng.choice([500, 1000, 2000, 8000])), float(rng.choice([500, 1000, 4000, 40000])))
+            for _ in range(n_nodes)]
+    n_src = max(2, n_nodes // 3)
+    L = int(rng.choice([20000, 100000, 1000000]))
+    n_res = 3
+    resources = [(int(rng.integers(0, n_src)), L) for _ in range(n_res)]
+    copies = [(s, r) for r in range(n_res) for s in range(n_src) if s != resources[r][0]]
+    groups: List[List[tuple]] = [[]]
+    ondone: Dict[int, int] = {}
+    used_pairs = set()
+    have = set()                   # (dst, res) already being fetched
+    first_strip: List[Tuple[int, int, int]] = []   # (dst, res, flow ordinal of the strip at 0)
+    ord_ = 0
+
+    def download():
+        nonlocal ord_
+        for _ in range(50):
+            r = int(rng.integers(0, n_res))
+            d = int(rng.integers(n_src, n_nodes))
+            if (d, r) in have:
+                continue
+            k = int(rng.integers(1, 5))
+            srcs = [int(x) for x in rng.permutation(n_src)[:k] if (int(x), d) not in used_pairs]
+            if not srcs:
+                continue
+            k = len(srcs)
+            have.add((d, r))
+            strip = L // k
+            out = []
+            for i, s in enumerate(srcs):
+                used_pairs.add((s, d))
+                ub = float(rng.choice([300, 700, 1500, 4000, 500000]))
+                dl = float(rng.choice([0.1, 0.12, 0.2, 0.34]))
+                out.append(create(s, d, r, i * strip, ub, dl))
+                if i == 0:
+                    first_strip.append((d, r, ord_))
+                ord_ += 1
+            return out
+        return []
+
+    groups[0].extend(download())
+    grid = [float(x) for x in rng.choice([1.0, 2.5, 10.0, 10.0, 40.0, 100.0], size=8)]
+    guard = 0
+    while ord_ < n_flows and guard < 40:
+        guard += 1
+        g_ops = download()
+        if not g_ops:
+            continue
+        by_done = rng.random() < 0.35 and ord_ - len(g_ops) > 0
+        if by_done:
+            k = int(rng.integers(0, ord_ - len(g_ops)))
+            if k in ondone:
+                by_done = False
+        if not by_done and closes and ord_ > 2 and rng.random() < 0.3:
+            g_ops.append(close(int(rng.integers(0, ord_))))
+        groups.append(g_ops)
+        g = len(groups) - 1
+        if by_done:
+            ondone[k] = g
+        else:
+            groups[0].append(sched(g, grid[int(rng.integers(0, len(grid)))]))
+    if relay and first_strip:
+        # a peer that is still downloading [0, ...) of r becomes the (only) source of another peer
+        d0, r0, _ = first_strip[0]
+        for d in range(n_src, n_nodes):
+            if d != d0 and (d0, d) not in used_pairs and (d, r0) not in have:
+                have.add((d, r0))
+                used_pairs.add((d0, d))
+                groups.append([create(d0, d, r0, 0, float(rng.choice([700, 4000, 500000])), 0.2)])
+                groups[0].append(sched(len(groups) - 1, float(rng.choice([0.05, 1.0, 3.0]))))
+                break
+    return _mk(caps, resources, copies, groups, ondone, seed=1 + seed % 7)
