@@ -1,0 +1,137 @@
+/* netsim_b200.h — C ABI of the B200 device layer for netsim's flow/event hot path.
+ *
+ * Plain C, no torch/CUDA types in any signature. Every entry point returns 0 on success or a
+ * negative ns_err / a positive CUDA error code; nothing throws across the boundary. The host core
+ * (plain C, netsim's sim.c/main.c side) owns every handle.
+ *
+ * What each entry point replaces in the reference (paths relative to yshui/netsim):
+ *
+ *   ns_dev_create        sim_state_new (data.h:215-224) + the module's *_init building nodes,
+ *                        resources and first flows (sim.c:113-154, sim.c:42-94); the device tables
+ *                        are the SoA form of struct node/flow/range/event (data.h:15-151).
+ *   ns_dev_run           the event loop main.c:50-67 with its default handlers main.c:44-48:
+ *                        event_pop (event.h:20-25) -> device argmin + equal-timestamp batch;
+ *                        handle_speed_change (flow.c:341-384), bwspread (flow.c:35-205),
+ *                        queue_speed_event (flow.c:16-29), _range_update (range.h:91-118),
+ *                        range_calc_and_requeue_events (range.c:16-79), flow_done_handler /
+ *                        flow_close (flow.c:391-406, 241-292), flow_throttle_handler (flow.c:408-423),
+ *                        range_merge_with_next (range.c:83-124), event_add/remove (event.h:13-74).
+ *   ns_dev_records       write_record's byte stream (record.c:27-117), to be appended by the host
+ *                        to the mmap'd record file (record.c:119-153).
+ *   ns_dev_pick_batch    server_picker_opt1 + qselect_eval (modules/client_behaviour.h:63-88,
+ *                        modules/qselect.h:5-27) and server_picker_opt2 (client_behaviour.h:90-124)
+ *                        for a batch of simultaneous NEW_CONNECTION events.
+ *   ns_ens_*             replica ensembles: independent simulations side by side on
+ *                        one GPU, one digest per replica.
+ *   ns_rand_*            glibc random()/srandom() (TYPE_3) as used by sim.c:117,132, flow.c:327 and
+ *                        skiplist.h:34-40, with O(log n) jump-ahead.
+ */
+#ifndef NETSIM_B200_H
+#define NETSIM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum ns_err {
+	NS_OK = 0,
+	NS_E_BAD_SCENARIO = -1,
+	NS_E_BACK_IN_TIME = -2,  /* event.h:60-64: the reference would abort() here */
+	NS_E_NAN_TIME = -3,      /* event.h:67-70 */
+	NS_E_NULL_RANGE = -4,    /* the reference would dereference a NULL range (sim.c:69 -> range.c:21) */
+	NS_E_NO_PRODUCER = -5,   /* flow.c:411 */
+	NS_E_RING_FULL = -6,     /* pending-event ring too small: recreate with a larger ring_cap */
+	NS_E_TABLE_FULL = -7,    /* flow/range/resource/adjacency capacity exhausted */
+	NS_E_RECORDS_FULL = -8,  /* record buffer full: drain with ns_dev_records, then run again */
+	NS_E_NO_DEVICE = -9,
+	NS_E_ARG = -10,
+	NS_E_BATCH_FULL = -11,
+};
+
+enum ns_counter {
+	NS_CNT_EVENTS = 0, NS_CNT_SOLVES, NS_CNT_FULL_SPREADS, NS_CNT_FLOW_VISITS, NS_CNT_SPEED_CHANGE,
+	NS_CNT_FLOW_DONE, NS_CNT_DRAIN, NS_CNT_THROTTLE, NS_CNT_USER, NS_CNT_CREATES, NS_CNT_CLOSES,
+	NS_CNT_DRAWS, NS_CNT_SEQ, NS_CNT_LIVE_FLOWS, NS_CNT_PEAK_FLOWS, NS_CNT_BATCHES,
+	NS_CNT_PAR_EVENTS,   /* events handled by the grid-parallel path */
+	NS_CNT_MAX_BATCH, NS_CNT_WAVES, NS_CNT_RESERVED, NS_CNT_COUNT
+};
+
+enum ns_mode {
+	NS_MODE_AUTO = 0,   /* grid-parallel batches where legal, sequential otherwise */
+	NS_MODE_SEQ = 1,    /* one warp, strictly sequential (always legal; the parity anchor) */
+};
+
+typedef struct ns_dev ns_dev;
+typedef struct ns_ens ns_ens;
+
+struct ns_dev_opts {
+	int device;            /* CUDA device ordinal */
+	int mode;              /* enum ns_mode */
+	int want_records;      /* build the record byte stream */
+	int want_trace;        /* fp64 event trace rows (tests) */
+	uint64_t ring_cap;     /* pending speed-event ring entries, 0 = auto */
+	uint64_t record_cap;   /* bytes, 0 = auto */
+	uint64_t trace_cap;    /* rows, 0 = auto */
+	int cap_flows;         /* concurrent flows, 0 = auto (number of CREATE ops) */
+	int reserved[5];
+};
+
+struct ns_trace_row32 { uint32_t type, ord; double time, v0, v1; };
+
+struct ns_digest {          /* one per simulation */
+	uint64_t seed, events, solves, record_bytes, record_fnv1a;
+	double t_end;
+	int64_t status;
+};
+
+int  ns_dev_count(void);
+int  ns_dev_create(ns_dev **out, const void *scenario, size_t len, const struct ns_dev_opts *opts);
+/* handle events until the queue is empty, the script ended the run, or max_events (0 = no limit)
+ * events have been handled in total; device_ms (may be NULL) receives the CUDA-event time. */
+int  ns_dev_run(ns_dev *d, uint64_t max_events, float *device_ms);
+int  ns_dev_status(ns_dev *d);
+double ns_dev_now(ns_dev *d);
+int  ns_dev_counters(ns_dev *d, uint64_t out[NS_CNT_COUNT]);
+/* copy record bytes [offset, offset+cap) of the stream produced so far; *len = bytes copied,
+ * *total = bytes produced so far. */
+int  ns_dev_records(ns_dev *d, void *dst, size_t cap, size_t offset, size_t *len, size_t *total);
+int  ns_dev_digest(ns_dev *d, struct ns_digest *out);
+int  ns_dev_trace(ns_dev *d, struct ns_trace_row32 *dst, size_t cap_rows, size_t *rows);
+/* per creation ordinal {alive, speed[0], speed[1], drng->len}; per node {usage[0], usage[1],
+ * total_bwupbound[0], total_bwupbound[1]} */
+int  ns_dev_flow_state(ns_dev *d, double *out4, size_t max_flows, size_t *n);
+int  ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size_t *n);
+uint64_t ns_dev_launches(ns_dev *d);
+void ns_dev_destroy(ns_dev *d);
+
+/* replica ensembles: n independent scenarios resident on one GPU, stepped together */
+int  ns_ens_create(ns_ens **out, const void *const *scenarios, const size_t *lens, int n,
+		   const struct ns_dev_opts *opts);
+int  ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms);
+int  ns_ens_digests(ns_ens *e, struct ns_digest *out, int n);
+uint64_t ns_ens_launches(ns_ens *e);
+void ns_ens_destroy(ns_ens *e);
+
+/* batched source selection. Candidate tables are CSR: request q owns entries
+ * [off[q], off[q+1]) of val/node (already filtered by is_connected / usability).
+ * mode 1: keep the k[q] smallest by Lomuto quick-select; out_node/out_val (same CSR layout) hold
+ *         the permuted table, out_cnt[q] = min(c, k).  mode 2: first strict minimum -> out_node[q]
+ *         at off[q] (or -1), out_cnt[q] = 0/1.  Host buffers in, host buffers out. */
+int  ns_dev_pick_batch(int device, int mode, int n_req, const int32_t *off, const int32_t *val,
+		       const int32_t *node, const int32_t *k, int32_t *out_val, int32_t *out_node,
+		       int32_t *out_cnt, float *device_ms);
+
+/* glibc TYPE_3 random(): state is 31 words + two indices */
+struct ns_rand_state { int32_t st[31]; int32_t f, r; };
+void ns_rand_seed_host(struct ns_rand_state *g, uint32_t seed);
+uint32_t ns_rand_next_host(struct ns_rand_state *g);
+void ns_rand_jump_host(struct ns_rand_state *g, uint64_t n);   /* == n calls of ns_rand_next_host */
+
+const char *ns_strerror(int err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,578 @@
+// ns_engine.cu — kernels and the extern "C" layer (include/netsim_b200.h).
+//
+// Host side here is what netsim keeps on the host: parsing the module's script, sim_create_node /
+// sim_node_new_resource / sim_node_add_resource (sim.c:113-154: ids from random(), the R_NODE_CREATE
+// records) and laying out the device tables.  Everything from the first sim_establish_flow on —
+// rate solves, byte progress, completion times, event selection — runs in the kernels.
+// There is no CPU fallback: every entry point fails with NS_E_NO_DEVICE when CUDA is unusable.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <unordered_set>
+
+#include "ns_sim.cuh"
+#include "ns_model.cuh"
+#include "ns_seq.cuh"
+#include "ns_par.cuh"
+
+namespace cg = cooperative_groups;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "netsim_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return (int)e_; } } while (0)
+
+// ---------------------------------------------------------------- small kernels
+__global__ void k_fill_f64(double *p, u64 n, double v){
+	for (u64 i = blockIdx.x*(u64)blockDim.x+threadIdx.x; i < n; i += (u64)gridDim.x*blockDim.x) p[i] = v;
+}
+__global__ void k_fill_i32(int *p, u64 n, int v){
+	for (u64 i = blockIdx.x*(u64)blockDim.x+threadIdx.x; i < n; i += (u64)gridDim.x*blockDim.x) p[i] = v;
+}
+
+// run the script's init group (module *_init: first flows and scheduled USER events)
+__global__ void __launch_bounds__(32) k_init_groups(const Sim *sims, int n){
+	int s = blockIdx.x;
+	if (s >= n) return;
+	Ctx c;
+	ctx_load(c, &sims[s], threadIdx.x);
+	run_group(c, 0);
+	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
+	ctx_flush(c);
+}
+
+// one warp per simulation, strictly sequential event handling
+__global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n){
+	int s = blockIdx.x;
+	if (s >= n) return;
+	seq_run(&sims[s], scr[s], threadIdx.x);
+}
+
+// order-sensitive, parallel digest of a byte stream: sum over little-endian 64-bit words w_j of
+// mix64(w_j + K*(j+1)), finalised with the length (see netsim_b200/digest.py for the host mirror).
+__global__ void k_stream_hash(const uint8_t *p, u64 len, u64 *out){
+	u64 nw = (len+7)/8;
+	u64 acc = 0;
+	for (u64 j = blockIdx.x*(u64)blockDim.x+threadIdx.x; j < nw; j += (u64)gridDim.x*blockDim.x) {
+		u64 w = 0;
+		u64 b0 = j*8;
+		for (int k = 0; k < 8; k++) if (b0+k < len) w |= (u64)p[b0+k] << (8*k);
+		acc += ns_mix64(w+0x9e3779b97f4a7c15ULL*(j+1));
+	}
+	for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(FULLMASK, acc, d);
+	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+__global__ void k_flow_state(const Sim *sp, double *out4, int n){
+	const Sim &S = *sp;
+	for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		int f = S.ord2flow[i];
+		double a = 0, s0 = 0, s1 = 0, l = 0;
+		if (f >= 0) { a = 1; s0 = S.f_speed[0][f]; s1 = S.f_speed[1][f]; int dr = S.f_drng[f]; l = dr >= 0 ? S.r_len[dr] : 0; }
+		out4[4*i] = a; out4[4*i+1] = s0; out4[4*i+2] = s1; out4[4*i+3] = l;
+	}
+}
+__global__ void k_node_state(const Sim *sp, double *out4, int n){
+	const Sim &S = *sp;
+	for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		out4[4*i] = S.n_usage[0][i]; out4[4*i+1] = S.n_usage[1][i];
+		out4[4*i+2] = S.n_total[0][i]; out4[4*i+3] = S.n_total[1][i];
+	}
+}
+
+// ---------------------------------------------------------------- host-side simulation object
+struct HostSim {
+	Sim S;                         // device pointers
+	SeqScratch scr;
+	ParScratch par;
+	std::vector<void *> allocs;
+	size_t bytes = 0;
+	uint32_t seed = 1;
+	int n_creates = 0;
+};
+
+static int dev_alloc(HostSim &h, void **p, size_t bytes){
+	if (bytes == 0) bytes = 8;
+	CK(cudaMalloc(p, bytes));
+	h.allocs.push_back(*p);
+	h.bytes += bytes;
+	return 0;
+}
+template <typename T> static int dalloc(HostSim &h, T **p, size_t n){ return dev_alloc(h, (void **)p, n*sizeof(T)); }
+static int fill_f64(double *p, u64 n, double v){ if (!n) return 0; k_fill_f64<<<(unsigned)std::min<u64>((n+255)/256, 4096), 256>>>(p, n, v); CK(cudaGetLastError()); return 0; }
+static int fill_i32(int *p, u64 n, int v){ if (!n) return 0; k_fill_i32<<<(unsigned)std::min<u64>((n+255)/256, 4096), 256>>>(p, n, v); CK(cudaGetLastError()); return 0; }
+static void free_sim(HostSim &h){ for (void *p : h.allocs) cudaFree(p); h.allocs.clear(); }
+
+static u64 next_pow2(u64 x){ u64 p = 1; while (p < x) p <<= 1; return p; }
+
+static int host_rec(std::vector<uint8_t> &rec, double now, uint8_t minor, uint32_t id, int bytes, uint32_t ival){
+	// record.c:53-116 for the init-time records written on the host (R_NODE_CREATE, sim.c:123)
+	uint8_t b[19]; int n = 0;
+	b[n++] = 0; b[n++] = minor;
+	b[n++] = id >> 24; b[n++] = id >> 16; b[n++] = id >> 8; b[n++] = id;
+	uint32_t t = (uint32_t)(int)now;
+	b[n++] = t >> 24; b[n++] = t >> 16; b[n++] = t >> 8; b[n++] = t;
+	uint16_t ut = (uint16_t)(int)((now-((int)now))*1000);
+	b[n++] = ut >> 8; b[n++] = ut;
+	b[n++] = (uint8_t)(int8_t)bytes;
+	if (bytes == 1) b[n++] = (uint8_t)ival;
+	else { b[n++] = ival >> 24; b[n++] = ival >> 16; b[n++] = ival >> 8; b[n++] = ival; }
+	rec.insert(rec.end(), b, b+n);
+	return n;
+}
+
+// Build one simulation's device tables from a scenario script.
+static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_opts &o, bool parallel_scratch){
+	if (len < sizeof(ns_sc_header)) return NS_E_BAD_SCENARIO;
+	ns_sc_header H;
+	memcpy(&H, scenario, sizeof H);
+	if (H.magic != NS_SC_MAGIC || H.version != NS_SC_VERSION || H.n_groups < 1 || H.n_nodes < 0) return NS_E_BAD_SCENARIO;
+	size_t need = sizeof H+(size_t)H.n_nodes*16+(size_t)H.n_resources*sizeof(ns_sc_resource)+(size_t)H.n_copies*sizeof(ns_sc_copy)+
+		(size_t)(H.n_groups+1)*4+(size_t)H.n_ops*sizeof(ns_sc_op)+(size_t)H.n_ondone*sizeof(ns_sc_ondone);
+	if (len < need) return NS_E_BAD_SCENARIO;
+	const char *p = (const char *)scenario+sizeof H;
+	const double *max_up = (const double *)p; p += (size_t)H.n_nodes*8;
+	const double *max_down = (const double *)p; p += (size_t)H.n_nodes*8;
+	const ns_sc_resource *rs = (const ns_sc_resource *)p; p += (size_t)H.n_resources*sizeof *rs;
+	const ns_sc_copy *cp = (const ns_sc_copy *)p; p += (size_t)H.n_copies*sizeof *cp;
+	const int32_t *goff = (const int32_t *)p; p += (size_t)(H.n_groups+1)*4;
+	const ns_sc_op *ops = (const ns_sc_op *)p; p += (size_t)H.n_ops*sizeof *ops;
+	const ns_sc_ondone *od = (const ns_sc_ondone *)p;
+	int n_create = 0, n_sched = 0;
+	for (int i = 0; i < H.n_ops; i++) {
+		if (ops[i].kind == NS_OP_CREATE) {
+			n_create++;
+			if (ops[i].a < 0 || ops[i].a >= H.n_nodes || ops[i].b < 0 || ops[i].b >= H.n_nodes || ops[i].c < 0 || ops[i].c >= H.n_resources) return NS_E_BAD_SCENARIO;
+		} else if (ops[i].kind == NS_OP_SCHED) {
+			n_sched++;
+			if (ops[i].a < 0 || ops[i].a >= H.n_groups) return NS_E_BAD_SCENARIO;
+		}
+	}
+	for (int i = 0; i < H.n_ondone; i++) if (od[i].group < 0 || od[i].group >= H.n_groups) return NS_E_BAD_SCENARIO;
+	h.seed = H.seed; h.n_creates = n_create;
+
+	Sim &S = h.S;
+	memset(&S, 0, sizeof S);
+	const int N = H.n_nodes;
+	S.n_nodes = N;
+	S.cap_flows = o.cap_flows > 0 ? o.cap_flows : std::max(16, n_create);
+	const int F = S.cap_flows;
+	S.cap_ranges = 2*n_create+H.n_resources+H.n_copies+16;
+	S.cap_res = H.n_resources+H.n_copies+n_create+16;
+	S.cap_users = 2*n_sched+16;
+	S.cap_ord = 2*n_create+16;
+	S.n_groups = H.n_groups; S.n_ops = H.n_ops; S.n_ondone = H.n_ondone; S.n_rids = H.n_resources;
+	S.ring_cap = o.ring_cap ? next_pow2(std::max<u64>(o.ring_cap, NS_TILE)) : next_pow2(std::min<u64>(std::max<u64>(1u << 16, 128ull*F), 1ull << 28));
+	S.n_ring_tiles = (int)(S.ring_cap >> NS_TILE_SHIFT);
+	S.n_l = 2*F+S.cap_users;
+	S.n_l_tiles = (S.n_l+NS_TILE-1)/NS_TILE;
+	S.adj_arena_cap = 16*F+8*N+64;
+	S.batch_cap = (int)std::min<u64>(S.ring_cap/2, 1ull << 30);
+	S.want_rec = o.want_records; S.want_tr = o.want_trace;
+	S.rec_cap = o.want_records ? (o.record_cap ? o.record_cap : std::max<u64>(1u << 20, 64ull*N+4096ull*F)) : 0;
+	S.tr_cap = o.want_trace ? (o.trace_cap ? o.trace_cap : (1u << 20)) : 0;
+
+	int rc;
+#define DA(ptr, n) if ((rc = dalloc(h, &(ptr), (size_t)(n)))) return rc
+	DA(S.st, 1);
+	for (int d = 0; d < 2; d++) { DA(S.n_max[d], N); DA(S.n_usage[d], N); DA(S.n_total[d], N); }
+	DA(S.n_id, N); DA(S.n_res_head, N);
+	DA(S.adj_off, 2*N); DA(S.adj_cap, 2*N); DA(S.adj_len, 2*N); DA(S.adj_live, 2*N); DA(S.adj_arena, S.adj_arena_cap);
+	DA(S.f_ub, F); DA(S.f_speed[0], F); DA(S.f_speed[1], F); DA(S.f_delay, F);
+	DA(S.f_peer[0], F); DA(S.f_peer[1], F); DA(S.f_id, F); DA(S.f_gen, F);
+	DA(S.f_srng, F); DA(S.f_drng, F); DA(S.f_cnext, F); DA(S.f_cprev, F); DA(S.f_pos[0], F); DA(S.f_pos[1], F);
+	DA(S.f_ord, F); DA(S.f_next_free, F); DA(S.f_alive, F); DA(S.f_drain_type, F);
+	const int R = S.cap_ranges;
+	DA(S.r_start, R); DA(S.r_total, R); DA(S.r_len, R); DA(S.r_lenc, R); DA(S.r_last, R);
+	DA(S.r_prod, R); DA(S.r_res, R); DA(S.r_next, R); DA(S.r_prev, R); DA(S.r_cons, R); DA(S.r_next_free, R);
+	const int Q = S.cap_res;
+	DA(S.s_id, Q); DA(S.s_len, Q); DA(S.s_node, Q); DA(S.s_first, Q); DA(S.s_nprod, Q); DA(S.s_ncons, Q); DA(S.s_next, Q);
+	DA(S.q_time, S.ring_cap); DA(S.q_speed, S.ring_cap); DA(S.q_fd, S.ring_cap); DA(S.q_gen, S.ring_cap); DA(S.q_tmin, S.n_ring_tiles);
+	DA(S.l_time, (size_t)S.n_l_tiles*NS_TILE); DA(S.l_seq, (size_t)S.n_l_tiles*NS_TILE); DA(S.l_tmin, S.n_l_tiles);
+	DA(S.u_group, S.cap_users); DA(S.u_next_free, S.cap_users);
+	ns_sc_op *d_ops; int *d_goff; ns_sc_ondone *d_od; uint32_t *d_rids;
+	DA(d_ops, H.n_ops); DA(d_goff, H.n_groups+1); DA(d_od, H.n_ondone); DA(d_rids, H.n_resources);
+	S.ops = d_ops; S.group_off = d_goff; S.ondone = d_od; S.rids = d_rids;
+	DA(S.ord2flow, S.cap_ord);
+	DA(S.b_seq, S.batch_cap); DA(S.b_ref, 8);
+	DA(h.scr.lb_seq, S.n_l); DA(h.scr.lb_ref, S.n_l); DA(h.scr.lb_tmp_seq, S.n_l); DA(h.scr.lb_tmp_ref, S.n_l);
+	if (S.rec_cap) DA(S.rec, S.rec_cap);
+	if (S.tr_cap) DA(S.tr, S.tr_cap);
+	if ((rc = par_alloc(h.par, S, parallel_scratch, [&](void **pp, size_t b){ return dev_alloc(h, pp, b); }))) return rc;
+#undef DA
+
+	// ---- host-side init: sim_create_node (sim.c:113-125), sim_node_new_resource (:129-140),
+	//      sim_node_add_resource (:141-154)
+	SimState st;
+	memset(&st, 0, sizeof st);
+	ns_rand_state g;
+	ns_rand_seed_host(&g, H.seed);
+	u64 draws = 0;
+	std::vector<uint8_t> rec;
+	std::vector<uint32_t> nid(N);
+	std::unordered_set<uint32_t> used;
+	used.reserve((size_t)N*2+16);
+	for (int i = 0; i < N; i++) {
+		uint32_t id;
+		do { id = ns_rand_next_host(&g); draws++; } while (!used.insert(id).second);
+		nid[i] = id;
+		if (o.want_records) host_rec(rec, 0.0, R_NODE_CREATE, id, 1, 0);
+	}
+	std::vector<int> res_head(N, -1);
+	std::vector<uint32_t> s_id; std::vector<long long> s_len; std::vector<int> s_node, s_first, s_next;
+	std::vector<long long> r_start, r_total; std::vector<double> r_len; std::vector<int> r_res;
+	std::vector<uint32_t> rids(H.n_resources);
+	auto store_find = [&](int node, uint32_t rid){ for (int r = res_head[node]; r >= 0; r = s_next[r]) if (s_id[r] == rid) return r; return -1; };
+	auto add_full = [&](int node, uint32_t rid, long long L){
+		int r = (int)s_id.size();
+		s_id.push_back(rid); s_len.push_back(L); s_node.push_back(node); s_next.push_back(res_head[node]); res_head[node] = r;
+		s_first.push_back((int)r_start.size());
+		r_start.push_back(0); r_total.push_back(L); r_len.push_back((double)L); r_res.push_back(r);
+		ns_rand_next_host(&g); draws++;                               // resource_new_range -> skip_list_insert
+	};
+	for (int i = 0; i < H.n_resources; i++) {
+		if (rs[i].owner < 0 || rs[i].owner >= N) return NS_E_BAD_SCENARIO;
+		uint32_t rid = ns_rand_next_host(&g); draws++;
+		while (store_find(rs[i].owner, rid) >= 0) { rid = ns_rand_next_host(&g); draws++; }
+		rids[i] = rid;
+		add_full(rs[i].owner, rid, rs[i].len);
+	}
+	for (int i = 0; i < H.n_copies; i++) {
+		if (cp[i].node < 0 || cp[i].node >= N || cp[i].res < 0 || cp[i].res >= H.n_resources) return NS_E_BAD_SCENARIO;
+		uint32_t rid = rids[cp[i].res];
+		if (store_find(cp[i].node, rid) >= 0) continue;
+		add_full(cp[i].node, rid, rs[cp[i].res].len);
+	}
+	const int nres0 = (int)s_id.size(), nrng0 = (int)r_start.size();
+	if (rec.size() > S.rec_cap && o.want_records) return NS_E_RECORDS_FULL;
+
+	// ---- fill and upload
+	for (int d = 0; d < 2; d++) { if ((rc = fill_f64(S.n_usage[d], N, 0))) return rc; if ((rc = fill_f64(S.n_total[d], N, 0))) return rc; }
+	CK(cudaMemcpy(S.n_max[0], max_up, (size_t)N*8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(S.n_max[1], max_down, (size_t)N*8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(S.n_id, nid.data(), (size_t)N*4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(S.n_res_head, res_head.data(), (size_t)N*4, cudaMemcpyHostToDevice));
+	if ((rc = fill_i32(S.adj_off, 2*N, 0)) || (rc = fill_i32(S.adj_cap, 2*N, 0)) || (rc = fill_i32(S.adj_len, 2*N, 0)) || (rc = fill_i32(S.adj_live, 2*N, 0))) return rc;
+	CK(cudaMemset(S.f_gen, 0, (size_t)F*4));
+	CK(cudaMemset(S.f_alive, 0, F));
+	if ((rc = fill_f64(S.q_time, S.ring_cap, INFINITY)) || (rc = fill_f64(S.q_tmin, S.n_ring_tiles, INFINITY))) return rc;
+	if ((rc = fill_f64(S.l_time, (u64)S.n_l_tiles*NS_TILE, INFINITY)) || (rc = fill_f64(S.l_tmin, S.n_l_tiles, INFINITY))) return rc;
+	if ((rc = fill_i32(S.ord2flow, S.cap_ord, -1))) return rc;
+	if (nres0) {
+		CK(cudaMemcpy(S.s_id, s_id.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.s_len, s_len.data(), (size_t)nres0*8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.s_node, s_node.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.s_first, s_first.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.s_next, s_next.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
+		CK(cudaMemset(S.s_nprod, 0, (size_t)nres0*4)); CK(cudaMemset(S.s_ncons, 0, (size_t)nres0*4));
+		CK(cudaMemcpy(S.r_start, r_start.data(), (size_t)nrng0*8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.r_total, r_total.data(), (size_t)nrng0*8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.r_len, r_len.data(), (size_t)nrng0*8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.r_res, r_res.data(), (size_t)nrng0*4, cudaMemcpyHostToDevice));
+		if ((rc = fill_f64(S.r_lenc, nrng0, 0)) || (rc = fill_f64(S.r_last, nrng0, 0))) return rc;
+		if ((rc = fill_i32(S.r_prod, nrng0, -1)) || (rc = fill_i32(S.r_next, nrng0, -1)) || (rc = fill_i32(S.r_prev, nrng0, -1)) || (rc = fill_i32(S.r_cons, nrng0, -1))) return rc;
+	}
+	CK(cudaMemcpy(d_ops, ops, (size_t)H.n_ops*sizeof *ops, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_goff, goff, (size_t)(H.n_groups+1)*4, cudaMemcpyHostToDevice));
+	if (H.n_ondone) CK(cudaMemcpy(d_od, od, (size_t)H.n_ondone*sizeof *od, cudaMemcpyHostToDevice));
+	if (H.n_resources) CK(cudaMemcpy(d_rids, rids.data(), (size_t)H.n_resources*4, cudaMemcpyHostToDevice));
+	if (!rec.empty()) CK(cudaMemcpy(S.rec, rec.data(), rec.size(), cudaMemcpyHostToDevice));
+
+	memcpy(st.rnd, g.st, sizeof st.rnd); st.rf = g.f; st.rr = g.r;
+	st.free_flow = st.free_range = st.free_user = -1;
+	st.hi_range = nrng0; st.hi_res = nres0;
+	st.rec_len = rec.size();
+	st.cnt[NS_CNT_DRAWS] = draws;
+	st.seed = H.seed;
+	CK(cudaMemcpy(S.st, &st, sizeof st, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+// ---------------------------------------------------------------- C ABI: single simulation
+struct ns_dev {
+	int device = 0, mode = 0;
+	HostSim h;
+	Sim *d_sim = nullptr; SeqScratch *d_scr = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	uint64_t launches = 0;
+	int sm_count = 0;
+	u64 *d_hash = nullptr;
+};
+
+extern "C" int ns_dev_count(void){
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+static int read_state(ns_dev *d, SimState *st){
+	CK(cudaMemcpyAsync(st, d->h.S.st, sizeof *st, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	return 0;
+}
+
+extern "C" int ns_dev_create(ns_dev **out, const void *scenario, size_t len, const ns_dev_opts *opts){
+	if (!out || !scenario) return NS_E_ARG;
+	*out = nullptr;
+	ns_dev_opts o;
+	memset(&o, 0, sizeof o);
+	if (opts) o = *opts;
+	if (ns_dev_count() <= o.device) return NS_E_NO_DEVICE;
+	CK(cudaSetDevice(o.device));
+	ns_dev *d = new ns_dev();
+	d->device = o.device; d->mode = o.mode;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, o.device));
+	d->sm_count = prop.multiProcessorCount;
+	int rc = build_sim(d->h, scenario, len, o, o.mode != NS_MODE_SEQ);
+	if (rc) { free_sim(d->h); delete d; return rc; }
+	CK(cudaStreamCreate(&d->stream));
+	CK(cudaEventCreate(&d->e0)); CK(cudaEventCreate(&d->e1));
+	CK(cudaMalloc(&d->d_sim, sizeof(Sim))); CK(cudaMalloc(&d->d_scr, sizeof(SeqScratch))); CK(cudaMalloc(&d->d_hash, 8));
+	CK(cudaMemcpy(d->d_sim, &d->h.S, sizeof(Sim), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d->d_scr, &d->h.scr, sizeof(SeqScratch), cudaMemcpyHostToDevice));
+	CK(cudaDeviceSynchronize());
+	// module init: group 0 of the script (first sim_establish_flow calls, scheduled USER events)
+	if (d->mode == NS_MODE_SEQ) {
+		k_init_groups<<<1, 32, 0, d->stream>>>(d->d_sim, 1);
+		d->launches++;
+	} else {
+		rc = par_init_group0(d->h.S, d->d_sim, d->h.par, d->sm_count, d->stream, &d->launches);
+		if (rc) { ns_dev_destroy(d); return rc; }
+	}
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(d->stream));
+	*out = d;
+	return 0;
+}
+
+extern "C" int ns_dev_run(ns_dev *d, uint64_t max_events, float *device_ms){
+	if (!d) return NS_E_ARG;
+	CK(cudaSetDevice(d->device));
+	CK(cudaMemcpyAsync(&d->h.S.st->max_events, &max_events, 8, cudaMemcpyHostToDevice, d->stream));
+	CK(cudaEventRecord(d->e0, d->stream));
+	if (d->mode == NS_MODE_SEQ) {
+		k_run_seq<<<1, 32, 0, d->stream>>>(d->d_sim, d->d_scr, 1);
+		d->launches++;
+		CK(cudaGetLastError());
+	} else {
+		int rc = par_run(d->h.S, d->d_sim, d->d_scr, d->h.par, d->sm_count, d->stream, &d->launches);
+		if (rc) return rc;
+	}
+	CK(cudaEventRecord(d->e1, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	if (device_ms) CK(cudaEventElapsedTime(device_ms, d->e0, d->e1));
+	return ns_dev_status(d);
+}
+
+extern "C" int ns_dev_status(ns_dev *d){
+	if (!d) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	return st.status;
+}
+extern "C" double ns_dev_now(ns_dev *d){
+	if (!d) return 0;
+	SimState st; if (read_state(d, &st)) return 0;
+	return st.now;
+}
+extern "C" int ns_dev_counters(ns_dev *d, uint64_t out[NS_CNT_COUNT]){
+	if (!d || !out) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	for (int i = 0; i < NS_CNT_COUNT; i++) out[i] = st.cnt[i];
+	out[NS_CNT_SEQ] = st.tail;
+	out[NS_CNT_DRAWS] = st.cnt[NS_CNT_DRAWS]+st.burns;
+	return 0;
+}
+extern "C" int ns_dev_records(ns_dev *d, void *dst, size_t cap, size_t offset, size_t *len, size_t *total){
+	if (!d) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	if (total) *total = st.rec_len;
+	size_t n = 0;
+	if (offset < st.rec_len) n = std::min<size_t>(cap, st.rec_len-offset);
+	if (n && dst) CK(cudaMemcpy(dst, d->h.S.rec+offset, n, cudaMemcpyDeviceToHost));
+	if (len) *len = n;
+	return 0;
+}
+static int stream_hash(ns_dev *d, u64 rec_len, u64 *out){
+	CK(cudaMemsetAsync(d->d_hash, 0, 8, d->stream));
+	if (rec_len) { k_stream_hash<<<296, 256, 0, d->stream>>>(d->h.S.rec, rec_len, d->d_hash); d->launches++; }
+	CK(cudaMemcpyAsync(out, d->d_hash, 8, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	*out = ns_mix64(*out ^ rec_len);
+	return 0;
+}
+extern "C" int ns_dev_digest(ns_dev *d, ns_digest *out){
+	if (!d || !out) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	out->seed = st.seed; out->events = st.cnt[NS_CNT_EVENTS]; out->solves = st.cnt[NS_CNT_SOLVES];
+	out->record_bytes = st.rec_len; out->t_end = st.now; out->status = st.status;
+	return stream_hash(d, st.rec_len, (u64 *)&out->record_fnv1a);
+}
+extern "C" int ns_dev_trace(ns_dev *d, ns_trace_row32 *dst, size_t cap_rows, size_t *rows){
+	if (!d) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	size_t n = std::min<size_t>(cap_rows, st.tr_len);
+	if (n && dst) CK(cudaMemcpy(dst, d->h.S.tr, n*sizeof *dst, cudaMemcpyDeviceToHost));
+	if (rows) *rows = st.tr_len;
+	return 0;
+}
+extern "C" int ns_dev_flow_state(ns_dev *d, double *out4, size_t max_flows, size_t *n){
+	if (!d || !out4) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	size_t k = std::min<size_t>(max_flows, (size_t)st.n_ord);
+	if (k) {
+		double *tmp; CK(cudaMalloc(&tmp, k*32));
+		k_flow_state<<<(unsigned)((k+255)/256), 256, 0, d->stream>>>(d->d_sim, tmp, (int)k); d->launches++;
+		CK(cudaMemcpyAsync(out4, tmp, k*32, cudaMemcpyDeviceToHost, d->stream));
+		CK(cudaStreamSynchronize(d->stream));
+		cudaFree(tmp);
+	}
+	if (n) *n = k;
+	return 0;
+}
+extern "C" int ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size_t *n){
+	if (!d || !out4) return NS_E_ARG;
+	size_t k = std::min<size_t>(max_nodes, (size_t)d->h.S.n_nodes);
+	if (k) {
+		double *tmp; CK(cudaMalloc(&tmp, k*32));
+		k_node_state<<<(unsigned)((k+255)/256), 256, 0, d->stream>>>(d->d_sim, tmp, (int)k); d->launches++;
+		CK(cudaMemcpyAsync(out4, tmp, k*32, cudaMemcpyDeviceToHost, d->stream));
+		CK(cudaStreamSynchronize(d->stream));
+		cudaFree(tmp);
+	}
+	if (n) *n = k;
+	return 0;
+}
+extern "C" uint64_t ns_dev_launches(ns_dev *d){ return d ? d->launches : 0; }
+extern "C" void ns_dev_destroy(ns_dev *d){
+	if (!d) return;
+	cudaSetDevice(d->device);
+	free_sim(d->h);
+	if (d->d_sim) cudaFree(d->d_sim);
+	if (d->d_scr) cudaFree(d->d_scr);
+	if (d->d_hash) cudaFree(d->d_hash);
+	if (d->e0) cudaEventDestroy(d->e0);
+	if (d->e1) cudaEventDestroy(d->e1);
+	if (d->stream) cudaStreamDestroy(d->stream);
+	delete d;
+}
+
+// ---------------------------------------------------------------- C ABI: replica ensembles
+struct ns_ens {
+	int device = 0, n = 0;
+	std::vector<HostSim> sims;
+	Sim *d_sims = nullptr; SeqScratch *d_scr = nullptr;
+	cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+	uint64_t launches = 0;
+	u64 *d_hash = nullptr;
+};
+
+extern "C" int ns_ens_create(ns_ens **out, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts *opts){
+	if (!out || !scenarios || !lens || n <= 0) return NS_E_ARG;
+	*out = nullptr;
+	ns_dev_opts o;
+	memset(&o, 0, sizeof o);
+	if (opts) o = *opts;
+	if (ns_dev_count() <= o.device) return NS_E_NO_DEVICE;
+	CK(cudaSetDevice(o.device));
+	ns_ens *e = new ns_ens();
+	e->device = o.device; e->n = n;
+	e->sims.resize(n);
+	std::vector<Sim> hs(n); std::vector<SeqScratch> hscr(n);
+	for (int i = 0; i < n; i++) {
+		int rc = build_sim(e->sims[i], scenarios[i], lens[i], o, false);
+		if (rc) { for (auto &h : e->sims) free_sim(h); delete e; return rc; }
+		hs[i] = e->sims[i].S; hscr[i] = e->sims[i].scr;
+	}
+	CK(cudaStreamCreate(&e->stream));
+	CK(cudaEventCreate(&e->e0)); CK(cudaEventCreate(&e->e1));
+	CK(cudaMalloc(&e->d_sims, sizeof(Sim)*n)); CK(cudaMalloc(&e->d_scr, sizeof(SeqScratch)*n)); CK(cudaMalloc(&e->d_hash, 8));
+	CK(cudaMemcpy(e->d_sims, hs.data(), sizeof(Sim)*n, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->d_scr, hscr.data(), sizeof(SeqScratch)*n, cudaMemcpyHostToDevice));
+	CK(cudaDeviceSynchronize());
+	k_init_groups<<<n, 32, 0, e->stream>>>(e->d_sims, n);
+	e->launches++;
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(e->stream));
+	*out = e;
+	return 0;
+}
+extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms){
+	if (!e) return NS_E_ARG;
+	CK(cudaSetDevice(e->device));
+	for (int i = 0; i < e->n; i++)
+		CK(cudaMemcpyAsync(&e->sims[i].S.st->max_events, &max_events_each, 8, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaEventRecord(e->e0, e->stream));
+	k_run_seq<<<e->n, 32, 0, e->stream>>>(e->d_sims, e->d_scr, e->n);
+	e->launches++;
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(e->e1, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	if (device_ms) CK(cudaEventElapsedTime(device_ms, e->e0, e->e1));
+	return 0;
+}
+extern "C" int ns_ens_digests(ns_ens *e, ns_digest *out, int n){
+	if (!e || !out) return NS_E_ARG;
+	for (int i = 0; i < n && i < e->n; i++) {
+		SimState st;
+		CK(cudaMemcpy(&st, e->sims[i].S.st, sizeof st, cudaMemcpyDeviceToHost));
+		out[i].seed = st.seed; out[i].events = st.cnt[NS_CNT_EVENTS]; out[i].solves = st.cnt[NS_CNT_SOLVES];
+		out[i].record_bytes = st.rec_len; out[i].t_end = st.now; out[i].status = st.status;
+		u64 hsum = 0;
+		CK(cudaMemsetAsync(e->d_hash, 0, 8, e->stream));
+		if (st.rec_len) { k_stream_hash<<<64, 256, 0, e->stream>>>(e->sims[i].S.rec, st.rec_len, e->d_hash); e->launches++; }
+		CK(cudaMemcpyAsync(&hsum, e->d_hash, 8, cudaMemcpyDeviceToHost, e->stream));
+		CK(cudaStreamSynchronize(e->stream));
+		out[i].record_fnv1a = ns_mix64(hsum ^ st.rec_len);
+	}
+	return 0;
+}
+extern "C" uint64_t ns_ens_launches(ns_ens *e){ return e ? e->launches : 0; }
+extern "C" void ns_ens_destroy(ns_ens *e){
+	if (!e) return;
+	cudaSetDevice(e->device);
+	for (auto &h : e->sims) free_sim(h);
+	if (e->d_sims) cudaFree(e->d_sims);
+	if (e->d_scr) cudaFree(e->d_scr);
+	if (e->d_hash) cudaFree(e->d_hash);
+	if (e->e0) cudaEventDestroy(e->e0);
+	if (e->e1) cudaEventDestroy(e->e1);
+	if (e->stream) cudaStreamDestroy(e->stream);
+	delete e;
+}
+
+// ---------------------------------------------------------------- host helpers
+extern "C" void ns_rand_seed_host(ns_rand_state *g, uint32_t seed){
+	int32_t word = seed ? (int32_t)seed : 1;
+	g->st[0] = word;
+	for (int i = 1; i < 31; i++) {
+		long hi = word/127773, lo = word%127773;
+		long w = 16807*lo-2836*hi;
+		if (w < 0) w += 2147483647;
+		word = (int32_t)w;
+		g->st[i] = word;
+	}
+	g->f = 3; g->r = 0;
+	for (int i = 0; i < 310; i++) ns_rand_step(g->st, g->f, g->r);
+}
+extern "C" uint32_t ns_rand_next_host(ns_rand_state *g){ return ns_rand_step(g->st, g->f, g->r); }
+extern "C" void ns_rand_jump_host(ns_rand_state *g, uint64_t n){ ns_rand_jump(g->st, g->f, g->r, n); }
+
+extern "C" const char *ns_strerror(int err){
+	switch (err) {
+	case NS_OK: return "ok";
+	case NS_E_BAD_SCENARIO: return "malformed scenario script";
+	case NS_E_BACK_IN_TIME: return "event added back in time (reference aborts, event.h:60-64)";
+	case NS_E_NAN_TIME: return "event added at NaN (reference aborts, event.h:67-70)";
+	case NS_E_NULL_RANGE: return "flow source range missing (reference dereferences NULL)";
+	case NS_E_NO_PRODUCER: return "throttle on a range without producer (flow.c:411)";
+	case NS_E_RING_FULL: return "pending-event ring full";
+	case NS_E_TABLE_FULL: return "device table capacity exhausted";
+	case NS_E_RECORDS_FULL: return "record buffer full";
+	case NS_E_NO_DEVICE: return "no usable CUDA device";
+	case NS_E_ARG: return "bad argument";
+	case NS_E_BATCH_FULL: return "equal-timestamp batch exceeds scratch capacity";
+	default: return err > 0 ? "CUDA error" : "unknown error";
+	}
+}

@@ -1,0 +1,763 @@
+// ns_model.cuh — the flow-level bandwidth model as warp-cooperative device functions.
+//
+// Execution model: every function here is called by ALL 32 lanes of one warp with identical
+// (warp-uniform) arguments.  Scalar state is loaded redundantly (one broadcast transaction), control
+// flow is uniform, stores are issued by lane 0, and the O(degree) loops of a full spread
+// (flow.c:127-200) are strided over the lanes.  Floating-point results are bit-identical to the
+// sequential reference: every sum that the reference accumulates in list order (e, new_use) is
+// accumulated in the same order from lane-shuffled terms; nvcc is run with -fmad=false.
+//
+// Each function cites the reference lines it re-implements (paths relative to yshui/netsim).
+#pragma once
+#include "ns_sim.cuh"
+
+struct Ctx {
+	const Sim *S; SimState *st; int lane;
+	double now;
+	u64 head, tail;        // ring window, cached in registers (flushed by ctx_flush)
+	u64 burns, rec_len, tr_len;
+	int par;               // 1 inside the grid-parallel path (atomics on shared scalars)
+};
+
+#define L0 if (c.lane == 0)
+
+__device__ __forceinline__ void ctx_load(Ctx &c, const Sim *S, int lane){
+	c.S = S; c.st = S->st; c.lane = lane; c.par = 0;
+	c.now = c.st->now; c.head = c.st->head; c.tail = c.st->tail; c.burns = c.st->burns;
+	c.rec_len = c.st->rec_len; c.tr_len = c.st->tr_len;
+}
+__device__ __forceinline__ void ctx_flush(Ctx &c){
+	L0 {
+		c.st->now = c.now; c.st->head = c.head; c.st->tail = c.tail; c.st->burns = c.burns;
+		c.st->rec_len = c.rec_len; c.st->tr_len = c.tr_len;
+	}
+	__syncwarp();
+}
+__device__ __forceinline__ void set_status(Ctx &c, int s){
+	L0 { if (c.st->status == 0) c.st->status = s; }
+}
+__device__ __forceinline__ void cnt_add(Ctx &c, int idx, u64 n){
+	L0 { c.st->cnt[idx] += n; }
+}
+__device__ __forceinline__ void tmin_lower(double *p, double t){
+	// times are >= 0, so the IEEE bit pattern orders like the value
+	atomicMin((u64 *)p, (u64)__double_as_longlong(t));
+}
+
+// ---------------------------------------------------------------- records (record.c:27-117)
+__device__ __forceinline__ int rec_encode(uint8_t *b, double now, uint8_t minor, uint32_t id, int bytes, uint32_t ival, double dval){
+	int n = 0;
+	b[n++] = 0; b[n++] = minor;
+	b[n++] = id >> 24; b[n++] = id >> 16; b[n++] = id >> 8; b[n++] = id;
+	uint32_t t = (uint32_t)(int)now;                                   // record.c:66
+	b[n++] = t >> 24; b[n++] = t >> 16; b[n++] = t >> 8; b[n++] = t;
+	uint16_t ut = (uint16_t)(int)((now-(double)((int)now))*1000);      // record.c:69
+	b[n++] = ut >> 8; b[n++] = ut;
+	b[n++] = (uint8_t)(int8_t)bytes;
+	if (bytes == 1) b[n++] = (uint8_t)ival;
+	else if (bytes == 4) { b[n++] = ival >> 24; b[n++] = ival >> 16; b[n++] = ival >> 8; b[n++] = ival; }
+	else {                                                             // record.c:98-106
+		double tmp = dval;
+		uint32_t ip = (uint32_t)(int)tmp;
+		b[n++] = ip >> 24; b[n++] = ip >> 16; b[n++] = ip >> 8; b[n++] = ip;
+		tmp = tmp-(double)((int)tmp);
+		uint16_t fp = (uint16_t)(int)(tmp*1000);
+		b[n++] = fp >> 8; b[n++] = fp;
+	}
+	return n;
+}
+__device__ __forceinline__ void write_record(Ctx &c, uint8_t minor, uint32_t id, int bytes, uint32_t ival, double dval){
+	const Sim &S = *c.S;
+	if (!S.want_rec) return;
+	int n = 13+(bytes == 1 ? 1 : bytes == 4 ? 4 : 6);
+	if (c.rec_len+n > S.rec_cap) { set_status(c, NS_E_RECORDS_FULL); return; }
+	L0 {
+		uint8_t b[19];
+		rec_encode(b, c.now, minor, id, bytes, ival, dval);
+		uint8_t *dst = S.rec+c.rec_len;
+		for (int i = 0; i < n; i++) dst[i] = b[i];
+	}
+	c.rec_len += n;
+}
+__device__ __forceinline__ void write_usage(Ctx &c, int dir, int n, double usage){  // record_wrapper.h:6-9
+	write_record(c, R_USAGE|dir, c.S->n_id[n], -1, 0, usage);
+}
+__device__ __forceinline__ void trace_row(Ctx &c, uint32_t type, uint32_t ord, double v0, double v1){
+	const Sim &S = *c.S;
+	if (!S.want_tr) return;
+	if (c.tr_len >= S.tr_cap) return;
+	L0 { ns_trace_row32 r; r.type = type; r.ord = ord; r.time = c.now; r.v0 = v0; r.v1 = v1; S.tr[c.tr_len] = r; }
+	c.tr_len++;
+}
+
+// ---------------------------------------------------------------- event store
+// event_add's time checks, event.h:58-70.  Returns false where the reference would abort().
+__device__ __forceinline__ bool ev_time_ok(Ctx &c, double &t){
+	if (t < c.now) {
+		if (t < c.now-NS_EPS) { set_status(c, NS_E_BACK_IN_TIME); return false; }
+		t = c.now;
+	}
+	if (isnan(t)) { set_status(c, NS_E_NAN_TIME); return false; }
+	return true;
+}
+// take n consecutive sequence numbers (each successful event_add: one skip-list insert, one
+// random() burned, skiplist.h:34-40,83)
+__device__ __forceinline__ u64 seq_reserve(Ctx &c, u64 n){
+	u64 s = c.tail;
+	if (c.tail+n-c.head > c.S->ring_cap) { set_status(c, NS_E_RING_FULL); return s; }
+	c.tail += n; c.burns += n;
+	return s;
+}
+__device__ __forceinline__ void ring_put(Ctx &c, u64 seq, double t, double speed, int f, int dir){
+	const Sim &S = *c.S;
+	u64 slot = seq & (S.ring_cap-1);
+	S.q_time[slot] = t; S.q_speed[slot] = speed; S.q_fd[slot] = f*2+dir; S.q_gen[slot] = S.f_gen[f];
+	tmin_lower(&S.q_tmin[slot >> NS_TILE_SHIFT], t);
+}
+__device__ __forceinline__ void l_put(Ctx &c, int slot, u64 seq, double t){
+	const Sim &S = *c.S;
+	S.l_time[slot] = t; S.l_seq[slot] = seq;
+	tmin_lower(&S.l_tmin[slot >> NS_TILE_SHIFT], t);
+}
+// is_later_than, event.h:82-88 (inactive events are stored as time == +inf)
+__device__ __forceinline__ bool is_later_than(double time, double etime){
+	if (etime == NS_INF) return false;
+	return time > etime+NS_EPS;
+}
+
+// queue_speed_event, flow.c:16-29
+__device__ __forceinline__ void queue_speed_event(Ctx &c, int f, int dir, double speed){
+	double t = c.now+c.S->f_delay[f];
+	if (!ev_time_ok(c, t)) return;
+	u64 seq = seq_reserve(c, 1);
+	if (c.st->status) return;
+	L0 ring_put(c, seq, t, speed, f, dir);
+}
+
+// get_share, flow.h:37-41
+__device__ __forceinline__ double get_share(const Sim &S, int f, int dir){
+	int n = S.f_peer[dir][f];
+	double total = S.n_total[dir][n], mx = S.n_max[dir][n];
+	double ub = S.f_ub[f];
+	return total > mx ? ub*mx/total : ub;
+}
+
+// ---------------------------------------------------------------- ranges
+// _range_update, range.h:91-118 (Kahan-compensated len += speed*dt); single-thread semantics,
+// callers guard the stores.
+__device__ __forceinline__ void range_update_1(const Sim &S, int r, double now){
+	double last = S.r_last[r];
+	if (now == last) return;
+	int p = S.r_prod[r];
+	if (p < 0) { S.r_last[r] = now; return; }
+	double len = S.r_len[r], lenc = S.r_lenc[r];
+	double delta = S.f_speed[1][p]*(now-last), t;
+	delta = delta-lenc;
+	t = delta+len;
+	S.r_lenc[r] = (t-len)-delta;
+	S.r_len[r] = t;
+	S.r_last[r] = now;
+}
+// flow_range_update, range.h:120-125
+__device__ __forceinline__ void flow_range_update(Ctx &c, int f){
+	if (f < 0) return;
+	const Sim &S = *c.S;
+	int sr = S.f_srng[f], dr = S.f_drng[f];
+	if (sr < 0 || dr < 0) { set_status(c, NS_E_NULL_RANGE); return; }
+	L0 { range_update_1(S, sr, c.now); range_update_1(S, dr, c.now); }
+	__syncwarp();
+}
+
+// range_calc_and_requeue_events, range.c:16-79, split into a per-thread "plan" (all arithmetic and
+// range updates, no sequence numbers) and a "commit" so that the victims of one full spread can be
+// re-timed by different lanes while their event_add order stays the list order.
+struct Retime { double drain_t, done_t; int add_drain, add_done; };
+
+__device__ __forceinline__ void retime_plan_1(const Sim &S, SimState *st, int f, double now, Retime &p){
+	p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
+	S.l_time[2*f] = NS_INF;                                           // range.c:19-20 event_remove
+	S.l_time[2*f+1] = NS_INF;
+	int sr = S.f_srng[f], dr = S.f_drng[f];
+	if (sr < 0 || dr < 0) { if (st->status == 0) st->status = NS_E_NULL_RANGE; return; }
+	range_update_1(S, sr, now);                                       // :21
+	range_update_1(S, dr, now);
+	double fbw = S.f_speed[1][f];
+	if (fbw < NS_EPS) return;                                         // :26-27
+	int prod = S.r_prod[sr];
+	double sgrow = prod >= 0 ? S.f_speed[1][prod] : 0;                // :33
+	double slen = S.r_len[sr], dlen = S.r_len[dr];
+	long long dstart = S.r_start[dr], sstart = S.r_start[sr];
+	double drng_start = (double)dstart+dlen-(double)sstart;           // :36
+	double drain_time = (slen-drng_start)/(fbw-sgrow);                // :38
+	double drain_active = NS_INF;                                     // time of f->drain if active
+	bool bad = false;
+	if (prod < 0) {                                                   // :40-44
+		double t = now+(slen-drng_start)/fbw;
+		S.f_drain_type[f] = EV_FLOW_DRAIN;
+		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+		if (isnan(t)) bad = true;
+		if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
+	} else if (!is_later_than(drain_time+now, S.l_time[2*prod]) && sgrow < fbw) {   // :45-61
+		S.f_drain_type[f] = EV_FLOW_SPEED_THROTTLE;
+		double d0 = slen-drng_start;
+		if (d0 > -NS_EPS && d0 < NS_EPS) {
+			double d1 = sgrow-fbw;
+			if (!(d1 > -NS_EPS && d1 < NS_EPS)) { p.add_drain = 1; p.drain_t = now; drain_active = now; }
+		} else {
+			double t = now+drain_time;
+			if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+			if (isnan(t)) bad = true;
+			if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
+		}
+	}
+	if (bad) { if (st->status == 0) st->status = isnan(drain_time) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; return; }
+	int nx = S.r_next[dr];                                            // :64-69 (int npos)
+	int npos = nx >= 0 ? (int)S.r_start[nx] : (int)S.r_total[dr];
+	double done_time = ((double)(u64)((u64)(long long)npos-(u64)dstart)-dlen)/fbw;  // :70
+	if (!is_later_than(now+done_time, drain_active)) {                // :73-78
+		double t = now+done_time;
+		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+		if (isnan(t)) bad = true;
+		if (bad) { if (st->status == 0) st->status = isnan(t) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; return; }
+		p.add_done = 1; p.done_t = t;
+	}
+}
+// sequence numbers: drain first, then done; a drain superseded by done keeps its burned number.
+__device__ __forceinline__ void retime_commit_1(Ctx &c, int f, const Retime &p, u64 seq){
+	if (p.add_done) l_put(c, 2*f, seq+p.add_drain, p.done_t);
+	else if (p.add_drain) l_put(c, 2*f+1, seq, p.drain_t);
+}
+__device__ __forceinline__ void range_calc_and_requeue_events(Ctx &c, int f){
+	if (f < 0) return;
+	Retime p;
+	p.add_drain = p.add_done = 0;
+	L0 retime_plan_1(*c.S, c.st, f, c.now, p);
+	p.add_drain = __shfl_sync(FULLMASK, p.add_drain, 0);
+	p.add_done = __shfl_sync(FULLMASK, p.add_done, 0);
+	int n = p.add_drain+p.add_done;
+	if (n) {
+		u64 seq = seq_reserve(c, n);
+		L0 { if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) retime_commit_1(c, f, p, seq); }
+	}
+	__syncwarp();
+}
+// range_update_consumer_events, range.h:65-69
+__device__ __forceinline__ void range_update_consumer_events(Ctx &c, int r){
+	for (int f = c.S->r_cons[r]; f >= 0; f = c.S->f_cnext[f])
+		range_calc_and_requeue_events(c, f);
+}
+
+// ---------------------------------------------------------------- bwspread, flow.c:35-205
+__device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
+	const Sim &S = *c.S;
+	const int lane = c.lane;
+	cnt_add(c, NS_CNT_SOLVES, 1);
+	double fs = S.f_speed[dir][f];
+	if (close) amount = -fs;                                          // :51-54
+	const int n = S.f_peer[dir][f];
+	const double total = S.n_total[dir][n], mx = S.n_max[dir][n];     // :59
+	const double used = S.n_usage[dir][n];
+	const double ub = S.f_ub[f];
+	const double share = total > mx ? ub*mx/total : ub;               // :61
+	if (amount > NS_EPS && fs+amount > share) {                       // :64
+		if (fs > share) { queue_speed_event(c, f, !dir, fs); return; } // :66-74
+		queue_speed_event(c, f, !dir, share);                         // :75
+		amount = share-fs;
+	}
+	if (amount > -NS_EPS && amount < NS_EPS) return;                  // :80-83
+	fs += amount;                                                     // :85
+	L0 S.f_speed[dir][f] = fs;
+	if (amount < NS_EPS && amount > -64) {                            // :86-91
+		double u = used+amount;
+		L0 S.n_usage[dir][n] = u;
+		write_usage(c, dir, n, u);
+		__syncwarp();
+		return;
+	}
+	if (total < mx+NS_EPS) {                                          // :94-109
+		if (!close || total+ub < mx+NS_EPS) {
+			double u = used+amount;
+			L0 S.n_usage[dir][n] = u;
+			write_usage(c, dir, n, u);
+			__syncwarp();
+			return;
+		}
+	}
+	double spread_amount = amount;                                    // :112
+	if (amount > -NS_EPS) {
+		if (used+amount < mx+NS_EPS) {                                // :114-119
+			double u = used+amount;
+			L0 S.n_usage[dir][n] = u;
+			write_usage(c, dir, n, u);
+			__syncwarp();
+			return;
+		}
+		spread_amount = amount-mx+used;                               // :122
+	}
+	// ---- full spread over the node's flows, newest first (list order of flow.c:129,157)
+	__syncwarp();
+	const int g = n*2+dir;
+	const int off = S.adj_off[g], len = S.adj_len[g];
+	cnt_add(c, NS_CNT_FULL_SPREADS, 1);
+	cnt_add(c, NS_CNT_FLOW_VISITS, 2ull*(u64)S.adj_live[g]);
+	const bool dec = amount < NS_EPS, inc = !dec && amount > NS_EPS;
+	double e = 0;                                                     // :128-145
+	for (int base = len-1; base >= 0; base -= 32) {
+		int p = base-lane;
+		int nf = p >= 0 ? S.adj_arena[off+p] : -1;
+		double term = 0.0;
+		if (nf >= 0 && nf != f) {
+			double sp = S.f_speed[dir][nf];
+			if (dec) { double ls = get_share(S, nf, !dir); if (sp < ls) term = ls-sp; }
+			else if (inc) { double ls = S.f_ub[nf]*mx/total; if (sp > ls) term = sp-ls; }
+		}
+		#pragma unroll
+		for (int l = 0; l < 32; l++) e += __shfl_sync(FULLMASK, term, l);
+	}
+	if (dec && -amount > e) amount = -e;                              // :149-154
+	const bool dec2 = amount < NS_EPS, inc2 = !dec2 && amount > NS_EPS;
+	double new_use = 0;                                               // :156-200
+	for (int base = len-1; base >= 0; base -= 32) {
+		int p = base-lane;
+		int nf = p >= 0 ? S.adj_arena[off+p] : -1;
+		double val = 0.0, emit_speed = 0;
+		int adj = 0;
+		Retime rp; rp.add_drain = rp.add_done = 0;
+		if (nf == f) val = fs;
+		else if (nf >= 0) {
+			double sp = S.f_speed[dir][nf];
+			val = sp;
+			if (dec2) {
+				double ls = get_share(S, nf, !dir);
+				if (sp < ls) {
+					double delta = ls-sp;
+					double new_speed = sp-amount*delta/e;             // :171
+					if (dir == SND) { S.f_speed[dir][nf] = new_speed; val = new_speed; }   // :172-176
+					adj = 1; emit_speed = new_speed;                  // :178
+				}
+			} else if (inc2) {
+				double ls = S.f_ub[nf]*mx/total;
+				if (sp > ls) {
+					double delta = sp-ls;
+					double ns = sp-spread_amount*delta/e;             // :187
+					S.f_speed[dir][nf] = ns; val = ns;
+					adj = 1; emit_speed = ns;                         // :189
+				}
+			}
+		}
+		// inserts of this chunk in list order: [speed event][drain][done] per adjusted flow
+		double et = 0; int ok = 0;
+		if (adj) {
+			et = c.now+S.f_delay[nf];
+			ok = 1;
+			if (et < c.now) { if (et < c.now-NS_EPS) ok = 0; else et = c.now; }
+			if (isnan(et)) ok = 0;
+			if (!ok) { if (c.st->status == 0) c.st->status = isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; }
+			if (dir == RCV && inc2) retime_plan_1(S, c.st, nf, c.now, rp);   // :193-194
+		}
+		int k = ok+rp.add_drain+rp.add_done;
+		int incl = k;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+		int tot = __shfl_sync(FULLMASK, incl, 31);
+		if (tot) {
+			u64 seq0 = seq_reserve(c, tot);
+			if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) {
+				u64 seq = seq0+(u64)(incl-k);
+				if (ok) { ring_put(c, seq, et, emit_speed, nf, !dir); seq++; }
+				if (adj) retime_commit_1(c, nf, rp, seq);
+			}
+		}
+		#pragma unroll
+		for (int l = 0; l < 32; l++) new_use += __shfl_sync(FULLMASK, val, l);   // :199
+	}
+	L0 S.n_usage[dir][n] = new_use;                                   // :201-202
+	write_usage(c, dir, n, new_use);
+	__syncwarp();
+}
+
+// ---------------------------------------------------------------- adjacency arrays (node->conns[dir])
+// list_add at head (flow.c:311-312) == append; list_del (flow.c:251-252) == tombstone.
+__device__ void adj_append(Ctx &c, int g, int f, int dir){
+	const Sim &S = *c.S;
+	int off = S.adj_off[g], cap = S.adj_cap[g], len = S.adj_len[g], live = S.adj_live[g];
+	if (len == cap) {
+		if (live*2 <= cap && cap > 0) {
+			// compact in place (drop tombstones, keep order)
+			L0 {
+				int w = 0;
+				for (int p = 0; p < len; p++) {
+					int x = S.adj_arena[off+p];
+					if (x >= 0) { S.adj_arena[off+w] = x; S.f_pos[dir][x] = w; w++; }
+				}
+				S.adj_len[g] = w;
+			}
+			__syncwarp();
+			len = live;
+		} else {
+			int ncap = cap ? cap*2 : 4;
+			int top = c.st->adj_top;
+			if (top+ncap > S.adj_arena_cap) { set_status(c, NS_E_TABLE_FULL); return; }
+			__syncwarp();
+			// move live entries to the new block, lanes strided; positions recomputed serially
+			L0 {
+				int w = 0;
+				for (int p = 0; p < len; p++) {
+					int x = S.adj_arena[off+p];
+					if (x >= 0) { S.adj_arena[top+w] = x; S.f_pos[dir][x] = w; w++; }
+				}
+				S.adj_off[g] = top; S.adj_cap[g] = ncap; S.adj_len[g] = w;
+				c.st->adj_top = top+ncap;
+			}
+			__syncwarp();
+			off = top; len = live;
+		}
+	}
+	L0 {
+		S.adj_arena[off+len] = f; S.f_pos[dir][f] = len;
+		S.adj_len[g] = len+1; S.adj_live[g] = live+1;
+	}
+	__syncwarp();
+}
+__device__ __forceinline__ void adj_remove(Ctx &c, int g, int f, int dir){
+	const Sim &S = *c.S;
+	L0 {
+		int off = S.adj_off[g], pos = S.f_pos[dir][f];
+		S.adj_arena[off+pos] = -1;
+		S.adj_live[g] -= 1;
+		int len = S.adj_len[g];
+		while (len > 0 && S.adj_arena[off+len-1] < 0) len--;      // trim trailing tombstones
+		S.adj_len[g] = len;
+	}
+	__syncwarp();
+}
+
+// ---------------------------------------------------------------- random draws (sim.c:117, flow.c:327)
+__device__ __forceinline__ uint32_t draw_random(Ctx &c){
+	uint32_t v = 0;
+	L0 {
+		SimState *st = c.st;
+		int32_t f = st->rf, r = st->rr;
+		if (c.burns) ns_rand_jump(st->rnd, f, r, c.burns);
+		v = ns_rand_step(st->rnd, f, r);
+		st->rf = f; st->rr = r;
+		st->cnt[NS_CNT_DRAWS] += c.burns+1;
+	}
+	c.burns = 0;
+	return __shfl_sync(FULLMASK, v, 0);
+}
+
+// ---------------------------------------------------------------- resources and ranges
+__device__ __forceinline__ int store_get(const Sim &S, int node, uint32_t rid){      // store.h:5-10
+	for (int r = S.n_res_head[node]; r >= 0; r = S.s_next[r])
+		if (S.s_id[r] == rid) return r;
+	return -1;
+}
+__device__ int resource_new(Ctx &c, int node, uint32_t rid, long long len){          // data.h:241-249, store.h:25-35
+	const Sim &S = *c.S;
+	int i = c.st->hi_res;
+	if (i >= S.cap_res) { set_status(c, NS_E_TABLE_FULL); return -1; }
+	__syncwarp();
+	L0 {
+		S.s_id[i] = rid; S.s_len[i] = len; S.s_node[i] = node; S.s_first[i] = -1;
+		S.s_nprod[i] = 0; S.s_ncons[i] = 0;
+		S.s_next[i] = S.n_res_head[node]; S.n_res_head[node] = i;
+		c.st->hi_res = i+1;
+	}
+	__syncwarp();
+	return i;
+}
+// range_get, range.h:30-41 with range_include_cmp :10-20 (key is an int)
+__device__ int range_get(const Sim &S, int res, int start){
+	int r = S.s_first[res];
+	for (; r >= 0; r = S.r_next[r]) {
+		long long rs = S.r_start[r];
+		int cmp;
+		if (rs <= (long long)start) cmp = ((double)rs+S.r_len[r] >= (double)start) ? 0 : -1;
+		else cmp = 1;
+		if (cmp >= 0) break;
+	}
+	if (r < 0) return -1;
+	if (S.r_start[r] > (long long)start) return -1;
+	return r;
+}
+// resource_new_range, range.h:71-82: sorted insert by start; the skip-list insert burns one random()
+__device__ int resource_new_range(Ctx &c, int res, long long start, double len, double last){
+	const Sim &S = *c.S;
+	int i = c.st->free_range;
+	if (i >= 0) { __syncwarp(); L0 c.st->free_range = S.r_next_free[i]; }
+	else {
+		i = c.st->hi_range;
+		if (i >= S.cap_ranges) { set_status(c, NS_E_TABLE_FULL); return -1; }
+		__syncwarp();
+		L0 c.st->hi_range = i+1;
+	}
+	c.burns += 1;
+	L0 {
+		S.r_start[i] = start; S.r_len[i] = len; S.r_lenc[i] = 0; S.r_last[i] = last;
+		S.r_total[i] = S.s_len[res]; S.r_res[i] = res; S.r_prod[i] = -1; S.r_cons[i] = -1;
+		int prev = -1, cur = S.s_first[res];
+		while (cur >= 0 && (int)((u64)S.r_start[cur]-(u64)(long long)(int)start) < 0) { prev = cur; cur = S.r_next[cur]; }
+		S.r_prev[i] = prev; S.r_next[i] = cur;
+		if (prev >= 0) S.r_next[prev] = i; else S.s_first[res] = i;
+		if (cur >= 0) S.r_prev[cur] = i;
+	}
+	__syncwarp();
+	return i;
+}
+
+// range_merge_with_next, range.c:83-124
+__device__ void range_merge_with_next(Ctx &c, int r){
+	const Sim &S = *c.S;
+	int nr = S.r_next[r];
+	if (nr < 0) return;
+	__syncwarp();
+	L0 {
+		S.r_len[r] = (double)(u64)((u64)S.r_start[nr]-(u64)S.r_start[r])+S.r_len[nr];   // :94
+		int p = S.r_prod[nr];
+		S.r_prod[r] = p;                                              // :96-98
+		if (p >= 0) S.f_drng[p] = r;
+		while (S.r_cons[nr] >= 0) {                                   // :100-107
+			int f = S.r_cons[nr];
+			int nx = S.f_cnext[f];
+			S.r_cons[nr] = nx;
+			if (nx >= 0) S.f_cprev[nx] = -1;
+			S.f_cprev[f] = -1; S.f_cnext[f] = S.r_cons[r];
+			if (S.r_cons[r] >= 0) S.f_cprev[S.r_cons[r]] = f;
+			S.r_cons[r] = f;
+			S.f_srng[f] = r;
+		}
+		int nn = S.r_next[nr];                                        // :109-110
+		S.r_next[r] = nn;
+		if (nn >= 0) S.r_prev[nn] = r;
+		S.r_next_free[nr] = c.st->free_range; c.st->free_range = nr;
+		range_update_1(S, r, c.now);                                  // :113
+	}
+	__syncwarp();
+	for (int f = S.r_cons[r]; f >= 0; f = S.f_cnext[f]) {             // :114-117
+		L0 range_update_1(S, S.f_drng[f], c.now);
+		__syncwarp();
+		range_calc_and_requeue_events(c, f);
+	}
+	int p = S.r_prod[r];
+	if (p >= 0) {                                                     // :119-123
+		L0 range_update_1(S, S.f_srng[p], c.now);
+		__syncwarp();
+		range_calc_and_requeue_events(c, p);
+	}
+}
+
+// ---------------------------------------------------------------- flows
+// flow_create, flow.c:296-337
+__device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
+	const Sim &S = *c.S;
+	int f = c.st->free_flow;
+	if (f >= 0) { __syncwarp(); L0 c.st->free_flow = S.f_next_free[f]; }
+	else {
+		f = c.st->hi_flow;
+		if (f >= S.cap_flows) { set_status(c, NS_E_TABLE_FULL); return -1; }
+		__syncwarp();
+		L0 c.st->hi_flow = f+1;
+	}
+	L0 {
+		S.f_ub[f] = ub; S.f_delay[f] = delay; S.f_speed[0][f] = 0; S.f_speed[1][f] = 0;
+		S.f_peer[0][f] = src; S.f_peer[1][f] = dst;
+		S.f_srng[f] = -1; S.f_drng[f] = -1; S.f_cnext[f] = -1; S.f_cprev[f] = -1;
+		S.f_alive[f] = 1; S.f_drain_type[f] = 0; S.f_ord[f] = -1;
+		S.l_time[2*f] = NS_INF; S.l_time[2*f+1] = NS_INF;
+		S.n_total[0][src] += ub;                                      // :314-315
+		S.n_total[1][dst] += ub;
+	}
+	__syncwarp();
+	adj_append(c, src*2+0, f, 0);                                     // :311-312
+	adj_append(c, dst*2+1, f, 1);
+	if (c.st->status) return f;
+	double spd0 = get_share(S, f, 0);                                 // :317-318
+	bwspread(c, f, spd0, 0, 0);
+	queue_speed_event(c, f, RCV, S.f_speed[0][f]);                    // :322
+	uint32_t id = draw_random(c);                                     // :326-330
+	L0 S.f_id[f] = id;
+	write_record(c, R_CONN_CREATE, S.n_id[src], 4, id, 0);            // :333-334
+	write_record(c, R_CONN_DST, id, 4, S.n_id[dst], 0);
+	__syncwarp();
+	return f;
+}
+
+// flow_close, flow.c:241-292
+__device__ void flow_close(Ctx &c, int f){
+	const Sim &S = *c.S;
+	int src = S.f_peer[0][f], dst = S.f_peer[1][f];
+	double ub = S.f_ub[f];
+	__syncwarp();
+	L0 { S.n_total[0][src] -= ub; S.n_total[1][dst] -= ub; }          // :246-247
+	__syncwarp();
+	flow_range_update(c, f);                                          // :248
+	if (c.st->status) return;
+	bwspread(c, f, S.f_speed[0][f], 0, 1);                            // :249-250
+	bwspread(c, f, S.f_speed[1][f], 1, 1);
+	adj_remove(c, src*2+0, f, 0);                                     // :251-252
+	adj_remove(c, dst*2+1, f, 1);
+	int sr = S.f_srng[f], dr = S.f_drng[f];
+	L0 {
+		S.f_gen[f] += 1;                                              // :260-270 cancels its pending speed events
+		if (dr >= 0 && S.r_prod[dr] == f) S.r_prod[dr] = -1;          // :273-274
+		S.s_ncons[S.r_res[sr]] -= 1;                                  // :275-276
+		S.s_nprod[S.r_res[dr]] -= 1;
+		int cp = S.f_cprev[f], cn = S.f_cnext[f];                     // :282
+		if (cp >= 0) S.f_cnext[cp] = cn; else S.r_cons[sr] = cn;
+		if (cn >= 0) S.f_cprev[cn] = cp;
+		S.l_time[2*f] = NS_INF; S.l_time[2*f+1] = NS_INF;             // :283-284
+		S.f_alive[f] = 0;
+		int ord = S.f_ord[f];
+		if (ord >= 0) S.ord2flow[ord] = -1;
+		S.f_next_free[f] = c.st->free_flow; c.st->free_flow = f;
+		c.st->cnt[NS_CNT_CLOSES] += 1; c.st->cnt[NS_CNT_LIVE_FLOWS] -= 1;
+	}
+	write_record(c, R_CONN_CLOSE, S.f_id[f], 1, 0, 0);                // :289-290
+	__syncwarp();
+}
+
+// sim_establish_flow, sim.c:42-94
+__device__ int sim_establish_flow(Ctx &c, uint32_t rid, long long start, int src, int dst, double ub, double delay){
+	const Sim &S = *c.S;
+	int sr = store_get(S, src, rid);
+	if (sr < 0) return -1;                                            // :49-53
+	int dr = store_get(S, dst, rid);
+	if (dr < 0) dr = resource_new(c, dst, rid, S.s_len[sr]);          // :54-61
+	if (dr < 0) return -1;
+	if (range_get(S, dr, (int)start) >= 0) return -1;                 // :62-67
+	int rng = range_get(S, sr, (int)start);                           // :69
+	int f = flow_create(c, src, dst, ub, delay);                      // :70
+	if (f < 0 || (c.st->status && c.st->status != NS_E_RECORDS_FULL)) return f;
+	int dg = resource_new_range(c, dr, start, 0, c.now);              // :74-76
+	if (dg < 0) return f;
+	L0 { S.f_drng[f] = dg; S.r_prod[dg] = f; S.f_srng[f] = rng; }     // :75-77
+	__syncwarp();
+	if (rng < 0) { set_status(c, NS_E_NULL_RANGE); return f; }
+	if (S.r_prod[rng] >= 0) { L0 c.st->relay_seen = 1; }
+	range_calc_and_requeue_events(c, f);                              // :79
+	L0 {
+		S.f_cprev[f] = -1; S.f_cnext[f] = S.r_cons[rng];              // :80
+		if (S.r_cons[rng] >= 0) S.f_cprev[S.r_cons[rng]] = f;
+		S.r_cons[rng] = f;
+		S.s_ncons[sr] += 1; S.s_nprod[dr] += 1;                       // :82-83
+	}
+	__syncwarp();
+	int ph = S.r_prev[dg];                                            // :86-91
+	if (ph >= 0) range_calc_and_requeue_events(c, S.r_prod[ph]);
+	return f;
+}
+
+// ---------------------------------------------------------------- handlers
+// handle_speed_change (flow.c:341-384) + speed_change_free (flow.c:386-389)
+__device__ void handle_speed_change(Ctx &c, int f, int type, double speed){
+	const Sim &S = *c.S;
+	if (type == RCV) flow_range_update(c, f);                         // :355-357
+	double delta = speed-S.f_speed[type][f];                          // :359
+	bwspread(c, f, delta, type, 0);                                   // :361
+	if (type == RCV) {                                                // :367-374
+		range_calc_and_requeue_events(c, f);
+		range_update_consumer_events(c, S.f_drng[f]);
+	} else if (delta > 0)
+		queue_speed_event(c, f, RCV, S.f_speed[0][f]);
+	write_record(c, R_SPD|type, S.f_id[f], -1, 0, speed);             // :383
+	trace_row(c, EV_SPEED_CHANGE|(type << 8), S.f_ord[f], speed, S.f_speed[type][f]);
+}
+
+__device__ void run_group(Ctx &c, int g);
+
+// flow_done_handler (flow.c:391-401), the script's HNDR_USER slot, flow_done_cleaner (flow.c:403-406)
+__device__ void handle_flow_done(Ctx &c, int f){
+	const Sim &S = *c.S;
+	flow_range_update(c, f);
+	int drng = S.f_drng[f];
+	int next = S.r_next[drng];
+	if (next >= 0) {
+		flow_range_update(c, S.r_prod[next]);
+		range_merge_with_next(c, drng);
+	}
+	int ord = S.f_ord[f];
+	trace_row(c, EV_FLOW_DONE, ord, S.r_len[S.f_drng[f]], S.f_speed[1][f]);
+	if (S.n_ondone) {
+		int lo = 0, hi = S.n_ondone-1, g = -1;
+		while (lo <= hi) {
+			int m = (lo+hi)/2;
+			int fo = S.ondone[m].flow_ord;
+			if (fo == ord) { g = S.ondone[m].group; break; }
+			if (fo < ord) lo = m+1; else hi = m-1;
+		}
+		if (g >= 0) run_group(c, g);
+	}
+	if (c.st->status) return;
+	flow_close(c, f);
+}
+
+// flow_throttle_handler, flow.c:408-423
+__device__ void handle_throttle(Ctx &c, int f){
+	const Sim &S = *c.S;
+	int prod = S.r_prod[S.f_srng[f]];
+	if (prod < 0) { set_status(c, NS_E_NO_PRODUCER); return; }
+	double delta = S.f_speed[1][prod]-S.f_speed[0][f];                // :412
+	if (!(delta >= NS_EPS)) {
+		flow_range_update(c, f);                                      // :416
+		bwspread(c, f, delta, SND, 0);                                // :418
+		delta = S.f_speed[1][prod]-S.f_speed[1][f];                   // :419
+		bwspread(c, f, delta, RCV, 0);
+		range_calc_and_requeue_events(c, f);                          // :421-422
+		range_update_consumer_events(c, S.f_drng[f]);
+	}
+	trace_row(c, EV_FLOW_SPEED_THROTTLE, S.f_ord[f], S.f_speed[0][f], S.f_speed[1][f]);
+}
+
+// one group of script operations == what oracle/ref_scenario.c run_group() does through the module API
+__device__ void run_group(Ctx &c, int g){
+	const Sim &S = *c.S;
+	int lo = S.group_off[g], hi = S.group_off[g+1];
+	for (int i = lo; i < hi; i++) {
+		if (c.st->status) return;
+		ns_sc_op op = S.ops[i];
+		switch (op.kind) {
+		case NS_OP_CREATE: {
+			int f = sim_establish_flow(c, S.rids[op.c], op.start, op.a, op.b, op.x, op.y);
+			int ord = c.st->n_ord;
+			if (ord >= S.cap_ord) { set_status(c, NS_E_TABLE_FULL); return; }
+			__syncwarp();
+			L0 {
+				S.ord2flow[ord] = f;
+				c.st->n_ord = ord+1;
+				if (f >= 0) {
+					S.f_ord[f] = ord;
+					c.st->cnt[NS_CNT_CREATES] += 1;
+					u64 live = ++c.st->cnt[NS_CNT_LIVE_FLOWS];
+					if (live > c.st->cnt[NS_CNT_PEAK_FLOWS]) c.st->cnt[NS_CNT_PEAK_FLOWS] = live;
+				}
+			}
+			__syncwarp();
+			break; }
+		case NS_OP_SCHED: {
+			int u = c.st->free_user;
+			if (u >= 0) { __syncwarp(); L0 c.st->free_user = S.u_next_free[u]; }
+			else {
+				u = c.st->hi_user;
+				if (u >= S.cap_users) { set_status(c, NS_E_TABLE_FULL); return; }
+				__syncwarp();
+				L0 c.st->hi_user = u+1;
+			}
+			double t = op.c ? c.now+op.x : op.x;
+			if (ev_time_ok(c, t)) {
+				u64 seq = seq_reserve(c, 1);
+				L0 { S.u_group[u] = op.a; l_put(c, 2*S.cap_flows+u, seq, t); }
+			}
+			__syncwarp();
+			break; }
+		case NS_OP_CLOSE: {
+			int f = (op.a < c.st->n_ord) ? S.ord2flow[op.a] : -1;
+			if (f >= 0) flow_close(c, f);
+			break; }
+		case NS_OP_END:
+			L0 c.st->exit_flag = 1;                                   // sim.h:42-45
+			__syncwarp();
+			break;
+		}
+	}
+}

@@ -1,0 +1,238 @@
+// ns_seq.cuh — one simulation stepped by ONE warp: next-completion argmin, equal-timestamp batch
+// extraction and strictly sequential handling of the batch.  This is the always-legal path (relay
+// topologies, FLOW_DONE / USER / THROTTLE events) and the per-replica engine of ensembles; the
+// grid-parallel path (ns_par.cuh) reuses its pieces.
+//
+// Replaces main.c:50-67: `while(!skip_list_empty) { e = event_pop(); now = e->time; handlers }`.
+// event_pop (event.h:20-25) becomes: t = min over the per-tile minima of the two event stores;
+// the batch is every pending event with time == t, in insertion order (FIFO ties, event.h:27-31).
+#pragma once
+#include "ns_model.cuh"
+
+__device__ __forceinline__ double warp_min_d(double v){
+	#pragma unroll
+	for (int d = 16; d; d >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, d));
+	return v;
+}
+__device__ __forceinline__ u64 warp_min_u64(u64 v){
+	#pragma unroll
+	for (int d = 16; d; d >>= 1) { u64 o = __shfl_xor_sync(FULLMASK, v, d); v = o < v ? o : v; }
+	return v;
+}
+
+// scratch layout inside b_seq/b_ref: [0, batch_cap) ring part, L part in lb arrays
+struct SeqScratch { u64 *lb_seq; int *lb_ref; u64 *lb_tmp_seq; int *lb_tmp_ref; };
+
+// Step 1: global minimum event time + ring head advance.
+__device__ double seq_find_tmin(Ctx &c){
+	const Sim &S = *c.S;
+	const int lane = c.lane;
+	double m = NS_INF;
+	const u64 tmask = (u64)S.n_ring_tiles-1;
+	u64 first = c.head >> NS_TILE_SHIFT;
+	u64 last = c.tail ? (c.tail-1) >> NS_TILE_SHIFT : 0;
+	u64 first_live = ~0ull;
+	if (c.tail > c.head || (c.tail & (NS_TILE-1))) {
+		for (u64 a = first+lane; a <= last; a += 32) {
+			double v = S.q_tmin[a & tmask];
+			if (v != NS_INF && a < first_live) first_live = a;
+			m = fmin(m, v);
+		}
+	}
+	first_live = warp_min_u64(first_live);
+	c.head = (first_live == ~0ull) ? ((c.tail >> NS_TILE_SHIFT) << NS_TILE_SHIFT) : (first_live << NS_TILE_SHIFT);
+	for (int t = lane; t < S.n_l_tiles; t += 32) m = fmin(m, S.l_tmin[t]);
+	return warp_min_d(m);
+}
+
+// Step 2a: ordered extraction of the ring entries with time == m.  Returns the count (or -1 when the
+// batch scratch overflows).  Tile minima are recomputed without the extracted entries.
+__device__ int seq_collect_ring(Ctx &c, double m){
+	const Sim &S = *c.S;
+	const int lane = c.lane;
+	const u64 tmask = (u64)S.n_ring_tiles-1;
+	const u64 smask = S.ring_cap-1;
+	int nb = 0;
+	u64 first = c.head >> NS_TILE_SHIFT;
+	u64 last = c.tail ? (c.tail-1) >> NS_TILE_SHIFT : 0;
+	if (c.tail <= c.head) return 0;
+	for (u64 a0 = first; a0 <= last; a0 += 32) {
+		u64 a = a0+lane;
+		bool hit = a <= last && S.q_tmin[a & tmask] == m;
+		unsigned hits = __ballot_sync(FULLMASK, hit);
+		while (hits) {
+			int b = __ffs(hits)-1; hits &= hits-1;
+			u64 at = a0+b;
+			u64 base = at << NS_TILE_SHIFT;
+			double nm = NS_INF;
+			for (int i = 0; i < NS_TILE; i += 32) {
+				u64 seq = base+i+lane;
+				double t = S.q_time[seq & smask];
+				bool match = t == m && seq >= c.head && seq < c.tail;
+				unsigned mm = __ballot_sync(FULLMASK, match);
+				if (mm) {
+					if (nb+__popc(mm) > S.batch_cap) return -1;
+					if (match) { int pos = nb+__popc(mm & ((1u << lane)-1)); S.b_seq[pos] = seq; }
+					nb += __popc(mm);
+				}
+				if (!match) nm = fmin(nm, t);
+			}
+			nm = warp_min_d(nm);
+			if (lane == 0) S.q_tmin[at & tmask] = nm;
+		}
+	}
+	__syncwarp();
+	return nb;
+}
+
+// Step 2b: long-lived events with time == m, sorted by sequence number.
+__device__ int seq_collect_l(Ctx &c, double m, const SeqScratch &sc){
+	const Sim &S = *c.S;
+	const int lane = c.lane;
+	int nl = 0;
+	for (int t0 = 0; t0 < S.n_l_tiles; t0 += 32) {
+		int t = t0+lane;
+		bool hit = t < S.n_l_tiles && S.l_tmin[t] == m;
+		unsigned hits = __ballot_sync(FULLMASK, hit);
+		while (hits) {
+			int b = __ffs(hits)-1; hits &= hits-1;
+			int tile = t0+b;
+			int base = tile << NS_TILE_SHIFT;
+			double nm = NS_INF;
+			for (int i = 0; i < NS_TILE; i += 32) {
+				int slot = base+i+lane;
+				double tt = slot < S.n_l ? S.l_time[slot] : NS_INF;
+				bool match = tt == m;
+				unsigned mm = __ballot_sync(FULLMASK, match);
+				if (match) { int pos = nl+__popc(mm & ((1u << lane)-1)); sc.lb_seq[pos] = S.l_seq[slot]; sc.lb_ref[pos] = slot; }
+				nl += __popc(mm);
+				if (!match) nm = fmin(nm, tt);
+			}
+			nm = warp_min_d(nm);
+			if (lane == 0) S.l_tmin[tile] = nm;
+		}
+	}
+	__syncwarp();
+	if (nl > 1) {
+		if (nl <= 64) {
+			if (lane == 0) {
+				for (int i = 1; i < nl; i++) {
+					u64 s = sc.lb_seq[i]; int r = sc.lb_ref[i]; int j = i-1;
+					while (j >= 0 && sc.lb_seq[j] > s) { sc.lb_seq[j+1] = sc.lb_seq[j]; sc.lb_ref[j+1] = sc.lb_ref[j]; j--; }
+					sc.lb_seq[j+1] = s; sc.lb_ref[j+1] = r;
+				}
+			}
+		} else {
+			// rank sort (sequence numbers are unique)
+			for (int i = lane; i < nl; i += 32) {
+				u64 s = sc.lb_seq[i]; int rank = 0;
+				for (int j = 0; j < nl; j++) rank += sc.lb_seq[j] < s;
+				sc.lb_tmp_seq[rank] = s; sc.lb_tmp_ref[rank] = sc.lb_ref[i];
+			}
+			__syncwarp();
+			for (int i = lane; i < nl; i += 32) { sc.lb_seq[i] = sc.lb_tmp_seq[i]; sc.lb_ref[i] = sc.lb_tmp_ref[i]; }
+		}
+		__syncwarp();
+	}
+	return nl;
+}
+
+// handle one long-lived event (FLOW_DONE / FLOW_DRAIN / FLOW_SPEED_THROTTLE / USER); returns false
+// when it had been cancelled or re-timed after extraction.
+__device__ bool seq_handle_l(Ctx &c, double m, u64 seq, int slot){
+	const Sim &S = *c.S;
+	if (!(S.l_time[slot] == m && S.l_seq[slot] == seq)) return false;
+	__syncwarp();
+	L0 S.l_time[slot] = NS_INF;                                       // event_pop: active = false
+	__syncwarp();
+	cnt_add(c, NS_CNT_EVENTS, 1);
+	if (slot < 2*S.cap_flows) {
+		int f = slot >> 1;
+		if (!(slot & 1)) { cnt_add(c, NS_CNT_FLOW_DONE, 1); handle_flow_done(c, f); }
+		else if (S.f_drain_type[f] == EV_FLOW_SPEED_THROTTLE) { cnt_add(c, NS_CNT_THROTTLE, 1); handle_throttle(c, f); }
+		else { cnt_add(c, NS_CNT_DRAIN, 1); trace_row(c, EV_FLOW_DRAIN, S.f_ord[f], 0, 0); }   // no handler (main.c:44-48)
+	} else {
+		int u = slot-2*S.cap_flows;
+		int g = S.u_group[u];
+		L0 { S.u_next_free[u] = c.st->free_user; c.st->free_user = u; }
+		__syncwarp();
+		cnt_add(c, NS_CNT_USER, 1);
+		trace_row(c, EV_USER, g, 0, 0);
+		run_group(c, g);
+	}
+	return true;
+}
+
+// handle one ring (SPEED_CHANGE) entry
+__device__ bool seq_handle_ring(Ctx &c, double m, u64 seq){
+	const Sim &S = *c.S;
+	u64 slot = seq & (S.ring_cap-1);
+	if (S.q_time[slot] != m) return false;
+	int fd = S.q_fd[slot];
+	int f = fd >> 1, dir = fd & 1;
+	double speed = S.q_speed[slot];
+	bool live = S.f_gen[f] == S.q_gen[slot] && S.f_alive[f];
+	__syncwarp();
+	L0 S.q_time[slot] = NS_INF;
+	__syncwarp();
+	if (!live) return false;                                          // cancelled by flow_close (flow.c:260-270)
+	cnt_add(c, NS_CNT_EVENTS, 1);
+	cnt_add(c, NS_CNT_SPEED_CHANGE, 1);
+	handle_speed_change(c, f, dir, speed);
+	return true;
+}
+
+__device__ __forceinline__ bool seq_should_stop(Ctx &c){
+	SimState *st = c.st;
+	if (st->status || st->exit_flag) return true;
+	if (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events) return true;
+	return false;
+}
+
+// put the unprocessed tail of a batch back under the tile minima (max_events / sim_end mid-batch)
+__device__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
+	const Sim &S = *c.S;
+	for (int k = i+c.lane; k < nr; k += 32) {
+		u64 seq = S.b_seq[k];
+		u64 slot = seq & (S.ring_cap-1);
+		if (S.q_time[slot] == m) tmin_lower(&S.q_tmin[slot >> NS_TILE_SHIFT], m);
+	}
+	for (int k = j+c.lane; k < nl; k += 32) {
+		int slot = sc.lb_ref[k];
+		if (S.l_time[slot] == m && S.l_seq[slot] == sc.lb_seq[k]) tmin_lower(&S.l_tmin[slot >> NS_TILE_SHIFT], m);
+	}
+	__syncwarp();
+}
+
+// process batch entries [i0,nr) x [j0,nl) in sequence order, strictly sequentially
+__device__ void seq_process(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
+	const Sim &S = *c.S;
+	while (i < nr || j < nl) {
+		if (seq_should_stop(c)) { seq_restore(c, m, i, nr, j, nl, sc); return; }
+		u64 sr = i < nr ? S.b_seq[i] : ~0ull;
+		u64 sl = j < nl ? sc.lb_seq[j] : ~0ull;
+		if (sr < sl) { seq_handle_ring(c, m, sr); i++; }
+		else { seq_handle_l(c, m, sl, sc.lb_ref[j]); j++; }
+	}
+}
+
+__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
+	Ctx c;
+	ctx_load(c, Sp, lane);
+	while (true) {
+		if (seq_should_stop(c)) break;
+		double m = seq_find_tmin(c);
+		if (m == NS_INF) break;                                       // queue empty (main.c:50)
+		int nr = seq_collect_ring(c, m);
+		if (nr < 0) { set_status(c, NS_E_BATCH_FULL); __syncwarp(); break; }
+		int nl = seq_collect_l(c, m, sc);
+		if (nr+nl == 0) continue;                                     // only stale lower bounds surfaced
+		c.now = m;                                                    // main.c:60
+		cnt_add(c, NS_CNT_BATCHES, 1);
+		L0 { if ((u64)(nr+nl) > c.st->cnt[NS_CNT_MAX_BATCH]) c.st->cnt[NS_CNT_MAX_BATCH] = nr+nl; }
+		seq_process(c, m, 0, nr, 0, nl, sc);
+		__syncwarp();
+	}
+	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
+	ctx_flush(c);
+}

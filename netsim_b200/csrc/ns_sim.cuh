@@ -1,0 +1,143 @@
+// ns_sim.cuh — device tables (structure of arrays in HBM) and small helpers shared by the kernels.
+//
+// The reference keeps one calloc'd struct per node/flow/range/event, linked by list_head, uthash and
+// skip lists (data.h:15-151).  Here every field is a column; links are 32-bit indices:
+//   nodes    data.h:100-112   max/usage/total per direction, id, resource list head
+//   adj      node->conns[dir] (list.h lists, newest first, flow.c:311-312) as growable index arrays:
+//            iteration newest-first == descending position, removed entries are tombstones (-1)
+//   flows    data.h:44-87     ub, speed[2], delay, peers, ranges, generation (cancels pending events)
+//   ranges   data.h:15-24     start/total_len/len/lenc/last_update/producer, sorted list per resource
+//   ring     every event_add (event.h:56-74) takes the next sequence number `tail`; SPEED_CHANGE
+//            events (flow.h:5-11) live in ring slot seq & (cap-1), so ring order == FIFO order of
+//            equal timestamps (event.h:27-31) and an equal-time batch is an ordered compaction.
+//   L table  long-lived events: FLOW_DONE (slot 2f) / FLOW_DRAIN|THROTTLE (slot 2f+1) of each flow
+//            (flow->done, flow->drain, data.h:84) and USER events, with explicit seq.
+// Both event stores keep a per-1024-entry lower bound of their minimum time (q_tmin/l_tmin): the
+// next-completion argmin reads only those, the batch extraction only the tiles that hit.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "../../include/ns_scenario.h"
+#include "../../include/netsim_b200.h"
+
+#define NS_TILE 1024
+#define NS_TILE_SHIFT 10
+#define NS_EPS 1e-4                       /* sim.c:11 */
+#define NS_INF (__longlong_as_double(0x7ff0000000000000LL))
+#define FULLMASK 0xffffffffu
+
+enum { SND = 0, RCV = 1 };
+enum { EV_FLOW_DRAIN = 0, EV_FLOW_DONE = 1, EV_FLOW_SPEED_THROTTLE = 2, EV_PACKET_DONE = 3, EV_SPEED_CHANGE = 4, EV_USER = 5 };
+enum { R_USAGE = 0, R_SPD = 2, R_CONN_CREATE = 4, R_CONN_DST = 5, R_CONN_CLOSE = 6, R_NODE_STATE = 7, R_NODE_CREATE = 8 };
+
+typedef unsigned long long u64;
+
+struct SimState {                 // mutable scalars of one simulation
+	double now;
+	u64 head, tail;               // ring window [head, tail) in absolute sequence numbers
+	u64 burns;                    // random() draws burned since the last real draw (skiplist.h:34-40)
+	int32_t rnd[31]; int32_t rf, rr;
+	int status, exit_flag, relay_seen, pad0;
+	u64 rec_len, tr_len;
+	u64 cnt[NS_CNT_COUNT];
+	int free_flow, hi_flow, free_range, hi_range, hi_res, free_user, hi_user, n_ord;
+	int adj_top, pad1;
+	u64 max_events;
+	u64 seed;
+};
+
+struct Sim {
+	// capacities
+	int n_nodes, cap_flows, cap_ranges, cap_res, cap_users, cap_ord;
+	int n_groups, n_ops, n_ondone, n_rids;
+	u64 ring_cap; int n_ring_tiles; int n_l, n_l_tiles;
+	int adj_arena_cap, batch_cap;
+	u64 rec_cap, tr_cap;
+	int want_rec, want_tr;
+	SimState *st;
+	// nodes
+	double *n_max[2], *n_usage[2], *n_total[2]; uint32_t *n_id; int *n_res_head;
+	// adjacency: group g = node*2+dir
+	int *adj_off, *adj_cap, *adj_len, *adj_live, *adj_arena;
+	// flows
+	double *f_ub, *f_speed[2], *f_delay; int *f_peer[2]; uint32_t *f_id, *f_gen;
+	int *f_srng, *f_drng, *f_cnext, *f_cprev, *f_pos[2], *f_ord, *f_next_free; uint8_t *f_alive, *f_drain_type;
+	// ranges
+	long long *r_start, *r_total; double *r_len, *r_lenc, *r_last;
+	int *r_prod, *r_res, *r_next, *r_prev, *r_cons, *r_next_free;
+	// resources
+	uint32_t *s_id; long long *s_len; int *s_node, *s_first, *s_nprod, *s_ncons, *s_next;
+	// speed-event ring
+	double *q_time, *q_speed; int *q_fd; uint32_t *q_gen; double *q_tmin;
+	// long-lived event table
+	double *l_time; u64 *l_seq; double *l_tmin; int *u_group, *u_next_free;
+	// script
+	const ns_sc_op *ops; const int *group_off; const ns_sc_ondone *ondone; const uint32_t *rids;
+	int *ord2flow;
+	// per-timestamp batch scratch
+	u64 *b_seq; int *b_ref;       // ring entries: ref = -1; L entries: ref = slot
+	// outputs
+	uint8_t *rec; ns_trace_row32 *tr;
+};
+
+// ---------------------------------------------------------------- glibc random(), TYPE_3
+// r[k] = r[k-31] + r[k-3] (mod 2^32), output r[k] >> 1.  Shared by host init (sim_create_node ids)
+// and the device (flow ids, flow.c:327).
+struct NsRand { int32_t *st; int32_t *f, *r; };
+
+__host__ __device__ inline uint32_t ns_rand_step(int32_t *st, int32_t &f, int32_t &r){
+	uint32_t v = (uint32_t)st[f]+(uint32_t)st[r];
+	st[f] = (int32_t)v;
+	if (++f >= 31) f = 0;
+	if (++r >= 31) r = 0;
+	return v >> 1;
+}
+
+// polynomial arithmetic modulo x^31 - x^28 - 1 over Z/2^32 (the recurrence's characteristic
+// polynomial), used to skip n draws in O(31^2 log n).
+__host__ __device__ inline void ns_poly_mulmod(const uint32_t *a, const uint32_t *b, uint32_t *out){
+	uint32_t t[61];
+	for (int i = 0; i < 61; i++) t[i] = 0;
+	for (int i = 0; i < 31; i++) {
+		uint32_t ai = a[i];
+		if (!ai) continue;
+		for (int j = 0; j < 31; j++) t[i+j] += ai*b[j];
+	}
+	for (int k = 60; k >= 31; k--) {      // x^k = x^(k-3) + x^(k-31)
+		uint32_t c = t[k];
+		t[k-3] += c; t[k-31] += c;
+	}
+	for (int i = 0; i < 31; i++) out[i] = t[i];
+}
+
+__host__ __device__ inline void ns_rand_jump(int32_t *st, int32_t &f, int32_t &r, u64 n){
+	if (n < 96) { for (u64 i = 0; i < n; i++) ns_rand_step(st, f, r); return; }
+	// chronological window s_0..s_30 (oldest first): the next draw overwrites the oldest word
+	// st[f] with st[f]+st[r], r = f+28 (mod 31), i.e. s_31 = s_0 + s_28.
+	uint32_t s[61];
+	for (int i = 0; i < 31; i++) s[i] = (uint32_t)st[(f+i)%31];
+	for (int i = 31; i < 61; i++) s[i] = s[i-31]+s[i-3];
+	uint32_t res[31], base[31], tmp[31];
+	for (int i = 0; i < 31; i++) { res[i] = 0; base[i] = 0; }
+	res[0] = 1; base[1] = 1;
+	u64 e = n;
+	while (e) {
+		if (e & 1) { ns_poly_mulmod(res, base, tmp); for (int i = 0; i < 31; i++) res[i] = tmp[i]; }
+		e >>= 1;
+		if (e) { ns_poly_mulmod(base, base, tmp); for (int i = 0; i < 31; i++) base[i] = tmp[i]; }
+	}
+	uint32_t ns[31];
+	for (int i = 0; i < 31; i++) {
+		uint32_t acc = 0;
+		for (int j = 0; j < 31; j++) acc += res[j]*s[i+j];
+		ns[i] = acc;
+	}
+	for (int i = 0; i < 31; i++) st[i] = (int32_t)ns[i];
+	f = 0; r = 28;                        // oldest word now at index 0
+}
+
+__host__ __device__ inline u64 ns_mix64(u64 z){
+	z = (z ^ (z >> 30))*0xbf58476d1ce4e5b9ULL;
+	z = (z ^ (z >> 27))*0x94d049bb133111ebULL;
+	return z ^ (z >> 31);
+}
