@@ -1,0 +1,159 @@
+"""GPU: the CUDA engine, called through the C ABI, against the CPU oracle on the same scripts, the
+committed golden vectors from the compiled reference, and (when it travelled) the reference itself."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases
+from netsim_b200 import engine as E
+from netsim_b200 import scenario as S
+from oracle import pyoracle, refrun
+
+pytestmark = pytest.mark.gpu
+CASES = golden_cases()
+MODES = [("seq", E.MODE_SEQ), ("auto", E.MODE_AUTO)]
+KEYS = ("events", "solves", "full_spreads", "flow_visits", "speed_change", "flow_done", "drain", "throttle", "user",
+        "creates", "closes", "draws", "seq")
+
+
+def run_engine(b, mode, max_events=0, **kw):
+    e = E.Engine(b, mode=mode, records=True, trace=True, **kw)
+    st = e.run(max_events)
+    return e, st
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+@pytest.mark.parametrize("name,z", CASES, ids=[c[0] for c in CASES])
+def test_engine_matches_reference_golden(name, z, mname, mode, built):
+    e, st = run_engine(z["scenario"].tobytes(), mode, int(z["max_events"]))
+    assert st == 0
+    assert e.records() == z["records"].tobytes()          # byte-identical record stream
+    assert e.trace().tobytes() == z["trace"].tobytes()    # bit-identical fp64 times / speeds
+    assert e.counters()["events"] == int(z["events"])
+    assert e.launches > 0
+    e.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+@pytest.mark.parametrize("seed", range(30))
+def test_engine_matches_oracle_random(seed, mname, mode, built):
+    for relay in (False, True):
+        sc = S.random_small(200 + seed, n_nodes=6 + seed % 7, n_flows=8 + seed % 17, relay=relay)
+        b = sc.to_bytes()
+        o = pyoracle.Oracle(b)
+        so = o.run(0)
+        e, se = run_engine(b, mode)
+        assert se == -so
+        if so == 0:
+            assert e.records() == o.records()
+            assert e.trace().tobytes() == o.trace().tobytes()
+            ce, co = e.counters(), o.counters()
+            assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+            fs = e.flow_state(sc.n_creates())
+            assert fs.tobytes() == o.flow_state(sc.n_creates()).tobytes()
+            assert e.node_state(sc.n_nodes).tobytes() == o.node_state(sc.n_nodes).tobytes()
+            assert e.digest()["record_hash"] == E.stream_hash(o.records())
+        e.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+def test_engine_swarm_window_and_resume(mname, mode, built):
+    """A bounded window of a 1.5k-peer swarm (equal-timestamp batches of thousands of events), run in
+    two instalments: stopping and resuming mid-batch must not change anything."""
+    sc = S.swarm(1500, 6, n_catalogue=8, seeds_per_peer=3, mean_strips=5.0)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(150000) == 0
+    e = E.Engine(b, mode=mode, records=True, trace=True, trace_cap=200000)
+    assert e.run(70001) == 0
+    assert e.counters()["events"] == 70001
+    assert e.run(150000) == 0
+    assert e.records() == o.records()
+    assert e.trace().tobytes() == o.trace().tobytes()
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    e.close()
+
+
+@pytest.mark.skipif(not refrun.available(), reason="compiled reference did not travel")
+@pytest.mark.parametrize("mname,mode", MODES)
+def test_engine_vs_compiled_reference(mname, mode, built):
+    sc = S.swarm(400, 4, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0, arrival_window=2.0)
+    b = sc.to_bytes()
+    r = refrun.run_reference(b, max_events=50000, trace=True)
+    assert r["returncode"] == 0
+    e, st = run_engine(b, mode, 50000, trace_cap=100000)
+    assert st == 0
+    assert e.records() == r["records"]
+    assert e.trace().tobytes() == r["trace"].tobytes()
+    e.close()
+
+
+def test_reference_abort_is_reported(built):
+    """Scripts on which the reference abort()s (event.h:60-64) end with the matching error code."""
+    found = 0
+    for seed in range(40, 140):
+        sc = S.random_small(seed, n_nodes=6 + seed % 7, n_flows=8 + seed % 17, relay=True)
+        b = sc.to_bytes()
+        o = pyoracle.Oracle(b)
+        so = o.run(0)
+        if so != 0:
+            e, se = run_engine(b, E.MODE_SEQ)
+            assert se == -so
+            e.close()
+            found += 1
+            if found >= 3:
+                break
+    assert found >= 1
+
+
+def test_ensemble_digests_match_single_runs(built):
+    scs = [S.random_small(300 + i, n_nodes=7, n_flows=10).to_bytes() for i in range(12)]
+    ens = E.Ensemble(scs)
+    ens.run(0)
+    dig = ens.digests()
+    for i, b in enumerate(scs):
+        o = pyoracle.Oracle(b)
+        so = o.run(0)
+        assert dig[i]["status"] == -so
+        if so == 0:
+            assert dig[i]["events"] == o.counters()["events"]
+            assert dig[i]["solves"] == o.counters()["solves"]
+            assert dig[i]["record_bytes"] == len(o.records())
+            assert dig[i]["record_hash"] == E.stream_hash(o.records())
+    ens.close()
+
+
+def test_pick_batch_matches_qselect(built):
+    rng = np.random.default_rng(11)
+    offs, vals, nodes, ks = [0], [], [], []
+    for _ in range(500):
+        c = int(rng.integers(0, 70))
+        offs.append(offs[-1] + c)
+        vals.extend(rng.integers(-30, 30, c).tolist())
+        nodes.extend(rng.permutation(1000)[:c].tolist())
+        ks.append(int(rng.integers(1, 40)))
+    big = 3000                                    # beyond the shared-memory staging size
+    offs.append(offs[-1] + big)
+    vals.extend(rng.integers(-1000, 1000, big).tolist())
+    nodes.extend(range(big))
+    ks.append(1500)
+    off, val, node, k = (np.array(x, dtype=np.int32) for x in (offs, vals, nodes, ks))
+    ov, on, oc, ms = E.pick_batch(1, off, val, node, k)
+    for q in range(len(ks)):
+        lo, hi = off[q], off[q + 1]
+        v, nd = val[lo:hi].copy(), node[lo:hi].copy()
+        cnt = pyoracle.lib().ns_oracle_pick_opt1(v.ctypes.data, nd.ctypes.data, hi - lo, int(k[q]))
+        assert oc[q] == cnt
+        assert (ov[lo:hi] == v).all() and (on[lo:hi] == nd).all()     # same order as the reference's partition
+    # mode 2: first strict minimum, INT32_MAX marks unusable holders
+    val2 = val.copy()
+    val2[rng.random(len(val2)) < 0.3] = np.iinfo(np.int32).max
+    ov, on, oc, ms = E.pick_batch(2, off, val2, node, None)
+    for q in range(len(ks)):
+        lo, hi = off[q], off[q + 1]
+        usable = (val2[lo:hi] != np.iinfo(np.int32).max).astype(np.uint8)
+        v = np.ascontiguousarray(val2[lo:hi])
+        i = pyoracle.lib().ns_oracle_pick_opt2(v.ctypes.data, usable.ctypes.data, hi - lo)
+        assert oc[q] == (1 if i >= 0 else 0)
+        if i >= 0:
+            assert on[lo] == node[lo + i]
