@@ -11,18 +11,35 @@
 #pragma once
 #include "ns_sim.cuh"
 
+// Staging area of the grid-parallel path: an event handled out of order cannot know its final
+// sequence numbers / record offset, so its event_adds, records and trace row are parked here under
+// LOCAL indices and committed in batch order by a prefix scan (ns_par.cuh).
+#define NS_STAGE_INLINE 4
+#define NS_STAGE_REC 40
+#define NS_SEQ_PROV (1ull << 63)
+#define NS_HOLE_PURE (-2147483647-1)
+struct ParStage {
+	double *st_time, *st_speed; int *st_fd;     // [NS_STAGE_INLINE*seg_cap] inline, then overflow
+	u64 inline_n, ovf_cap; u64 *ovf_top;
+	uint8_t *st_rec; ns_trace_row32 *st_tr;
+	unsigned *ev_nins; long long *ev_ovf; uint8_t *ev_nrec, *ev_ntr;
+};
+enum { LC_EVENTS = 0, LC_SPEED_CHANGE, LC_SOLVES, LC_FULL_SPREADS, LC_FLOW_VISITS, LC_N };
+
 struct Ctx {
 	const Sim *S; SimState *st; int lane;
 	double now;
 	u64 head, tail;        // ring window, cached in registers (flushed by ctx_flush)
 	u64 burns, rec_len, tr_len;
-	int par;               // 1 inside the grid-parallel path (atomics on shared scalars)
+	int par;               // 1 inside the grid-parallel path: emissions are staged
+	const ParStage *ps; unsigned ev, lseq, rec_n, tr_n; long long ovf_base;
+	u64 lc[LC_N];
 };
 
 #define L0 if (c.lane == 0)
 
 __device__ __forceinline__ void ctx_load(Ctx &c, const Sim *S, int lane){
-	c.S = S; c.st = S->st; c.lane = lane; c.par = 0;
+	c.S = S; c.st = S->st; c.lane = lane; c.par = 0; c.ps = nullptr;
 	c.now = c.st->now; c.head = c.st->head; c.tail = c.st->tail; c.burns = c.st->burns;
 	c.rec_len = c.st->rec_len; c.tr_len = c.st->tr_len;
 }
@@ -34,9 +51,14 @@ __device__ __forceinline__ void ctx_flush(Ctx &c){
 	__syncwarp();
 }
 __device__ __forceinline__ void set_status(Ctx &c, int s){
-	L0 { if (c.st->status == 0) c.st->status = s; }
+	L0 { atomicCAS(&c.st->status, 0, s); }
+}
+__device__ __forceinline__ int lc_slot(int idx){
+	return idx == NS_CNT_EVENTS ? LC_EVENTS : idx == NS_CNT_SPEED_CHANGE ? LC_SPEED_CHANGE : idx == NS_CNT_SOLVES ? LC_SOLVES :
+	       idx == NS_CNT_FULL_SPREADS ? LC_FULL_SPREADS : LC_FLOW_VISITS;
 }
 __device__ __forceinline__ void cnt_add(Ctx &c, int idx, u64 n){
+	if (c.par) { c.lc[lc_slot(idx)] += n; return; }
 	L0 { c.st->cnt[idx] += n; }
 }
 __device__ __forceinline__ void tmin_lower(double *p, double t){
@@ -70,6 +92,12 @@ __device__ __forceinline__ void write_record(Ctx &c, uint8_t minor, uint32_t id,
 	const Sim &S = *c.S;
 	if (!S.want_rec) return;
 	int n = 13+(bytes == 1 ? 1 : bytes == 4 ? 4 : 6);
+	if (c.par) {
+		if (c.rec_n+n > NS_STAGE_REC) { set_status(c, NS_E_TABLE_FULL); return; }
+		L0 rec_encode(c.ps->st_rec+(u64)c.ev*NS_STAGE_REC+c.rec_n, c.now, minor, id, bytes, ival, dval);
+		c.rec_n += n;
+		return;
+	}
 	if (c.rec_len+n > S.rec_cap) { set_status(c, NS_E_RECORDS_FULL); return; }
 	L0 {
 		uint8_t b[19];
@@ -85,6 +113,11 @@ __device__ __forceinline__ void write_usage(Ctx &c, int dir, int n, double usage
 __device__ __forceinline__ void trace_row(Ctx &c, uint32_t type, uint32_t ord, double v0, double v1){
 	const Sim &S = *c.S;
 	if (!S.want_tr) return;
+	if (c.par) {
+		L0 { ns_trace_row32 r; r.type = type; r.ord = ord; r.time = c.now; r.v0 = v0; r.v1 = v1; c.ps->st_tr[c.ev] = r; }
+		c.tr_n = 1;
+		return;
+	}
 	if (c.tr_len >= S.tr_cap) return;
 	L0 { ns_trace_row32 r; r.type = type; r.ord = ord; r.time = c.now; r.v0 = v0; r.v1 = v1; S.tr[c.tr_len] = r; }
 	c.tr_len++;
@@ -102,7 +135,22 @@ __device__ __forceinline__ bool ev_time_ok(Ctx &c, double &t){
 }
 // take n consecutive sequence numbers (each successful event_add: one skip-list insert, one
 // random() burned, skiplist.h:34-40,83)
+__device__ __forceinline__ u64 stage_index(const Ctx &c, u64 j){
+	return j < NS_STAGE_INLINE ? (u64)c.ev*NS_STAGE_INLINE+j : c.ps->inline_n+(u64)c.ovf_base+(j-NS_STAGE_INLINE);
+}
+// before a handler may stage more than NS_STAGE_INLINE inserts (a full spread) it takes a block
+// of the overflow arena sized for its worst case
+__device__ __forceinline__ void stage_ensure(Ctx &c, u64 need){
+	if (!c.par || c.ovf_base >= 0) return;
+	long long b = 0;
+	L0 {
+		b = (long long)atomicAdd((unsigned long long *)c.ps->ovf_top, (unsigned long long)need);
+		if ((u64)b+need > c.ps->ovf_cap) { atomicCAS(&c.st->status, 0, NS_E_TABLE_FULL); b = 0; }
+	}
+	c.ovf_base = __shfl_sync(FULLMASK, b, 0);
+}
 __device__ __forceinline__ u64 seq_reserve(Ctx &c, u64 n){
+	if (c.par) { u64 s0 = c.lseq; c.lseq += (unsigned)n; return s0; }
 	u64 s = c.tail;
 	if (c.tail+n-c.head > c.S->ring_cap) { set_status(c, NS_E_RING_FULL); return s; }
 	c.tail += n; c.burns += n;
@@ -110,14 +158,29 @@ __device__ __forceinline__ u64 seq_reserve(Ctx &c, u64 n){
 }
 __device__ __forceinline__ void ring_put(Ctx &c, u64 seq, double t, double speed, int f, int dir){
 	const Sim &S = *c.S;
+	if (c.par) {
+		u64 i = stage_index(c, seq);
+		c.ps->st_time[i] = t; c.ps->st_speed[i] = speed; c.ps->st_fd[i] = f*2+dir;
+		return;
+	}
 	u64 slot = seq & (S.ring_cap-1);
 	S.q_time[slot] = t; S.q_speed[slot] = speed; S.q_fd[slot] = f*2+dir; S.q_gen[slot] = S.f_gen[f];
 	tmin_lower(&S.q_tmin[slot >> NS_TILE_SHIFT], t);
 }
 __device__ __forceinline__ void l_put(Ctx &c, int slot, u64 seq, double t){
 	const Sim &S = *c.S;
+	if (c.par) {
+		// provisional sequence number (event, local index); the commit pass rewrites it
+		S.l_time[slot] = t; S.l_seq[slot] = NS_SEQ_PROV | ((u64)c.ev << 24) | seq;
+		tmin_lower(&S.l_tmin[slot >> NS_TILE_SHIFT], t);
+		c.ps->st_fd[stage_index(c, seq)] = -(slot+1);
+		return;
+	}
 	S.l_time[slot] = t; S.l_seq[slot] = seq;
 	tmin_lower(&S.l_tmin[slot >> NS_TILE_SHIFT], t);
+}
+__device__ __forceinline__ void stage_pure_hole(Ctx &c, u64 seq){
+	if (c.par) c.ps->st_fd[stage_index(c, seq)] = NS_HOLE_PURE;
 }
 // is_later_than, event.h:82-88 (inactive events are stored as time == +inf)
 __device__ __forceinline__ bool is_later_than(double time, double etime){
@@ -224,7 +287,7 @@ __device__ __forceinline__ void retime_plan_1(const Sim &S, SimState *st, int f,
 }
 // sequence numbers: drain first, then done; a drain superseded by done keeps its burned number.
 __device__ __forceinline__ void retime_commit_1(Ctx &c, int f, const Retime &p, u64 seq){
-	if (p.add_done) l_put(c, 2*f, seq+p.add_drain, p.done_t);
+	if (p.add_done) { if (p.add_drain) stage_pure_hole(c, seq); l_put(c, 2*f, seq+p.add_drain, p.done_t); }
 	else if (p.add_drain) l_put(c, 2*f+1, seq, p.drain_t);
 }
 __device__ __forceinline__ void range_calc_and_requeue_events(Ctx &c, int f){
@@ -298,6 +361,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 	__syncwarp();
 	const int g = n*2+dir;
 	const int off = S.adj_off[g], len = S.adj_len[g];
+	stage_ensure(c, 3ull*(u64)S.adj_live[g]+8);
 	cnt_add(c, NS_CNT_FULL_SPREADS, 1);
 	cnt_add(c, NS_CNT_FLOW_VISITS, 2ull*(u64)S.adj_live[g]);
 	const bool dec = amount < NS_EPS, inc = !dec && amount > NS_EPS;

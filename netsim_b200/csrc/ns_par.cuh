@@ -1,21 +1,486 @@
-// ns_par.cuh — grid-parallel handling of equal-timestamp SPEED_CHANGE batches (placeholder: falls
-// through to the single-warp engine until the parallel kernels land).
+// ns_par.cuh — the grid-parallel engine: one persistent cooperative kernel steps the simulation,
+// one equal-timestamp batch per iteration, all SMs working on the same batch.
+//
+//   A  argmin            min over the per-tile minima of both event stores        (event_pop, event.h:20-25)
+//   B  ordered extract   count / scan / write of the ring entries with time == t  (FIFO ties, event.h:27-31)
+//   C  legality          a batch segment made only of SPEED_CHANGE events in a relay-free simulation is
+//                        handled in parallel; anything else by one warp in sequence order (ns_seq.cuh)
+//   D  grouping          events are bucketed by the (node, direction) whose rates they rewrite
+//                        (bwspread, flow.c:56-60): that is the unit of mutual exclusion;
+//                        different groups touch disjoint mutable state, same-group events keep FIFO order
+//   E  solve             one warp per group walks its events in order: handle_speed_change + bwspread +
+//                        byte progress + completion re-time, emissions staged under local indices
+//   F  commit            prefix scan over the batch order of {event_adds, record bytes, trace rows}; staged
+//                        speed events are copied into the ring at their final sequence numbers, records
+//                        into the record stream — byte-identical to the sequential order
+//
+// Reads of state owned by another group (get_share(nf,!dir), flow.c:140,165: the remote node's
+// total_bwupbound / maximum_bandwidth) are stable inside such a segment because only flow
+// create/close write them (flow.c:246-247,314-315), and those are never part of it.
 #pragma once
+#include <cooperative_groups.h>
 #include "ns_seq.cuh"
 
-struct ParScratch { int enabled; };
+namespace cgp = cooperative_groups;
+
+#define PAR_THREADS 256
+#define PAR_WARPS (PAR_THREADS/32)
+#define PAR_MIN_BATCH 48          // smaller batches are cheaper on the single-warp path
+
+struct ParScratch {
+	int enabled;
+	int seg_cap;                  // events per parallel segment
+	ParStage stage;               // staging arrays (device pointers)
+	ParStage *d_stage;
+	// per-timestamp
+	int *tile_cnt, *tile_off;     // per ring-window tile: matches, exclusive offset
+	// grouping
+	int *grp_cnt, *grp_off, *grp_fill, *active, *grp_items, *b_grp;
+	// scan
+	u64 *cta_ins; unsigned *cta_rec, *cta_tr;
+	// control block (device)
+	struct Ctl {
+		u64 tmin_bits, first_live;
+		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, mode, stop, pad;
+		u64 tot_ins; unsigned tot_rec, tot_tr;
+		u64 lc[LC_N];
+	} *ctl;
+};
 
 __global__ void k_init_groups(const Sim *sims, int n);
 __global__ void k_run_seq(const Sim *sims, const SeqScratch *scr, int n);
 
-template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool enable, A alloc){ p.enabled = enable; return 0; }
+template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool enable, A alloc){
+	memset(&p, 0, sizeof p);
+	p.enabled = enable;
+	if (!enable) return 0;
+	int rc;
+	p.seg_cap = (int)std::min<u64>((u64)S.batch_cap, 1u << 20);
+	ParStage &st = p.stage;
+	st.inline_n = (u64)NS_STAGE_INLINE*p.seg_cap;
+	st.ovf_cap = std::max<u64>(1u << 22, 48ull*S.cap_flows);
+	u64 n = st.inline_n+st.ovf_cap;
+#define PA(ptr, cnt) if ((rc = alloc((void **)&(ptr), (size_t)(cnt)*sizeof(*(ptr))))) return rc
+	PA(st.st_time, n); PA(st.st_speed, n); PA(st.st_fd, n); PA(st.ovf_top, 1);
+	PA(st.st_rec, (u64)NS_STAGE_REC*p.seg_cap); PA(st.st_tr, p.seg_cap);
+	PA(st.ev_nins, p.seg_cap); PA(st.ev_ovf, p.seg_cap); PA(st.ev_nrec, p.seg_cap); PA(st.ev_ntr, p.seg_cap);
+	PA(p.d_stage, 1);
+	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
+	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
+	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
+	PA(p.cta_ins, 4096); PA(p.cta_rec, 4096); PA(p.cta_tr, 4096);
+	PA(p.ctl, 1);
+#undef PA
+	cudaError_t e;
+	if ((e = cudaMemcpy(p.d_stage, &p.stage, sizeof p.stage, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+	if ((e = cudaMemset(p.grp_cnt, 0, (size_t)(2*S.n_nodes+1)*4)) != cudaSuccess) return (int)e;
+	if ((e = cudaMemset(p.ctl, 0, sizeof *p.ctl)) != cudaSuccess) return (int)e;
+	if ((e = cudaMemset(st.ovf_top, 0, 8)) != cudaSuccess) return (int)e;
+	return 0;
+}
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ double block_min_d(double v, double *sh){
+	v = warp_min_d(v);
+	int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+	__syncthreads();
+	if (l == 0) sh[w] = v;
+	__syncthreads();
+	v = l < PAR_WARPS ? sh[l] : NS_INF;
+	return warp_min_d(v);
+}
+
+// ascending in-place sort of a[0..n) by one warp (bitonic network with mirrored first stage, so a
+// virtual +inf padding needs no storage)
+__device__ void warp_sort_global(int *a, int n, int lane){
+	int np = 1; while (np < n) np <<= 1;
+	for (int k = 2; k <= np; k <<= 1) {
+		for (int i = lane; i < np; i += 32) {
+			int p = i ^ (k-1);
+			if (p > i && p < n) { int x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+		}
+		__syncwarp();
+		for (int j = k >> 2; j > 0; j >>= 1) {
+			for (int i = lane; i < np; i += 32) {
+				int p = i ^ j;
+				if (p > i && p < n) { int x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// one staged SPEED_CHANGE event handled by a warp
+__device__ void par_handle_event(Ctx &c, const ParScratch &P, int seg_lo, int e, double m){
+	const Sim &S = *c.S;
+	u64 seq = S.b_seq[seg_lo+e];
+	u64 slot = seq & (S.ring_cap-1);
+	int fd = S.q_fd[slot];
+	double speed = S.q_speed[slot];
+	c.ev = (unsigned)e; c.lseq = 0; c.rec_n = 0; c.tr_n = 0; c.ovf_base = -1;
+	cnt_add(c, NS_CNT_EVENTS, 1);
+	cnt_add(c, NS_CNT_SPEED_CHANGE, 1);
+	handle_speed_change(c, fd >> 1, fd & 1, speed);
+	L0 {
+		const ParStage &ps = *c.ps;
+		ps.ev_nins[c.ev] = c.lseq; ps.ev_ovf[c.ev] = c.ovf_base;
+		ps.ev_nrec[c.ev] = (uint8_t)c.rec_n; ps.ev_ntr[c.ev] = (uint8_t)c.tr_n;
+		S.q_time[slot] = NS_INF;                                      // event_pop
+	}
+	__syncwarp();
+}
+
+// copy the staged outputs of segment-local event e to their final places
+__device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep){
+	unsigned nins = ps.ev_nins[e];
+	long long ovf = ps.ev_ovf[e];
+	for (unsigned j = lane0; j < nins; j += lstep) {
+		u64 si = j < NS_STAGE_INLINE ? (u64)e*NS_STAGE_INLINE+j : ps.inline_n+(u64)ovf+(j-NS_STAGE_INLINE);
+		int fd = ps.st_fd[si];
+		u64 seq = seq0+j;
+		if (fd >= 0) {
+			u64 slot = seq & (S.ring_cap-1);
+			double t = ps.st_time[si];
+			S.q_time[slot] = t; S.q_speed[slot] = ps.st_speed[si]; S.q_fd[slot] = fd; S.q_gen[slot] = S.f_gen[fd >> 1];
+			tmin_lower(&S.q_tmin[slot >> NS_TILE_SHIFT], t);
+		} else if (fd != NS_HOLE_PURE) {
+			int ls = -fd-1;
+			u64 prov = NS_SEQ_PROV | ((u64)e << 24) | j;
+			if (S.l_seq[ls] == prov) S.l_seq[ls] = seq;               // only the last add of a slot survives
+		}
+	}
+	if (lane0 == 0) {
+		unsigned nrec = ps.ev_nrec[e];
+		if (nrec) { const uint8_t *src = ps.st_rec+(u64)e*NS_STAGE_REC; uint8_t *dst = S.rec+rec0; for (unsigned k = 0; k < nrec; k++) dst[k] = src[k]; }
+		if (ps.ev_ntr[e] && tr0 < S.tr_cap) S.tr[tr0] = ps.st_tr[e];
+	}
+}
+
+// ---------------------------------------------------------------- the persistent kernel
+__global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const SeqScratch *scrp, ParScratch P){
+	cgp::grid_group grid = cgp::this_grid();
+	const Sim &S = *sp;
+	SimState *st = S.st;
+	ParScratch::Ctl *ctl = P.ctl;
+	const SeqScratch sc = *scrp;
+	__shared__ double sh_d[PAR_WARPS];
+	__shared__ u64 sh_u[PAR_WARPS];
+	__shared__ unsigned sh_r[PAR_WARPS], sh_t[PAR_WARPS];
+	__shared__ int sh_big[PAR_THREADS]; __shared__ int sh_nbig, sh_status;
+	__shared__ u64 sh_bseq[PAR_THREADS], sh_brec[PAR_THREADS], sh_btr[PAR_THREADS];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int gw = blockIdx.x*PAR_WARPS+warp, nw = gridDim.x*PAR_WARPS;
+	const u64 gtid = (u64)blockIdx.x*PAR_THREADS+tid, gth = (u64)gridDim.x*PAR_THREADS;
+	const u64 tmask = (u64)S.n_ring_tiles-1, smask = S.ring_cap-1;
+	const bool leader = blockIdx.x == 0 && tid == 0;
+
+	while (true) {
+		// ---- A: argmin over tile minima ------------------------------------------------------
+		if (leader) { ctl->tmin_bits = ~0ull; ctl->first_live = ~0ull; ctl->nl = 0; ctl->nb = 0; }
+		grid.sync();
+		if (st->status || st->exit_flag || (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events)) break;
+		const u64 head = st->head, tail = st->tail;
+		const u64 t_first = head >> NS_TILE_SHIFT, t_last = tail ? (tail-1) >> NS_TILE_SHIFT : 0;
+		const u64 n_wt = tail > head ? t_last-t_first+1 : 0;
+		{
+			double m = NS_INF; u64 fl = ~0ull;
+			for (u64 k = gtid; k < n_wt; k += gth) {
+				double v = S.q_tmin[(t_first+k) & tmask];
+				if (v != NS_INF && t_first+k < fl) fl = t_first+k;
+				m = fmin(m, v);
+			}
+			for (u64 k = gtid; k < (u64)S.n_l_tiles; k += gth) m = fmin(m, S.l_tmin[k]);
+			m = block_min_d(m, sh_d);
+			fl = warp_min_u64(fl);
+			if (lane == 0 && fl != ~0ull) atomicMin((unsigned long long *)&ctl->first_live, fl);
+			if (tid == 0 && m != NS_INF) atomicMin((unsigned long long *)&ctl->tmin_bits, (u64)__double_as_longlong(m));
+		}
+		grid.sync();
+		const u64 mb = ctl->tmin_bits;
+		if (mb == ~0ull) break;                                       // queue empty
+		const double m = __longlong_as_double((long long)mb);
+		// ---- B1: per-tile match counts; block 0 warp 0 also extracts the long-lived events -----
+		for (u64 k = gw; k < n_wt; k += nw) {
+			u64 at = t_first+k;
+			int cnt = 0;
+			if (S.q_tmin[at & tmask] == m) {
+				u64 base = at << NS_TILE_SHIFT;
+				for (int i = lane; i < NS_TILE; i += 32) { u64 s = base+i; cnt += (S.q_time[s & smask] == m && s >= head && s < tail); }
+				for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, d);
+			}
+			if (lane == 0) P.tile_cnt[k] = cnt;
+		}
+		if (gw == nw-1) {
+			Ctx c; ctx_load(c, sp, lane);
+			int nl = seq_collect_l(c, m, sc);
+			if (lane == 0) ctl->nl = nl;
+		}
+		grid.sync();
+		// ---- B2: exclusive scan of tile counts (block 0) ---------------------------------------
+		if (blockIdx.x == 0) {
+			__shared__ int sh_scan[PAR_THREADS];
+			u64 per = (n_wt+PAR_THREADS-1)/PAR_THREADS;
+			u64 lo = tid*per, hi = lo+per < n_wt ? lo+per : n_wt;
+			int s = 0;
+			for (u64 k = lo; k < hi; k++) s += P.tile_cnt[k];
+			sh_scan[tid] = s;
+			__syncthreads();
+			if (tid == 0) { int acc = 0; for (int i = 0; i < PAR_THREADS; i++) { int v = sh_scan[i]; sh_scan[i] = acc; acc += v; } ctl->nb = acc; }
+			__syncthreads();
+			int acc = sh_scan[tid];
+			for (u64 k = lo; k < hi; k++) { int v = P.tile_cnt[k]; P.tile_off[k] = acc; acc += v; }
+		}
+		grid.sync();
+		const int nb = ctl->nb, nl = ctl->nl;
+		if (nb > S.batch_cap) { if (leader) atomicCAS(&st->status, 0, NS_E_BATCH_FULL); continue; }
+		// ---- B3: write the batch in order, refresh the tile minima ------------------------------
+		for (u64 k = gw; k < n_wt; k += nw) {
+			u64 at = t_first+k;
+			if (S.q_tmin[at & tmask] != m) continue;
+			u64 base = at << NS_TILE_SHIFT;
+			int off = P.tile_off[k];
+			double nm = NS_INF;
+			for (int i = 0; i < NS_TILE; i += 32) {
+				u64 s = base+i+lane;
+				double t = S.q_time[s & smask];
+				bool match = t == m && s >= head && s < tail;
+				unsigned mm = __ballot_sync(FULLMASK, match);
+				if (match) S.b_seq[off+__popc(mm & ((1u << lane)-1))] = s;
+				off += __popc(mm);
+				if (!match) nm = fmin(nm, t);
+			}
+			nm = warp_min_d(nm);
+			if (lane == 0) S.q_tmin[at & tmask] = nm;
+		}
+		if (leader) {
+			u64 fl = ctl->first_live;
+			st->head = fl == ~0ull ? ((tail >> NS_TILE_SHIFT) << NS_TILE_SHIFT) : (fl << NS_TILE_SHIFT);
+		}
+		grid.sync();
+		if (nb+nl == 0) continue;                                     // only stale lower bounds surfaced
+		// ---- C: legality --------------------------------------------------------------------
+		// (a run bounded by max_events must stop at an exact event count: the parallel prefix is
+		//  clipped to the remaining budget and the rest goes through the sequential path)
+		const u64 ev_now = st->cnt[NS_CNT_EVENTS], ev_max = st->max_events;
+		const u64 budget = ev_max ? (ev_max > ev_now ? ev_max-ev_now : 0) : ~0ull;
+		const bool parallel = nl == 0 && !st->relay_seen && nb >= PAR_MIN_BATCH && budget >= PAR_MIN_BATCH;
+		if (!parallel) {
+			if (blockIdx.x == 0 && warp == 0) {
+				Ctx c; ctx_load(c, sp, lane);
+				c.now = m;
+				cnt_add(c, NS_CNT_BATCHES, 1);
+				L0 { if ((u64)(nb+nl) > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb+nl; }
+				seq_process(c, m, 0, nb, 0, nl, sc);
+				L0 st->cnt[NS_CNT_SEQ] = c.tail;
+				ctx_flush(c);
+			}
+			continue;                                                 // next iteration starts with a grid.sync
+		}
+		if (leader) {
+			st->now = m;
+			st->cnt[NS_CNT_BATCHES] += 1;
+			if ((u64)nb > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb;
+			u64 lim = budget < (u64)P.seg_cap ? budget : (u64)P.seg_cap;
+			ctl->seg_lo = 0; ctl->seg_hi = (u64)nb < lim ? nb : (int)lim;
+			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0;
+			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
+			*P.stage.ovf_top = 0;
+		}
+		grid.sync();
+		// ---- segments of at most seg_cap events, in order --------------------------------------
+		while (true) {
+			const int seg_lo = ctl->seg_lo, seg_hi = ctl->seg_hi;
+			const int ns = seg_hi-seg_lo;
+			if (ns <= 0 || st->status) break;
+			// ---- D1: group of every event; cancelled events drop out ---------------------------
+			for (u64 e = gtid; e < (u64)ns; e += gth) {
+				u64 s = S.b_seq[seg_lo+e];
+				u64 slot = s & smask;
+				int fd = S.q_fd[slot];
+				int f = fd >> 1, dir = fd & 1;
+				int g = -1;
+				if (S.f_gen[f] == S.q_gen[slot] && S.f_alive[f]) {
+					g = S.f_peer[dir][f]*2+dir;
+					if (atomicAdd(&P.grp_cnt[g], 1) == 0) P.active[atomicAdd(&ctl->n_active, 1)] = g;
+				} else {
+					S.q_time[slot] = NS_INF;                          // flow_close cancelled it (flow.c:260-270)
+					P.stage.ev_nins[e] = 0; P.stage.ev_nrec[e] = 0; P.stage.ev_ntr[e] = 0; P.stage.ev_ovf[e] = -1;
+				}
+				P.b_grp[e] = g;
+			}
+			grid.sync();
+			const int n_active = ctl->n_active;
+			// ---- D2: slice of grp_items per active group ---------------------------------------
+			for (u64 k = gtid; k < (u64)n_active; k += gth) {
+				int g = P.active[k];
+				P.grp_off[g] = atomicAdd(&ctl->cursor, P.grp_cnt[g]);
+				P.grp_fill[g] = 0;
+			}
+			grid.sync();
+			// ---- D3: fill -------------------------------------------------------------------------
+			for (u64 e = gtid; e < (u64)ns; e += gth) {
+				int g = P.b_grp[e];
+				if (g >= 0) P.grp_items[P.grp_off[g]+atomicAdd(&P.grp_fill[g], 1)] = (int)e;
+			}
+			grid.sync();
+			// ---- E: one warp per group, events in sequence order ----------------------------------
+			{
+				Ctx c;
+				c.S = sp; c.st = st; c.lane = lane; c.par = 1; c.ps = P.d_stage; c.now = m;
+				c.head = head; c.tail = 0; c.burns = 0; c.rec_len = 0; c.tr_len = 0;
+				c.ev = 0; c.lseq = 0; c.rec_n = 0; c.tr_n = 0; c.ovf_base = -1;
+				for (int q = 0; q < LC_N; q++) c.lc[q] = 0;
+				while (true) {
+					int k = 0;
+					if (lane == 0) k = atomicAdd(&ctl->work, 1);
+					k = __shfl_sync(FULLMASK, k, 0);
+					if (k >= n_active) break;
+					int g = P.active[k];
+					int cnt = P.grp_cnt[g], off = P.grp_off[g];
+					if (cnt == 1) {
+						par_handle_event(c, P, seg_lo, P.grp_items[off], m);
+					} else if (cnt <= 32) {
+						int it = lane < cnt ? P.grp_items[off+lane] : 0x7fffffff;
+						// sort across lanes (rank = number of smaller items; items are unique)
+						int rank = 0;
+						for (int l = 0; l < 32; l++) rank += __shfl_sync(FULLMASK, it, l) < it;
+						int mine = 0;
+						for (int l = 0; l < 32; l++) { int r = __shfl_sync(FULLMASK, rank, l), v = __shfl_sync(FULLMASK, it, l); if (r == lane) mine = v; }
+						for (int j = 0; j < cnt; j++) {
+							int e = __shfl_sync(FULLMASK, mine, j);
+							par_handle_event(c, P, seg_lo, e, m);
+						}
+					} else {
+						warp_sort_global(P.grp_items+off, cnt, lane);
+						for (int j = 0; j < cnt; j++) par_handle_event(c, P, seg_lo, P.grp_items[off+j], m);
+					}
+					if (lane == 0) P.grp_cnt[g] = 0;                  // ready for the next segment
+				}
+				if (lane == 0) for (int q = 0; q < LC_N; q++) if (c.lc[q]) atomicAdd((unsigned long long *)&ctl->lc[q], c.lc[q]);
+			}
+			grid.sync();
+			// ---- F1: per-CTA sums over a contiguous chunk of the segment ----------------------------
+			const int per = (ns+gridDim.x-1)/gridDim.x;
+			const int c_lo = (int)blockIdx.x*per < ns ? (int)blockIdx.x*per : ns;
+			const int c_hi = c_lo+per < ns ? c_lo+per : ns;
+			{
+				u64 a = 0; unsigned r = 0, t = 0;
+				for (int e = c_lo+tid; e < c_hi; e += PAR_THREADS) { a += P.stage.ev_nins[e]; r += P.stage.ev_nrec[e]; t += P.stage.ev_ntr[e]; }
+				for (int d = 16; d; d >>= 1) { a += __shfl_xor_sync(FULLMASK, a, d); r += __shfl_xor_sync(FULLMASK, r, d); t += __shfl_xor_sync(FULLMASK, t, d); }
+				__syncthreads();
+				if (lane == 0) { sh_u[warp] = a; sh_r[warp] = r; sh_t[warp] = t; }
+				__syncthreads();
+				if (tid == 0) {
+					for (int w = 1; w < PAR_WARPS; w++) { a += sh_u[w]; r += sh_r[w]; t += sh_t[w]; }
+					P.cta_ins[blockIdx.x] = a; P.cta_rec[blockIdx.x] = r; P.cta_tr[blockIdx.x] = t;
+				}
+			}
+			grid.sync();
+			// ---- F2: chunk bases, capacity checks, ordered commit --------------------------------
+			{
+				u64 b_ins = 0, t_ins = 0; unsigned b_rec = 0, t_rec = 0, b_tr = 0, t_tr = 0;
+				for (int b = 0; b < (int)gridDim.x; b++) {
+					u64 a = P.cta_ins[b]; unsigned r = P.cta_rec[b], t = P.cta_tr[b];
+					if (b < (int)blockIdx.x) { b_ins += a; b_rec += r; b_tr += t; }
+					t_ins += a; t_rec += r; t_tr += t;
+				}
+				const u64 tail0 = st->tail, rec0 = st->rec_len, tr0 = st->tr_len;
+				if (tid == 0) sh_status = st->status;
+				__syncthreads();
+				bool okc = sh_status == 0;            // block-uniform: the CAS below only fires when okc is false anyway
+				if (tail0+t_ins-st->head > S.ring_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RING_FULL); }
+				if (S.want_rec && rec0+t_rec > S.rec_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RECORDS_FULL); }
+				if (leader) { ctl->tot_ins = t_ins; ctl->tot_rec = t_rec; ctl->tot_tr = t_tr; }
+				if (okc) {
+					// block-wide running scan over the chunk, PAR_THREADS events at a time
+					u64 run_ins = tail0+b_ins, run_rec = rec0+b_rec, run_tr = tr0+b_tr;
+					for (int e0 = c_lo; e0 < c_hi; e0 += PAR_THREADS) {
+						int e = e0+tid;
+						unsigned ni = 0, nr = 0, nt = 0;
+						if (e < c_hi) { ni = P.stage.ev_nins[e]; nr = P.stage.ev_nrec[e]; nt = P.stage.ev_ntr[e]; }
+						u64 xi = ni; unsigned xr = nr, xt = nt;
+						for (int d = 1; d < 32; d <<= 1) {
+							u64 yi = __shfl_up_sync(FULLMASK, xi, d); unsigned yr = __shfl_up_sync(FULLMASK, xr, d), yt = __shfl_up_sync(FULLMASK, xt, d);
+							if (lane >= d) { xi += yi; xr += yr; xt += yt; }
+						}
+						__syncthreads();
+						if (lane == 31) { sh_u[warp] = xi; sh_r[warp] = xr; sh_t[warp] = xt; }
+						if (tid == 0) sh_nbig = 0;
+						__syncthreads();
+						u64 wi = 0; unsigned wr = 0, wt = 0;
+						u64 tot_i = 0; unsigned tot_r = 0, tot_t = 0;
+						for (int w = 0; w < PAR_WARPS; w++) {
+							if (w < warp) { wi += sh_u[w]; wr += sh_r[w]; wt += sh_t[w]; }
+							tot_i += sh_u[w]; tot_r += sh_r[w]; tot_t += sh_t[w];
+						}
+						u64 my_seq = run_ins+wi+xi-ni, my_rec = run_rec+wr+xr-nr, my_tr = run_tr+wt+xt-nt;
+						if (e < c_hi) {
+							if (ni > 32) {                            // a full spread: copied by a whole warp below
+								int q = atomicAdd(&sh_nbig, 1);
+								sh_big[q] = e; sh_bseq[q] = my_seq; sh_brec[q] = my_rec; sh_btr[q] = my_tr;
+							} else par_commit_event(S, P.stage, e, my_seq, my_rec, my_tr, 0, 1);
+						}
+						__syncthreads();
+						int nbig = sh_nbig;
+						for (int q = warp; q < nbig; q += PAR_WARPS)
+							par_commit_event(S, P.stage, sh_big[q], sh_bseq[q], sh_brec[q], sh_btr[q], lane, 32);
+						run_ins += tot_i; run_rec += tot_r; run_tr += tot_t;
+					}
+				}
+			}
+			grid.sync();
+			if (leader) {
+				st->tail += ctl->tot_ins; st->burns += ctl->tot_ins;
+				st->rec_len += S.want_rec ? ctl->tot_rec : 0;
+				u64 ntr = st->tr_len+ctl->tot_tr;
+				st->tr_len = S.want_tr ? (ntr < S.tr_cap ? ntr : S.tr_cap) : 0;
+				st->cnt[NS_CNT_EVENTS] += ctl->lc[LC_EVENTS]; st->cnt[NS_CNT_SPEED_CHANGE] += ctl->lc[LC_SPEED_CHANGE];
+				st->cnt[NS_CNT_SOLVES] += ctl->lc[LC_SOLVES]; st->cnt[NS_CNT_FULL_SPREADS] += ctl->lc[LC_FULL_SPREADS];
+				st->cnt[NS_CNT_FLOW_VISITS] += ctl->lc[LC_FLOW_VISITS]; st->cnt[NS_CNT_PAR_EVENTS] += ctl->lc[LC_EVENTS];
+				st->cnt[NS_CNT_WAVES] += 1;
+				st->cnt[NS_CNT_SEQ] = st->tail;
+				for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
+				// next segment, clipped to the remaining event budget
+				u64 evn = st->cnt[NS_CNT_EVENTS];
+				u64 bud = ev_max ? (ev_max > evn ? ev_max-evn : 0) : ~0ull;
+				u64 lim = bud < (u64)P.seg_cap ? bud : (u64)P.seg_cap;
+				int nlo = seg_hi, left = nb-seg_hi;
+				ctl->seg_lo = nlo;
+				ctl->seg_hi = (left <= 0 || lim < PAR_MIN_BATCH) ? nlo : nlo+((u64)left < lim ? left : (int)lim);
+				ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0;
+				ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
+				*P.stage.ovf_top = 0;
+			}
+			grid.sync();
+		}
+		// whatever the parallel prefix left (event budget or an error) goes through the sequential
+		// path, which stops at the exact count and puts unhandled events back under the tile minima
+		if (ctl->seg_lo < nb && blockIdx.x == 0 && warp == 0) {
+			Ctx c; ctx_load(c, sp, lane);
+			c.now = m;
+			seq_process(c, m, ctl->seg_lo, nb, 0, 0, sc);
+			L0 st->cnt[NS_CNT_SEQ] = c.tail;
+			ctx_flush(c);
+		}
+	}
+}
+
+// ---------------------------------------------------------------- host launchers
 static int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){
 	k_init_groups<<<1, 32, 0, stream>>>(d_sim, 1);
 	(*launches)++;
 	return 0;
 }
 static int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){
-	k_run_seq<<<1, 32, 0, stream>>>(d_sim, d_scr, 1);
+	int per_sm = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run_par, PAR_THREADS, 0);
+	if (e != cudaSuccess) return (int)e;
+	if (per_sm < 1) return NS_E_ARG;
+	int grid = sm_count*per_sm;
+	if (grid > 4096) grid = 4096;
+	void *args[] = { (void *)&d_sim, (void *)&d_scr, (void *)&p };
+	e = cudaLaunchCooperativeKernel((void *)k_run_par, dim3(grid), dim3(PAR_THREADS), args, 0, stream);
+	if (e != cudaSuccess) return (int)e;
 	(*launches)++;
 	return 0;
 }

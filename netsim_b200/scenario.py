@@ -315,3 +315,74 @@ def random_small(seed: int, n_nodes: int = 8, n_flows: int = 12, relay: bool = F
                 groups[0].append(sched(len(groups) - 1, float(rng.choice([0.05, 1.0, 3.0]))))
                 break
     return _mk(caps, resources, copies, groups, ondone, seed=1 + seed % 7)
+
+
+def swarm_fast(n_peers: int = 100032, n_hubs: int = 320, n_catalogue: int = 64, seeds_per_peer: int = 8,
+               mean_strips: float = 9.0, max_strips: int = 32, hub_frac: float = 0.1, res_len: int = 600000,
+               seed: int = 12345, rand_seed: int = 1) -> Scenario:
+    """Vectorised `swarm()` for the 100k-peer / ~1M-flow config: same shape
+    (hubs hold the whole catalogue, peers seed `seeds_per_peer` entries and fetch one they lack in
+    1+Poisson(mean_strips) strips from distinct holders, ub/delay by time-zone distance), all flows
+    established at init like modules/p2p.c's init loop does for its first connections."""
+    rng = np.random.default_rng(seed)
+    n = n_hubs + n_peers
+    idx = np.arange(n)
+    is_hub = idx < n_hubs
+    tz = np.where(is_hub, _tz(idx, n_hubs), _tz(idx - n_hubs, n_peers))
+    mu = np.where(is_hub, 160000.0, 8000.0)
+    md = np.where(is_hub, 160000.0, 40000.0)
+    res = np.zeros(n_catalogue, dtype=RES_DTYPE)
+    res["owner"] = rng.integers(0, n_hubs, n_catalogue)
+    res["len"] = res_len
+    res["bit_rate"] = 2000
+    # every peer: a random permutation prefix of the catalogue -> seeds + the wanted entry
+    perm = np.argsort(rng.random((n_peers, n_catalogue)), axis=1)[:, :seeds_per_peer + 1]
+    seeds, want = perm[:, :seeds_per_peer], perm[:, seeds_per_peer]
+    hub_cp = np.array([(h, r) for r in range(n_catalogue) for h in range(n_hubs) if h != res["owner"][r]],
+                      dtype=np.int64).reshape(-1, 2)
+    peer_cp = np.stack([np.repeat(np.arange(n_peers) + n_hubs, seeds_per_peer), seeds.reshape(-1)], axis=1)
+    cp = np.zeros(len(hub_cp) + len(peer_cp), dtype=COPY_DTYPE)
+    cp["node"] = np.concatenate([hub_cp[:, 0], peer_cp[:, 0]])
+    cp["res"] = np.concatenate([hub_cp[:, 1], peer_cp[:, 1]])
+    # holders per catalogue entry
+    order = np.argsort(peer_cp[:, 1], kind="stable")
+    hold_nodes = peer_cp[order, 0]
+    hold_off = np.searchsorted(peer_cp[order, 1], np.arange(n_catalogue + 1))
+    k = np.minimum(max_strips, 1 + rng.poisson(mean_strips, n_peers))
+    kmax = int(k.max())
+    zipf_w = 1.0 / np.arange(1, n_hubs + 1)
+    zipf_w /= zipf_w.sum()
+    use_hub = rng.random((n_peers, kmax)) < hub_frac
+    hub_pick = rng.choice(n_hubs, size=(n_peers, kmax), p=zipf_w)
+    cnt = (hold_off[want + 1] - hold_off[want])
+    r_idx = (rng.random((n_peers, kmax)) * np.maximum(cnt, 1)[:, None]).astype(np.int64)
+    peer_pick = hold_nodes[np.minimum(hold_off[want][:, None] + r_idx, len(hold_nodes) - 1)]
+    src = np.where(use_hub | (cnt == 0)[:, None], hub_pick, peer_pick)
+    me = (np.arange(n_peers) + n_hubs)[:, None]
+    valid = (np.arange(kmax)[None, :] < k[:, None]) & (src != me)
+    # drop duplicate sources within a row (keep first occurrence)
+    srt = np.argsort(src, axis=1, kind="stable")
+    ss = np.take_along_axis(src, srt, axis=1)
+    dup_sorted = np.zeros_like(valid)
+    dup_sorted[:, 1:] = ss[:, 1:] == ss[:, :-1]
+    dup = np.zeros_like(valid)
+    np.put_along_axis(dup, srt, dup_sorted, axis=1)
+    # a duplicate is only a problem if the earlier twin is itself valid; being conservative is fine
+    valid &= ~dup
+    kk = valid.sum(axis=1)
+    rows, cols = np.nonzero(valid)
+    strip_no = (np.cumsum(valid, axis=1) - 1)[rows, cols]
+    strip = res_len // np.maximum(kk, 1)
+    ops = np.zeros(len(rows), dtype=OP_DTYPE)
+    ops["kind"] = OP_CREATE
+    ops["a"] = src[rows, cols]
+    ops["b"] = rows + n_hubs
+    ops["c"] = want[rows]
+    ops["start"] = strip_no * strip[rows]
+    ub, dl = _ub_delay(tz[ops["a"]], tz[ops["b"]])
+    ops["x"] = ub
+    ops["y"] = dl
+    sc = Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, [], {}, seed=rand_seed)
+    sc._ops = ops
+    sc._group_off = np.array([0, len(ops)], dtype="<i4")
+    return sc

@@ -1,0 +1,55 @@
+"""Stand-alone GPU probe: throughput of the engine on swarm scripts + record-stream digest vs the oracle."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from netsim_b200 import engine as E
+from netsim_b200 import scenario as S
+from oracle import pyoracle
+
+
+def probe(npeers, nhubs, max_events, modes, check=True, **kw):
+    t0 = time.time()
+    sc = S.swarm_fast(npeers, nhubs, **kw)
+    b = sc.to_bytes()
+    print(f"--- swarm {npeers}+{nhubs}: {sc.n_creates()} flows, script {len(b)>>20} MiB, gen {time.time()-t0:.1f}s", flush=True)
+    ref_hash = None
+    if check:
+        t0 = time.time()
+        o = pyoracle.Oracle(b, trace=False, records=True)
+        t1 = time.time()
+        o.run(max_events)
+        t2 = time.time()
+        co = o.counters()
+        ref_hash = E.stream_hash(o.records())
+        print(f"oracle: init {t1-t0:.2f}s run {t2-t1:.2f}s -> {co['events']/(t2-t1):.0f} ev/s; events {co['events']} solves {co['solves']} full {co['full_spreads']} visits {co['flow_visits']} seq {co['seq']}", flush=True)
+        o.close()
+    for mname, mode in modes:
+        t0 = time.time()
+        e = E.Engine(b, mode=mode, records=True)
+        t1 = time.time()
+        st = e.run(max_events)
+        t2 = time.time()
+        c = e.counters()
+        d = e.digest()
+        ok = (d["record_hash"] == ref_hash) if ref_hash is not None else None
+        print(f"{mname}: status {st} create+init {t1-t0:.2f}s run wall {t2-t1:.3f}s device {e.device_ms:.1f} ms -> {c['events']/(e.device_ms/1e3):.0f} ev/s; "
+              f"events {c['events']} par {c['par_events']} batches {c['batches']} maxbatch {c['max_batch']} segs {c['waves']} records {d['record_bytes']} hash_ok {ok}", flush=True)
+        if check:
+            for k in ("events", "solves", "full_spreads", "flow_visits", "seq", "draws"):
+                if c[k] != co[k]:
+                    print("   COUNTER MISMATCH", k, c[k], co[k])
+        e.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "small"
+    both = [("auto", E.MODE_AUTO), ("seq", E.MODE_SEQ)]
+    if which == "small":
+        probe(2000, 8, 500000, both, n_catalogue=16, seeds_per_peer=4)
+        probe(10000, 32, 2000000, both, n_catalogue=32, seeds_per_peer=6)
+    elif which == "mid":
+        probe(10000, 32, 5000000, [("auto", E.MODE_AUTO)], n_catalogue=32, seeds_per_peer=6)
+    elif which == "big":
+        probe(100032, 320, int(sys.argv[2]) if len(sys.argv) > 2 else 5000000, [("auto", E.MODE_AUTO)], check=len(sys.argv) > 3)
