@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py — netsim flow/event hot path on B200: simulated events/s and rate solves/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2]): a p2p swarm of 100 032 peers + 320 hubs with ~1M concurrent
+flows, one simulation per GPU (generator netsim_b200/scenario.py:swarm_fast).
+A "step" is one window of `--events-per-step` simulated events handled by ONE launch of the
+persistent engine kernel (ns_dev_run through the C ABI).  With N>1 every rank simulates its own
+seeded replica of the swarm (weak scaling, no data-path collective: a single simulation is globally
+coupled); the per-replica digests are gathered with one NCCL all_gather.
+
+--impl reference times the UNMODIFIED reference core (oracle/_ref, compiled from /root/reference
+by oracle/Makefile) on the same script on one host core (the reference is single-threaded).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "simulated events/s (p2p swarm, 100k peers / ~1M flows, one simulation per GPU)"
+UNIT = "events/s"
+
+# algorithmic bytes per unit of work (SURVEY.md §8d byte model)
+B_SOLVE = 56          # node {total,max,usage} + flow {ub,speed} read, speed+usage written
+B_VISIT = 20          # per flow visited by a full-spread pass: ub 8 + speed 8 + index 4 (lower bound)
+B_INSERT = 32         # one emitted event {time, seq, flow, dir, speed}
+B_RETIME = 92 + 120   # completion re-time of one flow + the byte-progress update of its two ranges
+
+
+def workload(args, rank):
+    from netsim_b200 import scenario as S
+    return S.swarm_fast(args.peers, args.hubs, n_catalogue=64, seeds_per_peer=8, mean_strips=9.0,
+                        hub_frac=args.hub_frac, res_len=600000, seed=12345 + rank, rand_seed=1 + rank)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args, sc_bytes, steps, warmup, events_per_step):
+    """The reference core on this script, one process / one core; wall clock per window from the
+    replay module (oracle/ref_scenario.c, NS_STEP_EVENTS)."""
+    from oracle import refrun
+    if not refrun.available():
+        return None
+    with tempfile.TemporaryDirectory(prefix="nsbench") as d:
+        path = os.path.join(d, "sc.bin")
+        with open(path, "wb") as f:
+            f.write(sc_bytes)
+        env = dict(os.environ, NS_SCENARIO=path, NS_RECORD=os.path.join(d, "rec"), NS_STATS=os.path.join(d, "stats.json"),
+                   NS_MAX_EVENTS=str((steps + warmup) * events_per_step), NS_STEP_EVENTS=str(events_per_step))
+        t0 = time.time()
+        p = subprocess.run([os.path.join(refrun.REF, "netsim"), os.path.join(refrun.REF, "modules", "scenario")],
+                           cwd=d, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=args.ref_timeout)
+        wall = time.time() - t0
+        if p.returncode != 0:
+            return {"error": f"reference exited {p.returncode}: {p.stderr.decode(errors='replace')[-200:]}"}
+        st = json.load(open(os.path.join(d, "stats.json")))
+        rec_bytes = os.path.getsize(os.path.join(d, "rec"))
+    ts = st["step_times"]
+    done = len(ts)
+    if done <= warmup:
+        return {"error": f"reference handled only {st['events']} events"}
+    t_w = ts[warmup - 1] if warmup else 0.0
+    k = done - warmup
+    sec = ts[-1] - t_w
+    return {"events": k * events_per_step, "seconds": sec, "events_per_s": k * events_per_step / sec, "steps": k,
+            "init_seconds": wall - st["loop_seconds"], "record_file_bytes": rec_bytes, "total_events": st["events"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--peers", type=int, default=100032)
+    ap.add_argument("--hubs", type=int, default=320)
+    ap.add_argument("--hub-frac", type=float, default=0.02)
+    ap.add_argument("--events-per-step", type=int, default=2000000)
+    ap.add_argument("--ref-events-per-step", type=int, default=150000)
+    ap.add_argument("--ref-timeout", type=float, default=1500.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"p2p swarm script: {args.peers} peers + {args.hubs} hubs, ~{args.peers * 10 // 1000}k flows established at init, "
+                          f"records on; step = window of events",
+              "peers": args.peers, "hubs": args.hubs, "hub_frac": args.hub_frac,
+              "working_set": "node/flow/range tables + pending-event ring (several GB) exceed the 126 MB L2; no explicit L2 flush"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sc = workload(args, 0)
+        eps = args.ref_events_per_step
+        r = run_reference(args, sc.to_bytes(), args.steps, args.warmup, eps)
+        if r is None or "error" in r:
+            print(json.dumps({"impl": "reference", "unavailable": (r or {}).get("error", "oracle/_ref not built")}))
+            return 0
+        val = r["events_per_s"]
+        config["events_per_step"] = eps
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+                "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
+                                 "sample": f"{r['steps']} windows of {eps} events after {args.warmup} warm-up windows of the same script; "
+                                           f"unmodified reference core, single-threaded by design; init {r['init_seconds']:.1f}s untimed"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from netsim_b200 import engine as E
+
+    if E.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sc = workload(args, rank)
+    sc_bytes = sc.to_bytes()
+    eps = args.events_per_step
+    total_steps = args.steps + args.warmup
+    t0 = time.time()
+    rec_cap = int((total_steps * eps + 4 * sc.n_creates()) * 48 + (64 << 20))
+    eng = E.Engine(sc_bytes, device=local_rank, mode=E.MODE_AUTO, records=True, record_cap=rec_cap)
+    create_s = time.time() - t0
+    c_init = eng.counters()
+    import ctypes as C
+    pinned = torch.empty(int(eps * 48 + (16 << 20)), dtype=torch.uint8).pin_memory()
+    rec_off = eng.digest()["record_bytes"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        """one window through the C ABI with host buffers: control word in, the window's records out"""
+        nonlocal rec_off
+        t_a = time.perf_counter()
+        rc = eng.run((i + 1) * eps)
+        if rc != 0:
+            raise SystemExit(f"engine status {rc}: {E.strerror(rc)}")
+        dev_ms = eng.device_ms
+        n, tot = C.c_size_t(), C.c_size_t()
+        E.lib().ns_dev_records(eng.h, C.c_void_p(pinned.data_ptr()), pinned.numel(), rec_off, C.byref(n), C.byref(tot))
+        got = n.value
+        rec_off += got
+        return dev_ms, time.perf_counter() - t_a, got
+
+    for i in range(args.warmup):
+        step(i)
+    c0 = eng.counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms_sum, wall_sum, d2h = 0.0, 0.0, 0
+    t_region = time.perf_counter()
+    for i in range(args.warmup, total_steps):
+        dm, w, got = step(i)
+        dev_ms_sum += dm
+        wall_sum += w
+        d2h += got
+    barrier()
+    t_region = time.perf_counter() - t_region
+    sampler.stop_flag = True
+    c1 = eng.counters()
+    dig = eng.digest()
+    d = {k: c1[k] - c0[k] for k in c1}
+    events = d["events"]
+
+    # max over ranks of the timed quantities, sum of the work
+    vals = torch.tensor([dev_ms_sum, wall_sum, t_region, float(events), float(d["solves"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        digs = torch.zeros(world, 4, dtype=torch.int64, device="cuda")
+        mine = torch.tensor([dig["events"], dig["record_bytes"], dig["record_hash"] & 0x7FFFFFFFFFFFFFFF, dig["status"]],
+                            dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(digs, mine)          # the only cross-GPU exchange: per-replica digests
+        dev_ms_max, wall_max, region_max = mx[0].item(), mx[1].item(), mx[2].item()
+        events_all, solves_all = sm[3].item(), sm[4].item()
+    else:
+        dev_ms_max, wall_max, region_max = dev_ms_sum, wall_sum, t_region
+        events_all, solves_all = float(events), float(d["solves"])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = events_all / (dev_ms_max / 1e3)
+    alg_bytes = B_SOLVE * d["solves"] + B_VISIT * d["flow_visits"] + B_INSERT * d["seq"] + d2h + B_RETIME * d["retimes"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (dev_ms_sum / 1e3) / 1e9
+    config.update({"events_per_step": eps, "flows": c_init["creates"], "create_init_s": round(create_s, 2),
+                   "pending_events_at_end": c1["seq"] - c1["events"], "batches_timed": d["batches"], "max_batch": c1["max_batch"],
+                   "parallel_fraction": d["par_events"] / max(1, events), "solves_per_s": solves_all / (dev_ms_max / 1e3),
+                   "full_spreads": d["full_spreads"], "flow_visits": d["flow_visits"], "record_hash": dig["record_hash"],
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"})
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "ours", "config": config,
+            "clocks": sampler.summary(),
+            "e2e": {"value": events_all / wall_max, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": d2h // max(1, args.steps),
+                    "note": "wall clock per window through ns_dev_run + ns_dev_records into pinned host memory; the script upload "
+                            "and init (create_init_s) happen once before the windows, like the reference's untimed module init"},
+            "gpu_launches": args.steps * 1 + 1,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_run_par (persistent, one launch per window)", "algorithmic_bytes_per_launch": alg_bytes / args.steps}}
+    if not args.no_cpu_baseline and world == 1:
+        r = run_reference(args, sc_bytes, 2, 1, args.ref_events_per_step)
+        if r and "error" not in r:
+            line["cpu_baseline"] = {"value": r["events_per_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": f"unmodified reference core (oracle/_ref) on the same script: {r['steps']} windows of "
+                                              f"{args.ref_events_per_step} events after 1 warm-up window; init {r['init_seconds']:.1f}s untimed"}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": (r or {}).get("error", "oracle/_ref missing")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,7 +55,9 @@ enum ns_counter {
 	NS_CNT_FLOW_DONE, NS_CNT_DRAIN, NS_CNT_THROTTLE, NS_CNT_USER, NS_CNT_CREATES, NS_CNT_CLOSES,
 	NS_CNT_DRAWS, NS_CNT_SEQ, NS_CNT_LIVE_FLOWS, NS_CNT_PEAK_FLOWS, NS_CNT_BATCHES,
 	NS_CNT_PAR_EVENTS,   /* events handled by the grid-parallel path */
-	NS_CNT_MAX_BATCH, NS_CNT_WAVES, NS_CNT_RESERVED, NS_CNT_COUNT
+	NS_CNT_MAX_BATCH, NS_CNT_WAVES,
+	NS_CNT_RETIMES,     /* range_calc_and_requeue_events invocations (range.c:16) */
+	NS_CNT_COUNT
 };
 
 enum ns_mode {

@@ -24,7 +24,7 @@ struct ParStage {
 	uint8_t *st_rec; ns_trace_row32 *st_tr;
 	unsigned *ev_nins; long long *ev_ovf; uint8_t *ev_nrec, *ev_ntr;
 };
-enum { LC_EVENTS = 0, LC_SPEED_CHANGE, LC_SOLVES, LC_FULL_SPREADS, LC_FLOW_VISITS, LC_N };
+enum { LC_EVENTS = 0, LC_SPEED_CHANGE, LC_SOLVES, LC_FULL_SPREADS, LC_FLOW_VISITS, LC_RETIMES, LC_N };
 
 struct Ctx {
 	const Sim *S; SimState *st; int lane;
@@ -55,7 +55,7 @@ __device__ __forceinline__ void set_status(Ctx &c, int s){
 }
 __device__ __forceinline__ int lc_slot(int idx){
 	return idx == NS_CNT_EVENTS ? LC_EVENTS : idx == NS_CNT_SPEED_CHANGE ? LC_SPEED_CHANGE : idx == NS_CNT_SOLVES ? LC_SOLVES :
-	       idx == NS_CNT_FULL_SPREADS ? LC_FULL_SPREADS : LC_FLOW_VISITS;
+	       idx == NS_CNT_FULL_SPREADS ? LC_FULL_SPREADS : idx == NS_CNT_RETIMES ? LC_RETIMES : LC_FLOW_VISITS;
 }
 __device__ __forceinline__ void cnt_add(Ctx &c, int idx, u64 n){
 	if (c.par) { c.lc[lc_slot(idx)] += n; return; }
@@ -292,6 +292,7 @@ __device__ __forceinline__ void retime_commit_1(Ctx &c, int f, const Retime &p, 
 }
 __device__ __forceinline__ void range_calc_and_requeue_events(Ctx &c, int f){
 	if (f < 0) return;
+	cnt_add(c, NS_CNT_RETIMES, 1);
 	Retime p;
 	p.add_drain = p.add_done = 0;
 	L0 retime_plan_1(*c.S, c.st, f, c.now, p);
@@ -419,6 +420,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 			if (!ok) { if (c.st->status == 0) c.st->status = isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; }
 			if (dir == RCV && inc2) retime_plan_1(S, c.st, nf, c.now, rp);   // :193-194
 		}
+		if (dir == RCV && inc2) cnt_add(c, NS_CNT_RETIMES, __popc(__ballot_sync(FULLMASK, adj)));
 		int k = ok+rp.add_drain+rp.add_done;
 		int incl = k;
 		#pragma unroll

@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 				st->cnt[NS_CNT_EVENTS] += ctl->lc[LC_EVENTS]; st->cnt[NS_CNT_SPEED_CHANGE] += ctl->lc[LC_SPEED_CHANGE];
 				st->cnt[NS_CNT_SOLVES] += ctl->lc[LC_SOLVES]; st->cnt[NS_CNT_FULL_SPREADS] += ctl->lc[LC_FULL_SPREADS];
 				st->cnt[NS_CNT_FLOW_VISITS] += ctl->lc[LC_FLOW_VISITS]; st->cnt[NS_CNT_PAR_EVENTS] += ctl->lc[LC_EVENTS];
+				st->cnt[NS_CNT_RETIMES] += ctl->lc[LC_RETIMES];
 				st->cnt[NS_CNT_WAVES] += 1;
 				st->cnt[NS_CNT_SEQ] = st->tail;
 				for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;

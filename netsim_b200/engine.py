@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libnetsim_b200.so")
 
 COUNTERS = ["events", "solves", "full_spreads", "flow_visits", "speed_change", "flow_done", "drain",
             "throttle", "user", "creates", "closes", "draws", "seq", "live_flows", "peak_flows",
-            "batches", "par_events", "max_batch", "waves", "reserved"]
+            "batches", "par_events", "max_batch", "waves", "retimes"]
 MODE_AUTO, MODE_SEQ = 0, 1
 TRACE_DTYPE = np.dtype([("type", "<u4"), ("ord", "<u4"), ("time", "<f8"), ("v0", "<f8"), ("v1", "<f8")])
 

@@ -12,7 +12,8 @@
  *
  * Environment: NS_SCENARIO (input file), NS_RECORD (record file, default "ns_record"),
  * NS_TRACE (optional binary trace: 32-byte rows {u32 type,u32 ord,f64 time,f64 v0,f64 v1}),
- * NS_MAX_EVENTS (stop after that many popped events), NS_STATS (json with counts and timing).
+ * NS_MAX_EVENTS (stop after that many popped events), NS_STEP_EVENTS (wall clock every that many
+ * events, for bench.py's reference arm), NS_STATS (json with counts and timing).
  */
 #define _GNU_SOURCE
 #include <unistd.h>
@@ -51,6 +52,7 @@ static struct fl_ent *by_ptr;
 static double cur_ub, cur_delay;
 static FILE *trace;
 static uint64_t n_events, max_events, n_by_type[LAST_EVENT], n_create, n_close, n_throttle_taken;
+static uint64_t step_events; static double *step_t; static int n_steps, cap_steps;
 static struct timespec t_init_done;
 static const char *stats_path;
 static struct sim_state *S;
@@ -122,9 +124,14 @@ static void run_group(int g, struct sim_state *s){
 	}
 }
 
+static double since_init(void);
 static void count_event(struct event *e, struct sim_state *s){
 	n_events++;
 	n_by_type[e->type]++;
+	if (step_events && n_events % step_events == 0) {         /* NS_STEP_EVENTS: wall clock per window */
+		if (n_steps == cap_steps) { cap_steps = cap_steps ? cap_steps*2 : 64; step_t = realloc(step_t, cap_steps*sizeof *step_t); }
+		step_t[n_steps++] = since_init();
+	}
 	if (max_events && n_events >= max_events)
 		sim_end(s);
 }
@@ -177,10 +184,14 @@ static void on_drain(struct event *e, struct sim_state *s){
 	count_event(e, s);
 }
 
-static void finish(void){
+static double since_init(void){
 	struct timespec t1;
 	clock_gettime(CLOCK_MONOTONIC, &t1);
-	double el = (t1.tv_sec-t_init_done.tv_sec)+1e-9*(t1.tv_nsec-t_init_done.tv_nsec);
+	return (t1.tv_sec-t_init_done.tv_sec)+1e-9*(t1.tv_nsec-t_init_done.tv_nsec);
+}
+
+static void finish(void){
+	double el = since_init();
 	if (trace) fclose(trace);
 	if (!stats_path) return;
 	FILE *f = fopen(stats_path, "w");
@@ -189,11 +200,13 @@ static void finish(void){
 	 * (flow.c:318), 2 per close (flow.c:249-250); throttle solves are counted by the oracle only. */
 	fprintf(f, "{\"events\": %llu, \"speed_change\": %llu, \"flow_done\": %llu, \"drain\": %llu, "
 		   "\"throttle\": %llu, \"user\": %llu, \"creates\": %llu, \"closes\": %llu, "
-		   "\"loop_seconds\": %.9f, \"now\": %.17g}\n",
+		   "\"loop_seconds\": %.9f, \"now\": %.17g, \"step_times\": [",
 		(unsigned long long)n_events, (unsigned long long)n_by_type[SPEED_CHANGE],
 		(unsigned long long)n_by_type[FLOW_DONE], (unsigned long long)n_by_type[FLOW_DRAIN],
 		(unsigned long long)n_by_type[FLOW_SPEED_THROTTLE], (unsigned long long)n_by_type[USER],
 		(unsigned long long)n_create, (unsigned long long)n_close, el, S ? S->now : 0.0);
+	for (int i = 0; i < n_steps; i++) fprintf(f, "%s%.9f", i ? ", " : "", step_t[i]);
+	fprintf(f, "]}\n");
 	fclose(f);
 }
 
@@ -206,6 +219,7 @@ void scenario_init(struct sim_state *s){
 	if (!path) { fprintf(stderr, "scenario: NS_SCENARIO not set\n"); exit(2); }
 	if (!rec) rec = "ns_record";
 	if (me) max_events = strtoull(me, NULL, 10);
+	if (getenv("NS_STEP_EVENTS")) step_events = strtoull(getenv("NS_STEP_EVENTS"), NULL, 10);
 	FILE *f = fopen(path, "rb");
 	if (!f) { perror(path); exit(2); }
 	if (fread(&H, sizeof H, 1, f) != 1 || H.magic != NS_SC_MAGIC || H.version != NS_SC_VERSION) {

@@ -52,4 +52,4 @@ if __name__ == "__main__":
     elif which == "mid":
         probe(10000, 32, 5000000, [("auto", E.MODE_AUTO)], n_catalogue=32, seeds_per_peer=6)
     elif which == "big":
-        probe(100032, 320, int(sys.argv[2]) if len(sys.argv) > 2 else 5000000, [("auto", E.MODE_AUTO)], check=len(sys.argv) > 3)
+        probe(100032, 320, int(sys.argv[2]) if len(sys.argv) > 2 else 5000000, [("auto", E.MODE_AUTO)], check=len(sys.argv) > 3, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
