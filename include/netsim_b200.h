@@ -105,6 +105,9 @@ int  ns_dev_trace(ns_dev *d, struct ns_trace_row32 *dst, size_t cap_rows, size_t
  * total_bwupbound[0], total_bwupbound[1]} */
 int  ns_dev_flow_state(ns_dev *d, double *out4, size_t max_flows, size_t *n);
 int  ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size_t *n);
+/* leader-thread nanoseconds per engine phase of the grid-parallel path:
+ * {argmin, extract, sequential, group, solve, commit} — a profiling aid */
+int  ns_dev_phase_ns(ns_dev *d, uint64_t out[16]);
 uint64_t ns_dev_launches(ns_dev *d);
 void ns_dev_destroy(ns_dev *d);
 

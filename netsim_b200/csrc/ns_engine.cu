@@ -444,6 +444,12 @@ extern "C" int ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size
 	if (n) *n = k;
 	return 0;
 }
+extern "C" int ns_dev_phase_ns(ns_dev *d, uint64_t out[16]){
+	if (!d || !out) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	for (int i = 0; i < 16; i++) out[i] = st.phase_ns[i];
+	return 0;
+}
 extern "C" uint64_t ns_dev_launches(ns_dev *d){ return d ? d->launches : 0; }
 extern "C" void ns_dev_destroy(ns_dev *d){
 	if (!d) return;

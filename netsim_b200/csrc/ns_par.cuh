@@ -24,6 +24,9 @@
 namespace cgp = cooperative_groups;
 
 #define PAR_THREADS 256
+#ifndef PAR_MIN_BLOCKS
+#define PAR_MIN_BLOCKS 1       // CTAs per SM the persistent kernel is compiled for (register budget)
+#endif
 #define PAR_WARPS (PAR_THREADS/32)
 #define PAR_MIN_BATCH 48          // smaller batches are cheaper on the single-warp path
 
@@ -156,8 +159,13 @@ __device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &p
 	}
 }
 
+__device__ __forceinline__ u64 gtimer(){ u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// phase ids for SimState::phase_ns
+enum { PH_ARGMIN = 0, PH_EXTRACT, PH_SEQ, PH_GROUP, PH_SOLVE, PH_COMMIT, PH_TAIL, PH_KERNEL, PH_N };
+#define PHASE_MARK(id) do { if (leader) { u64 t_ = gtimer(); st->phase_ns[id] += t_-t_ph; t_ph = t_; } } while (0)
+
 // ---------------------------------------------------------------- the persistent kernel
-__global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const SeqScratch *scrp, ParScratch P){
+__global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const Sim *sp, const SeqScratch *scrp, ParScratch P){
 	cgp::grid_group grid = cgp::this_grid();
 	const Sim &S = *sp;
 	SimState *st = S.st;
@@ -173,6 +181,8 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 	const u64 gtid = (u64)blockIdx.x*PAR_THREADS+tid, gth = (u64)gridDim.x*PAR_THREADS;
 	const u64 tmask = (u64)S.n_ring_tiles-1, smask = S.ring_cap-1;
 	const bool leader = blockIdx.x == 0 && tid == 0;
+	u64 t_ph = gtimer();
+	const u64 t_kernel0 = t_ph;
 
 	while (true) {
 		// ---- A: argmin over tile minima ------------------------------------------------------
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 			if (tid == 0 && m != NS_INF) atomicMin((unsigned long long *)&ctl->tmin_bits, (u64)__double_as_longlong(m));
 		}
 		grid.sync();
+		PHASE_MARK(PH_ARGMIN);
 		const u64 mb = ctl->tmin_bits;
 		if (mb == ~0ull) break;                                       // queue empty
 		const double m = __longlong_as_double((long long)mb);
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 			st->head = fl == ~0ull ? ((tail >> NS_TILE_SHIFT) << NS_TILE_SHIFT) : (fl << NS_TILE_SHIFT);
 		}
 		grid.sync();
+		PHASE_MARK(PH_EXTRACT);
 		if (nb+nl == 0) continue;                                     // only stale lower bounds surfaced
 		// ---- C: legality --------------------------------------------------------------------
 		// (a run bounded by max_events must stop at an exact event count: the parallel prefix is
@@ -274,6 +286,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 				L0 st->cnt[NS_CNT_SEQ] = c.tail;
 				ctx_flush(c);
 			}
+			PHASE_MARK(PH_SEQ);
 			continue;                                                 // next iteration starts with a grid.sync
 		}
 		if (leader) {
@@ -323,6 +336,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 				if (g >= 0) P.grp_items[P.grp_off[g]+atomicAdd(&P.grp_fill[g], 1)] = (int)e;
 			}
 			grid.sync();
+			PHASE_MARK(PH_GROUP);
 			// ---- E: one warp per group, events in sequence order ----------------------------------
 			{
 				Ctx c;
@@ -359,6 +373,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 				if (lane == 0) for (int q = 0; q < LC_N; q++) if (c.lc[q]) atomicAdd((unsigned long long *)&ctl->lc[q], c.lc[q]);
 			}
 			grid.sync();
+			PHASE_MARK(PH_SOLVE);
 			// ---- F1: per-CTA sums over a contiguous chunk of the segment ----------------------------
 			const int per = (ns+gridDim.x-1)/gridDim.x;
 			const int c_lo = (int)blockIdx.x*per < ns ? (int)blockIdx.x*per : ns;
@@ -453,17 +468,30 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_par(const Sim *sp, const
 				*P.stage.ovf_top = 0;
 			}
 			grid.sync();
+			PHASE_MARK(PH_COMMIT);
 		}
-		// whatever the parallel prefix left (event budget or an error) goes through the sequential
-		// path, which stops at the exact count and puts unhandled events back under the tile minima
-		if (ctl->seg_lo < nb && blockIdx.x == 0 && warp == 0) {
-			Ctx c; ctx_load(c, sp, lane);
-			c.now = m;
-			seq_process(c, m, ctl->seg_lo, nb, 0, 0, sc);
-			L0 st->cnt[NS_CNT_SEQ] = c.tail;
-			ctx_flush(c);
+		// whatever the parallel prefix left goes back under the tile minima (event budget exhausted:
+		// the whole grid lowers one minimum per touched tile) or, if events were cancelled and budget
+		// remains, through the sequential path, which stops at the exact count
+		if (ctl->seg_lo < nb) {
+			const int lo = ctl->seg_lo;
+			const u64 evn = st->cnt[NS_CNT_EVENTS];
+			if (st->status == 0 && ev_max && evn >= ev_max) {
+				for (u64 k = lo+gtid; k < (u64)nb; k += gth) {
+					u64 tl = S.b_seq[k] >> NS_TILE_SHIFT;
+					if (k == (u64)lo || (S.b_seq[k-1] >> NS_TILE_SHIFT) != tl) tmin_lower(&S.q_tmin[tl & tmask], m);
+				}
+			} else if (blockIdx.x == 0 && warp == 0) {
+				Ctx c; ctx_load(c, sp, lane);
+				c.now = m;
+				seq_process(c, m, lo, nb, 0, 0, sc);
+				L0 st->cnt[NS_CNT_SEQ] = c.tail;
+				ctx_flush(c);
+			}
+			PHASE_MARK(PH_TAIL);
 		}
 	}
+	if (leader) { u64 t_ = gtimer(); st->phase_ns[PH_TAIL] += t_-t_ph; st->phase_ns[PH_KERNEL] += t_-t_kernel0; }
 }
 
 // ---------------------------------------------------------------- host launchers

@@ -44,6 +44,7 @@ struct SimState {                 // mutable scalars of one simulation
 	int adj_top, pad1;
 	u64 max_events;
 	u64 seed;
+	u64 phase_ns[16];             // leader-thread wall time per engine phase (profiling aid)
 };
 
 struct Sim {

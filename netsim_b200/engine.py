@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnetsim_b200.so")
+LIB_PATH = os.environ.get("NS_LIB") or os.path.join(HERE, "libnetsim_b200.so")
 
 COUNTERS = ["events", "solves", "full_spreads", "flow_visits", "speed_change", "flow_done", "drain",
             "throttle", "user", "creates", "closes", "draws", "seq", "live_flows", "peak_flows",
@@ -67,6 +67,7 @@ def lib():
         L.ns_dev_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_flow_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_node_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ns_dev_phase_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ns_dev_launches.restype = C.c_uint64
         L.ns_dev_launches.argtypes = [C.c_void_p]
         L.ns_dev_destroy.argtypes = [C.c_void_p]
@@ -177,6 +178,12 @@ class Engine:
         if rc:
             raise NsError(rc, "ns_dev_node_state")
         return out[:n.value]
+
+    def phase_ms(self) -> dict:
+        a = (C.c_uint64 * 16)()
+        self.L.ns_dev_phase_ns(self.h, a)
+        names = ["argmin", "extract", "sequential", "group", "solve", "commit", "tail", "kernel"]
+        return {n: a[i] / 1e6 for i, n in enumerate(names)}
 
     @property
     def launches(self) -> int:

@@ -36,6 +36,7 @@ def probe(npeers, nhubs, max_events, modes, check=True, **kw):
         ok = (d["record_hash"] == ref_hash) if ref_hash is not None else None
         print(f"{mname}: status {st} create+init {t1-t0:.2f}s run wall {t2-t1:.3f}s device {e.device_ms:.1f} ms -> {c['events']/(e.device_ms/1e3):.0f} ev/s; "
               f"events {c['events']} par {c['par_events']} batches {c['batches']} maxbatch {c['max_batch']} segs {c['waves']} records {d['record_bytes']} hash_ok {ok}", flush=True)
+        print('   phases(ms):', {k: round(v, 1) for k, v in e.phase_ms().items()}, flush=True)
         if check:
             for k in ("events", "solves", "full_spreads", "flow_visits", "seq", "draws"):
                 if c[k] != co[k]:
@@ -51,5 +52,17 @@ if __name__ == "__main__":
         probe(10000, 32, 2000000, both, n_catalogue=32, seeds_per_peer=6)
     elif which == "mid":
         probe(10000, 32, 5000000, [("auto", E.MODE_AUTO)], n_catalogue=32, seeds_per_peer=6)
+    elif which == "windows":
+        sc = S.swarm_fast(100032, 320, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
+        e = E.Engine(sc.to_bytes(), mode=E.MODE_AUTO, records=True, record_cap=4 << 30)
+        last = {k: 0.0 for k in e.phase_ms()}
+        for i in range(1, 11):
+            t0 = time.time()
+            e.run(i * 2000000)
+            w = time.time() - t0
+            ph = e.phase_ms()
+            print(f"window {i}: device {e.device_ms:.1f} ms wall {w*1e3:.1f} ms phases", {k: round(ph[k] - last[k], 1) for k in ph}, flush=True)
+            last = ph
+        e.close()
     elif which == "big":
         probe(100032, 320, int(sys.argv[2]) if len(sys.argv) > 2 else 5000000, [("auto", E.MODE_AUTO)], check=len(sys.argv) > 3, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
