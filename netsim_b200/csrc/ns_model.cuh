@@ -32,14 +32,16 @@ struct Ctx {
 	u64 head, tail;        // ring window, cached in registers (flushed by ctx_flush)
 	u64 burns, rec_len, tr_len;
 	int par;               // 1 inside the grid-parallel path: emissions are staged
+	int scalar;            // 1 when ONE thread runs the handler alone (O(1) solves, ns_par.cuh phase E1)
 	const ParStage *ps; unsigned ev, lseq, rec_n, tr_n; long long ovf_base;
 	u64 lc[LC_N];
 };
 
-#define L0 if (c.lane == 0)
+#define L0 if (c.scalar || c.lane == 0)
+#define WSYNC() do { if (!c.scalar) __syncwarp(); } while (0)
 
 __device__ __forceinline__ void ctx_load(Ctx &c, const Sim *S, int lane){
-	c.S = S; c.st = S->st; c.lane = lane; c.par = 0; c.ps = nullptr;
+	c.S = S; c.st = S->st; c.lane = lane; c.par = 0; c.scalar = 0; c.ps = nullptr;
 	c.now = c.st->now; c.head = c.st->head; c.tail = c.st->tail; c.burns = c.st->burns;
 	c.rec_len = c.st->rec_len; c.tr_len = c.st->tr_len;
 }
@@ -48,7 +50,7 @@ __device__ __forceinline__ void ctx_flush(Ctx &c){
 		c.st->now = c.now; c.st->head = c.head; c.st->tail = c.tail; c.st->burns = c.burns;
 		c.st->rec_len = c.rec_len; c.st->tr_len = c.tr_len;
 	}
-	__syncwarp();
+	WSYNC();
 }
 __device__ __forceinline__ void set_status(Ctx &c, int s){
 	L0 { atomicCAS(&c.st->status, 0, s); }
@@ -228,13 +230,15 @@ __device__ __forceinline__ void flow_range_update(Ctx &c, int f){
 	int sr = S.f_srng[f], dr = S.f_drng[f];
 	if (sr < 0 || dr < 0) { set_status(c, NS_E_NULL_RANGE); return; }
 	L0 { range_update_1(S, sr, c.now); range_update_1(S, dr, c.now); }
-	__syncwarp();
+	WSYNC();
 }
 
 // range_calc_and_requeue_events, range.c:16-79, split into a per-thread "plan" (all arithmetic and
 // range updates, no sequence numbers) and a "commit" so that the victims of one full spread can be
 // re-timed by different lanes while their event_add order stays the list order.
 struct Retime { double drain_t, done_t; int add_drain, add_done; };
+#define SP_U1 8     // chunks of 32 flows in flight in pass 1 of a full spread
+#define SP_U2 4     // ... in pass 2
 
 __device__ __forceinline__ void retime_plan_1(const Sim &S, SimState *st, int f, double now, Retime &p){
 	p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
@@ -296,14 +300,16 @@ __device__ __forceinline__ void range_calc_and_requeue_events(Ctx &c, int f){
 	Retime p;
 	p.add_drain = p.add_done = 0;
 	L0 retime_plan_1(*c.S, c.st, f, c.now, p);
-	p.add_drain = __shfl_sync(FULLMASK, p.add_drain, 0);
-	p.add_done = __shfl_sync(FULLMASK, p.add_done, 0);
+	if (!c.scalar) {
+		p.add_drain = __shfl_sync(FULLMASK, p.add_drain, 0);
+		p.add_done = __shfl_sync(FULLMASK, p.add_done, 0);
+	}
 	int n = p.add_drain+p.add_done;
 	if (n) {
 		u64 seq = seq_reserve(c, n);
 		L0 { if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) retime_commit_1(c, f, p, seq); }
 	}
-	__syncwarp();
+	WSYNC();
 }
 // range_update_consumer_events, range.h:65-69
 __device__ __forceinline__ void range_update_consumer_events(Ctx &c, int r){
@@ -335,7 +341,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 		double u = used+amount;
 		L0 S.n_usage[dir][n] = u;
 		write_usage(c, dir, n, u);
-		__syncwarp();
+		WSYNC();
 		return;
 	}
 	if (total < mx+NS_EPS) {                                          // :94-109
@@ -343,7 +349,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 			double u = used+amount;
 			L0 S.n_usage[dir][n] = u;
 			write_usage(c, dir, n, u);
-			__syncwarp();
+			WSYNC();
 			return;
 		}
 	}
@@ -353,93 +359,121 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 			double u = used+amount;
 			L0 S.n_usage[dir][n] = u;
 			write_usage(c, dir, n, u);
-			__syncwarp();
+			WSYNC();
 			return;
 		}
 		spread_amount = amount-mx+used;                               // :122
 	}
 	// ---- full spread over the node's flows, newest first (list order of flow.c:129,157)
-	__syncwarp();
+	if (c.scalar) { set_status(c, NS_E_ARG); return; }                // classified away by sc_needs_full_spread
+	WSYNC();
 	const int g = n*2+dir;
 	const int off = S.adj_off[g], len = S.adj_len[g];
 	stage_ensure(c, 3ull*(u64)S.adj_live[g]+8);
 	cnt_add(c, NS_CNT_FULL_SPREADS, 1);
 	cnt_add(c, NS_CNT_FLOW_VISITS, 2ull*(u64)S.adj_live[g]);
 	const bool dec = amount < NS_EPS, inc = !dec && amount > NS_EPS;
+	// Both passes walk the list in chunks of 32 (one flow per lane).  SP_U1/SP_U2 chunks are loaded
+	// together so that their dependent gathers (index -> flow -> remote node) overlap; the sums are
+	// then accumulated chunk by chunk, lane by lane, i.e. in exactly the list order.
 	double e = 0;                                                     // :128-145
-	for (int base = len-1; base >= 0; base -= 32) {
-		int p = base-lane;
-		int nf = p >= 0 ? S.adj_arena[off+p] : -1;
-		double term = 0.0;
-		if (nf >= 0 && nf != f) {
-			double sp = S.f_speed[dir][nf];
-			if (dec) { double ls = get_share(S, nf, !dir); if (sp < ls) term = ls-sp; }
-			else if (inc) { double ls = S.f_ub[nf]*mx/total; if (sp > ls) term = sp-ls; }
+	for (int base = len-1; base >= 0; base -= 32*SP_U1) {
+		double term[SP_U1];
+		#pragma unroll
+		for (int u = 0; u < SP_U1; u++) {
+			int p = base-32*u-lane;
+			int nf = p >= 0 ? S.adj_arena[off+p] : -1;
+			double t = 0.0;
+			if (nf >= 0 && nf != f) {
+				double sp = S.f_speed[dir][nf];
+				if (dec) { double ls = get_share(S, nf, !dir); if (sp < ls) t = ls-sp; }
+				else if (inc) { double ls = S.f_ub[nf]*mx/total; if (sp > ls) t = sp-ls; }
+			}
+			term[u] = t;
 		}
 		#pragma unroll
-		for (int l = 0; l < 32; l++) e += __shfl_sync(FULLMASK, term, l);
+		for (int u = 0; u < SP_U1; u++) {
+			if (base-32*u < 0) break;
+			#pragma unroll
+			for (int l = 0; l < 32; l++) e += __shfl_sync(FULLMASK, term[u], l);
+		}
 	}
 	if (dec && -amount > e) amount = -e;                              // :149-154
 	const bool dec2 = amount < NS_EPS, inc2 = !dec2 && amount > NS_EPS;
 	double new_use = 0;                                               // :156-200
-	for (int base = len-1; base >= 0; base -= 32) {
-		int p = base-lane;
-		int nf = p >= 0 ? S.adj_arena[off+p] : -1;
-		double val = 0.0, emit_speed = 0;
-		int adj = 0;
-		Retime rp; rp.add_drain = rp.add_done = 0;
-		if (nf == f) val = fs;
-		else if (nf >= 0) {
-			double sp = S.f_speed[dir][nf];
-			val = sp;
-			if (dec2) {
-				double ls = get_share(S, nf, !dir);
-				if (sp < ls) {
-					double delta = ls-sp;
-					double new_speed = sp-amount*delta/e;             // :171
-					if (dir == SND) { S.f_speed[dir][nf] = new_speed; val = new_speed; }   // :172-176
-					adj = 1; emit_speed = new_speed;                  // :178
-				}
-			} else if (inc2) {
-				double ls = S.f_ub[nf]*mx/total;
-				if (sp > ls) {
-					double delta = sp-ls;
-					double ns = sp-spread_amount*delta/e;             // :187
-					S.f_speed[dir][nf] = ns; val = ns;
-					adj = 1; emit_speed = ns;                         // :189
+	for (int base = len-1; base >= 0; base -= 32*SP_U2) {
+		int nfv[SP_U2], adjv[SP_U2], okv[SP_U2];
+		double valv[SP_U2], emitv[SP_U2], etv[SP_U2];
+		Retime rpv[SP_U2];
+		#pragma unroll
+		for (int u = 0; u < SP_U2; u++) {
+			int p = base-32*u-lane;
+			int nf = p >= 0 ? S.adj_arena[off+p] : -1;
+			double val = 0.0, emit_speed = 0;
+			int adj = 0;
+			if (nf == f) val = fs;
+			else if (nf >= 0) {
+				double sp = S.f_speed[dir][nf];
+				val = sp;
+				if (dec2) {
+					double ls = get_share(S, nf, !dir);
+					if (sp < ls) {
+						double delta = ls-sp;
+						double new_speed = sp-amount*delta/e;         // :171
+						if (dir == SND) { S.f_speed[dir][nf] = new_speed; val = new_speed; }   // :172-176
+						adj = 1; emit_speed = new_speed;              // :178
+					}
+				} else if (inc2) {
+					double ls = S.f_ub[nf]*mx/total;
+					if (sp > ls) {
+						double delta = sp-ls;
+						double ns = sp-spread_amount*delta/e;         // :187
+						S.f_speed[dir][nf] = ns; val = ns;
+						adj = 1; emit_speed = ns;                     // :189
+					}
 				}
 			}
+			nfv[u] = nf; adjv[u] = adj; valv[u] = val; emitv[u] = emit_speed;
 		}
-		// inserts of this chunk in list order: [speed event][drain][done] per adjusted flow
-		double et = 0; int ok = 0;
-		if (adj) {
-			et = c.now+S.f_delay[nf];
-			ok = 1;
-			if (et < c.now) { if (et < c.now-NS_EPS) ok = 0; else et = c.now; }
-			if (isnan(et)) ok = 0;
-			if (!ok) { if (c.st->status == 0) c.st->status = isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; }
-			if (dir == RCV && inc2) retime_plan_1(S, c.st, nf, c.now, rp);   // :193-194
-		}
-		if (dir == RCV && inc2) cnt_add(c, NS_CNT_RETIMES, __popc(__ballot_sync(FULLMASK, adj)));
-		int k = ok+rp.add_drain+rp.add_done;
-		int incl = k;
+		// inserts in list order: [speed event][drain][done] per adjusted flow
 		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
-		int tot = __shfl_sync(FULLMASK, incl, 31);
-		if (tot) {
-			u64 seq0 = seq_reserve(c, tot);
-			if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) {
-				u64 seq = seq0+(u64)(incl-k);
-				if (ok) { ring_put(c, seq, et, emit_speed, nf, !dir); seq++; }
-				if (adj) retime_commit_1(c, nf, rp, seq);
+		for (int u = 0; u < SP_U2; u++) {
+			double et = 0; int ok = 0;
+			rpv[u].add_drain = rpv[u].add_done = 0;
+			if (adjv[u]) {
+				et = c.now+S.f_delay[nfv[u]];
+				ok = 1;
+				if (et < c.now) { if (et < c.now-NS_EPS) ok = 0; else et = c.now; }
+				if (isnan(et)) ok = 0;
+				if (!ok) atomicCAS(&c.st->status, 0, isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME);
+				if (dir == RCV && inc2) retime_plan_1(S, c.st, nfv[u], c.now, rpv[u]);   // :193-194
 			}
+			etv[u] = et; okv[u] = ok;
 		}
 		#pragma unroll
-		for (int l = 0; l < 32; l++) new_use += __shfl_sync(FULLMASK, val, l);   // :199
+		for (int u = 0; u < SP_U2; u++) {
+			if (base-32*u < 0) break;
+			if (dir == RCV && inc2) cnt_add(c, NS_CNT_RETIMES, __popc(__ballot_sync(FULLMASK, adjv[u])));
+			int k = okv[u]+rpv[u].add_drain+rpv[u].add_done;
+			int incl = k;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+			int tot = __shfl_sync(FULLMASK, incl, 31);
+			if (tot) {
+				u64 seq0 = seq_reserve(c, tot);
+				if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) {
+					u64 seq = seq0+(u64)(incl-k);
+					if (okv[u]) { ring_put(c, seq, etv[u], emitv[u], nfv[u], !dir); seq++; }
+					if (adjv[u]) retime_commit_1(c, nfv[u], rpv[u], seq);
+				}
+			}
+			#pragma unroll
+			for (int l = 0; l < 32; l++) new_use += __shfl_sync(FULLMASK, valv[u], l);   // :199
+		}
 	}
 	L0 S.n_usage[dir][n] = new_use;                                   // :201-202
 	write_usage(c, dir, n, new_use);
-	__syncwarp();
+	WSYNC();
 }
 
 // ---------------------------------------------------------------- adjacency arrays (node->conns[dir])
@@ -458,13 +492,13 @@ __device__ void adj_append(Ctx &c, int g, int f, int dir){
 				}
 				S.adj_len[g] = w;
 			}
-			__syncwarp();
+			WSYNC();
 			len = live;
 		} else {
 			int ncap = cap ? cap*2 : 4;
 			int top = c.st->adj_top;
 			if (top+ncap > S.adj_arena_cap) { set_status(c, NS_E_TABLE_FULL); return; }
-			__syncwarp();
+			WSYNC();
 			// move live entries to the new block, lanes strided; positions recomputed serially
 			L0 {
 				int w = 0;
@@ -475,7 +509,7 @@ __device__ void adj_append(Ctx &c, int g, int f, int dir){
 				S.adj_off[g] = top; S.adj_cap[g] = ncap; S.adj_len[g] = w;
 				c.st->adj_top = top+ncap;
 			}
-			__syncwarp();
+			WSYNC();
 			off = top; len = live;
 		}
 	}
@@ -483,7 +517,7 @@ __device__ void adj_append(Ctx &c, int g, int f, int dir){
 		S.adj_arena[off+len] = f; S.f_pos[dir][f] = len;
 		S.adj_len[g] = len+1; S.adj_live[g] = live+1;
 	}
-	__syncwarp();
+	WSYNC();
 }
 __device__ __forceinline__ void adj_remove(Ctx &c, int g, int f, int dir){
 	const Sim &S = *c.S;
@@ -495,7 +529,7 @@ __device__ __forceinline__ void adj_remove(Ctx &c, int g, int f, int dir){
 		while (len > 0 && S.adj_arena[off+len-1] < 0) len--;      // trim trailing tombstones
 		S.adj_len[g] = len;
 	}
-	__syncwarp();
+	WSYNC();
 }
 
 // ---------------------------------------------------------------- random draws (sim.c:117, flow.c:327)
@@ -523,14 +557,14 @@ __device__ int resource_new(Ctx &c, int node, uint32_t rid, long long len){     
 	const Sim &S = *c.S;
 	int i = c.st->hi_res;
 	if (i >= S.cap_res) { set_status(c, NS_E_TABLE_FULL); return -1; }
-	__syncwarp();
+	WSYNC();
 	L0 {
 		S.s_id[i] = rid; S.s_len[i] = len; S.s_node[i] = node; S.s_first[i] = -1;
 		S.s_nprod[i] = 0; S.s_ncons[i] = 0;
 		S.s_next[i] = S.n_res_head[node]; S.n_res_head[node] = i;
 		c.st->hi_res = i+1;
 	}
-	__syncwarp();
+	WSYNC();
 	return i;
 }
 // range_get, range.h:30-41 with range_include_cmp :10-20 (key is an int)
@@ -551,11 +585,11 @@ __device__ int range_get(const Sim &S, int res, int start){
 __device__ int resource_new_range(Ctx &c, int res, long long start, double len, double last){
 	const Sim &S = *c.S;
 	int i = c.st->free_range;
-	if (i >= 0) { __syncwarp(); L0 c.st->free_range = S.r_next_free[i]; }
+	if (i >= 0) { WSYNC(); L0 c.st->free_range = S.r_next_free[i]; }
 	else {
 		i = c.st->hi_range;
 		if (i >= S.cap_ranges) { set_status(c, NS_E_TABLE_FULL); return -1; }
-		__syncwarp();
+		WSYNC();
 		L0 c.st->hi_range = i+1;
 	}
 	c.burns += 1;
@@ -568,7 +602,7 @@ __device__ int resource_new_range(Ctx &c, int res, long long start, double len, 
 		if (prev >= 0) S.r_next[prev] = i; else S.s_first[res] = i;
 		if (cur >= 0) S.r_prev[cur] = i;
 	}
-	__syncwarp();
+	WSYNC();
 	return i;
 }
 
@@ -577,7 +611,7 @@ __device__ void range_merge_with_next(Ctx &c, int r){
 	const Sim &S = *c.S;
 	int nr = S.r_next[r];
 	if (nr < 0) return;
-	__syncwarp();
+	WSYNC();
 	L0 {
 		S.r_len[r] = (double)(u64)((u64)S.r_start[nr]-(u64)S.r_start[r])+S.r_len[nr];   // :94
 		int p = S.r_prod[nr];
@@ -599,16 +633,16 @@ __device__ void range_merge_with_next(Ctx &c, int r){
 		S.r_next_free[nr] = c.st->free_range; c.st->free_range = nr;
 		range_update_1(S, r, c.now);                                  // :113
 	}
-	__syncwarp();
+	WSYNC();
 	for (int f = S.r_cons[r]; f >= 0; f = S.f_cnext[f]) {             // :114-117
 		L0 range_update_1(S, S.f_drng[f], c.now);
-		__syncwarp();
+		WSYNC();
 		range_calc_and_requeue_events(c, f);
 	}
 	int p = S.r_prod[r];
 	if (p >= 0) {                                                     // :119-123
 		L0 range_update_1(S, S.f_srng[p], c.now);
-		__syncwarp();
+		WSYNC();
 		range_calc_and_requeue_events(c, p);
 	}
 }
@@ -618,11 +652,11 @@ __device__ void range_merge_with_next(Ctx &c, int r){
 __device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
 	const Sim &S = *c.S;
 	int f = c.st->free_flow;
-	if (f >= 0) { __syncwarp(); L0 c.st->free_flow = S.f_next_free[f]; }
+	if (f >= 0) { WSYNC(); L0 c.st->free_flow = S.f_next_free[f]; }
 	else {
 		f = c.st->hi_flow;
 		if (f >= S.cap_flows) { set_status(c, NS_E_TABLE_FULL); return -1; }
-		__syncwarp();
+		WSYNC();
 		L0 c.st->hi_flow = f+1;
 	}
 	L0 {
@@ -634,7 +668,7 @@ __device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
 		S.n_total[0][src] += ub;                                      // :314-315
 		S.n_total[1][dst] += ub;
 	}
-	__syncwarp();
+	WSYNC();
 	adj_append(c, src*2+0, f, 0);                                     // :311-312
 	adj_append(c, dst*2+1, f, 1);
 	if (c.st->status) return f;
@@ -645,7 +679,7 @@ __device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
 	L0 S.f_id[f] = id;
 	write_record(c, R_CONN_CREATE, S.n_id[src], 4, id, 0);            // :333-334
 	write_record(c, R_CONN_DST, id, 4, S.n_id[dst], 0);
-	__syncwarp();
+	WSYNC();
 	return f;
 }
 
@@ -654,9 +688,9 @@ __device__ void flow_close(Ctx &c, int f){
 	const Sim &S = *c.S;
 	int src = S.f_peer[0][f], dst = S.f_peer[1][f];
 	double ub = S.f_ub[f];
-	__syncwarp();
+	WSYNC();
 	L0 { S.n_total[0][src] -= ub; S.n_total[1][dst] -= ub; }          // :246-247
-	__syncwarp();
+	WSYNC();
 	flow_range_update(c, f);                                          // :248
 	if (c.st->status) return;
 	bwspread(c, f, S.f_speed[0][f], 0, 1);                            // :249-250
@@ -680,7 +714,7 @@ __device__ void flow_close(Ctx &c, int f){
 		c.st->cnt[NS_CNT_CLOSES] += 1; c.st->cnt[NS_CNT_LIVE_FLOWS] -= 1;
 	}
 	write_record(c, R_CONN_CLOSE, S.f_id[f], 1, 0, 0);                // :289-290
-	__syncwarp();
+	WSYNC();
 }
 
 // sim_establish_flow, sim.c:42-94
@@ -698,7 +732,7 @@ __device__ int sim_establish_flow(Ctx &c, uint32_t rid, long long start, int src
 	int dg = resource_new_range(c, dr, start, 0, c.now);              // :74-76
 	if (dg < 0) return f;
 	L0 { S.f_drng[f] = dg; S.r_prod[dg] = f; S.f_srng[f] = rng; }     // :75-77
-	__syncwarp();
+	WSYNC();
 	if (rng < 0) { set_status(c, NS_E_NULL_RANGE); return f; }
 	if (S.r_prod[rng] >= 0) { L0 c.st->relay_seen = 1; }
 	range_calc_and_requeue_events(c, f);                              // :79
@@ -708,13 +742,30 @@ __device__ int sim_establish_flow(Ctx &c, uint32_t rid, long long start, int src
 		S.r_cons[rng] = f;
 		S.s_ncons[sr] += 1; S.s_nprod[dr] += 1;                       // :82-83
 	}
-	__syncwarp();
+	WSYNC();
 	int ph = S.r_prev[dg];                                            // :86-91
 	if (ph >= 0) range_calc_and_requeue_events(c, S.r_prod[ph]);
 	return f;
 }
 
 // ---------------------------------------------------------------- handlers
+// Would this SPEED_CHANGE reach bwspread's full spread (flow.c:126)?  Pure function of the current
+// state, same branch sequence as flow.c:51-124 with close == 0.  Lets the grid-parallel path run the
+// O(1) solves one per THREAD and keep whole warps for the O(degree) ones.
+__device__ __forceinline__ bool sc_needs_full_spread(const Sim &S, int f, int type, double speed){
+	double fs = S.f_speed[type][f];
+	double amount = speed-fs;                                         // flow.c:359
+	int n = S.f_peer[type][f];
+	double total = S.n_total[type][n], mx = S.n_max[type][n], used = S.n_usage[type][n], ub = S.f_ub[f];
+	double share = total > mx ? ub*mx/total : ub;
+	if (amount > NS_EPS && fs+amount > share) { if (fs > share) return false; amount = share-fs; }
+	if (amount > -NS_EPS && amount < NS_EPS) return false;
+	if (amount < NS_EPS && amount > -64) return false;
+	if (total < mx+NS_EPS) return false;
+	if (amount > -NS_EPS && used+amount < mx+NS_EPS) return false;
+	return true;
+}
+
 // handle_speed_change (flow.c:341-384) + speed_change_free (flow.c:386-389)
 __device__ void handle_speed_change(Ctx &c, int f, int type, double speed){
 	const Sim &S = *c.S;
@@ -787,7 +838,7 @@ __device__ void run_group(Ctx &c, int g){
 			int f = sim_establish_flow(c, S.rids[op.c], op.start, op.a, op.b, op.x, op.y);
 			int ord = c.st->n_ord;
 			if (ord >= S.cap_ord) { set_status(c, NS_E_TABLE_FULL); return; }
-			__syncwarp();
+			WSYNC();
 			L0 {
 				S.ord2flow[ord] = f;
 				c.st->n_ord = ord+1;
@@ -798,15 +849,15 @@ __device__ void run_group(Ctx &c, int g){
 					if (live > c.st->cnt[NS_CNT_PEAK_FLOWS]) c.st->cnt[NS_CNT_PEAK_FLOWS] = live;
 				}
 			}
-			__syncwarp();
+			WSYNC();
 			break; }
 		case NS_OP_SCHED: {
 			int u = c.st->free_user;
-			if (u >= 0) { __syncwarp(); L0 c.st->free_user = S.u_next_free[u]; }
+			if (u >= 0) { WSYNC(); L0 c.st->free_user = S.u_next_free[u]; }
 			else {
 				u = c.st->hi_user;
 				if (u >= S.cap_users) { set_status(c, NS_E_TABLE_FULL); return; }
-				__syncwarp();
+				WSYNC();
 				L0 c.st->hi_user = u+1;
 			}
 			double t = op.c ? c.now+op.x : op.x;
@@ -814,7 +865,7 @@ __device__ void run_group(Ctx &c, int g){
 				u64 seq = seq_reserve(c, 1);
 				L0 { S.u_group[u] = op.a; l_put(c, 2*S.cap_flows+u, seq, t); }
 			}
-			__syncwarp();
+			WSYNC();
 			break; }
 		case NS_OP_CLOSE: {
 			int f = (op.a < c.st->n_ord) ? S.ord2flow[op.a] : -1;
@@ -822,7 +873,7 @@ __device__ void run_group(Ctx &c, int g){
 			break; }
 		case NS_OP_END:
 			L0 c.st->exit_flag = 1;                                   // sim.h:42-45
-			__syncwarp();
+			WSYNC();
 			break;
 		}
 	}

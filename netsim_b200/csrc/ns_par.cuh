@@ -39,12 +39,14 @@ struct ParScratch {
 	int *tile_cnt, *tile_off;     // per ring-window tile: matches, exclusive offset
 	// grouping
 	int *grp_cnt, *grp_off, *grp_fill, *active, *grp_items, *b_grp;
+	int *deferred, *defer_pos;     // groups handed from the per-thread pass to the per-warp pass
 	// scan
 	u64 *cta_ins; unsigned *cta_rec, *cta_tr;
 	// control block (device)
 	struct Ctl {
 		u64 tmin_bits, first_live;
-		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, mode, stop, pad;
+		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
+		u64 dbg_key;
 		u64 tot_ins; unsigned tot_rec, tot_tr;
 		u64 lc[LC_N];
 	} *ctl;
@@ -71,6 +73,7 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
 	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
 	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
+	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1);
 	PA(p.cta_ins, 4096); PA(p.cta_rec, 4096); PA(p.cta_tr, 4096);
 	PA(p.ctl, 1);
 #undef PA
@@ -130,7 +133,7 @@ __device__ void par_handle_event(Ctx &c, const ParScratch &P, int seg_lo, int e,
 		ps.ev_nrec[c.ev] = (uint8_t)c.rec_n; ps.ev_ntr[c.ev] = (uint8_t)c.tr_n;
 		S.q_time[slot] = NS_INF;                                      // event_pop
 	}
-	__syncwarp();
+	WSYNC();
 }
 
 // copy the staged outputs of segment-local event e to their final places
@@ -161,7 +164,7 @@ __device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &p
 
 __device__ __forceinline__ u64 gtimer(){ u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // phase ids for SimState::phase_ns
-enum { PH_ARGMIN = 0, PH_EXTRACT, PH_SEQ, PH_GROUP, PH_SOLVE, PH_COMMIT, PH_TAIL, PH_KERNEL, PH_N };
+enum { PH_ARGMIN = 0, PH_EXTRACT, PH_SEQ, PH_GROUP, PH_SOLVE, PH_COMMIT, PH_TAIL, PH_KERNEL, PH_SOLVE1, PH_N };
 #define PHASE_MARK(id) do { if (leader) { u64 t_ = gtimer(); st->phase_ns[id] += t_-t_ph; t_ph = t_; } } while (0)
 
 // ---------------------------------------------------------------- the persistent kernel
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			if ((u64)nb > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb;
 			u64 lim = budget < (u64)P.seg_cap ? budget : (u64)P.seg_cap;
 			ctl->seg_lo = 0; ctl->seg_hi = (u64)nb < lim ? nb : (int)lim;
-			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0;
+			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
 			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 			*P.stage.ovf_top = 0;
 		}
@@ -337,10 +340,45 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			}
 			grid.sync();
 			PHASE_MARK(PH_GROUP);
-			// ---- E: one warp per group, events in sequence order ----------------------------------
+			// ---- E1: one THREAD per group: O(1) solves (no full spread), events in sequence order ----
 			{
 				Ctx c;
-				c.S = sp; c.st = st; c.lane = lane; c.par = 1; c.ps = P.d_stage; c.now = m;
+				c.S = sp; c.st = st; c.lane = 0; c.par = 1; c.scalar = 1; c.ps = P.d_stage; c.now = m;
+				c.head = head; c.tail = 0; c.burns = 0; c.rec_len = 0; c.tr_len = 0;
+				c.ev = 0; c.lseq = 0; c.rec_n = 0; c.tr_n = 0; c.ovf_base = -1;
+				for (int q = 0; q < LC_N; q++) c.lc[q] = 0;
+				for (u64 k = gtid; k < (u64)n_active; k += gth) {
+					int g = P.active[k];
+					int cnt = P.grp_cnt[g], off = P.grp_off[g];
+					int j = 0;
+					if (cnt > 32) j = -1;                             // long chains: sorted and run by a warp
+					else {
+						int *it = P.grp_items+off;
+						for (int a = 1; a < cnt; a++) {               // insertion sort by batch position
+							int x = it[a], b = a-1;
+							while (b >= 0 && it[b] > x) { it[b+1] = it[b]; b--; }
+							it[b+1] = x;
+						}
+						for (; j < cnt; j++) {
+							int e = it[j];
+							u64 slot = S.b_seq[seg_lo+e] & smask;
+							int fd = S.q_fd[slot];
+							if (sc_needs_full_spread(S, fd >> 1, fd & 1, S.q_speed[slot])) break;
+							par_handle_event(c, P, seg_lo, e, m);
+						}
+					}
+					if (j < cnt) { P.defer_pos[g] = j; P.deferred[atomicAdd(&ctl->n_deferred, 1)] = g; }
+					else P.grp_cnt[g] = 0;                            // ready for the next segment
+				}
+				for (int q = 0; q < LC_N; q++) if (c.lc[q]) atomicAdd((unsigned long long *)&ctl->lc[q], c.lc[q]);
+			}
+			grid.sync();
+			PHASE_MARK(PH_SOLVE1);
+			// ---- E2: one WARP per remaining group: full spreads strided over the lanes ----------------
+			{
+				const int n_def = ctl->n_deferred;
+				Ctx c;
+				c.S = sp; c.st = st; c.lane = lane; c.par = 1; c.scalar = 0; c.ps = P.d_stage; c.now = m;
 				c.head = head; c.tail = 0; c.burns = 0; c.rec_len = 0; c.tr_len = 0;
 				c.ev = 0; c.lseq = 0; c.rec_n = 0; c.tr_n = 0; c.ovf_base = -1;
 				for (int q = 0; q < LC_N; q++) c.lc[q] = 0;
@@ -348,27 +386,20 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 					int k = 0;
 					if (lane == 0) k = atomicAdd(&ctl->work, 1);
 					k = __shfl_sync(FULLMASK, k, 0);
-					if (k >= n_active) break;
-					int g = P.active[k];
+					if (k >= n_def) break;
+					int g = P.deferred[k];
 					int cnt = P.grp_cnt[g], off = P.grp_off[g];
-					if (cnt == 1) {
-						par_handle_event(c, P, seg_lo, P.grp_items[off], m);
-					} else if (cnt <= 32) {
-						int it = lane < cnt ? P.grp_items[off+lane] : 0x7fffffff;
-						// sort across lanes (rank = number of smaller items; items are unique)
-						int rank = 0;
-						for (int l = 0; l < 32; l++) rank += __shfl_sync(FULLMASK, it, l) < it;
-						int mine = 0;
-						for (int l = 0; l < 32; l++) { int r = __shfl_sync(FULLMASK, rank, l), v = __shfl_sync(FULLMASK, it, l); if (r == lane) mine = v; }
-						for (int j = 0; j < cnt; j++) {
-							int e = __shfl_sync(FULLMASK, mine, j);
-							par_handle_event(c, P, seg_lo, e, m);
-						}
-					} else {
-						warp_sort_global(P.grp_items+off, cnt, lane);
-						for (int j = 0; j < cnt; j++) par_handle_event(c, P, seg_lo, P.grp_items[off+j], m);
+					int j = P.defer_pos[g];
+					u64 t_g0 = gtimer();
+					if (j < 0) { warp_sort_global(P.grp_items+off, cnt, lane); j = 0; }
+					int j0 = j;
+					for (; j < cnt; j++) par_handle_event(c, P, seg_lo, P.grp_items[off+j], m);
+					if (lane == 0) {
+						P.grp_cnt[g] = 0;                             // ready for the next segment
+						u64 dt = gtimer()-t_g0;                       // profiling aid: the slowest group of the segment
+						u64 key = (dt << 20) | (u64)(cnt-j0 < 0xfffff ? cnt-j0 : 0xfffff);
+						if (atomicMax((unsigned long long *)&ctl->dbg_key, key) < key) { ctl->dbg_g = g; ctl->dbg_deg = S.adj_live[g]; }
 					}
-					if (lane == 0) P.grp_cnt[g] = 0;                  // ready for the next segment
 				}
 				if (lane == 0) for (int q = 0; q < LC_N; q++) if (c.lc[q]) atomicAdd((unsigned long long *)&ctl->lc[q], c.lc[q]);
 			}
@@ -454,6 +485,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				st->cnt[NS_CNT_FLOW_VISITS] += ctl->lc[LC_FLOW_VISITS]; st->cnt[NS_CNT_PAR_EVENTS] += ctl->lc[LC_EVENTS];
 				st->cnt[NS_CNT_RETIMES] += ctl->lc[LC_RETIMES];
 				st->cnt[NS_CNT_WAVES] += 1;
+				{ u64 k_ = ctl->dbg_key; st->phase_ns[13] += k_ >> 20; if ((k_ >> 20) > st->phase_ns[10]) { st->phase_ns[10] = k_ >> 20; st->phase_ns[11] = ctl->dbg_deg; st->phase_ns[12] = k_ & 0xfffff; } ctl->dbg_key = 0; st->phase_ns[14] += ctl->n_deferred; }
 				st->cnt[NS_CNT_SEQ] = st->tail;
 				for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
 				// next segment, clipped to the remaining event budget
@@ -463,7 +495,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				int nlo = seg_hi, left = nb-seg_hi;
 				ctl->seg_lo = nlo;
 				ctl->seg_hi = (left <= 0 || lim < PAR_MIN_BATCH) ? nlo : nlo+((u64)left < lim ? left : (int)lim);
-				ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0;
+				ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
 				ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 				*P.stage.ovf_top = 0;
 			}

@@ -182,7 +182,7 @@ class Engine:
     def phase_ms(self) -> dict:
         a = (C.c_uint64 * 16)()
         self.L.ns_dev_phase_ns(self.h, a)
-        names = ["argmin", "extract", "sequential", "group", "solve", "commit", "tail", "kernel"]
+        names = ["argmin", "extract", "sequential", "group", "solve_warp", "commit", "tail", "kernel", "solve_thread", "p9", "slowest_group_ms", "slowest_group_degree_x1e6", "slowest_group_events_x1e6", "sum_slowest_ms", "deferred_groups_x1e6"]
         return {n: a[i] / 1e6 for i, n in enumerate(names)}
 
     @property

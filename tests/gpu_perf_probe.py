@@ -61,7 +61,7 @@ if __name__ == "__main__":
             e.run(i * 2000000)
             w = time.time() - t0
             ph = e.phase_ms()
-            print(f"window {i}: device {e.device_ms:.1f} ms wall {w*1e3:.1f} ms phases", {k: round(ph[k] - last[k], 1) for k in ph}, flush=True)
+            print(f"window {i}: device {e.device_ms:.1f} ms", {k: (round(ph[k] - last[k], 1) if 'x1e6' not in k else int(ph[k] * 1e6)) for k in ph if k not in ('p9', 'sequential', 'tail')}, flush=True)
             last = ph
         e.close()
     elif which == "big":
