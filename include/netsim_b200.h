@@ -105,6 +105,27 @@ int  ns_dev_trace(ns_dev *d, struct ns_trace_row32 *dst, size_t cap_rows, size_t
  * total_bwupbound[0], total_bwupbound[1]} */
 int  ns_dev_flow_state(ns_dev *d, double *out4, size_t max_flows, size_t *n);
 int  ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size_t *n);
+/* ---- host-callback mode: modules that register their own handlers (sim_register_handler,
+ * sim.c:96-111) get them called on the host between the device's DEFAULT and CLEANER work.
+ * ns_dev_set_host_mask: bit t = stop after every handled event of enum event_type t (data.h:114-122).
+ * ns_dev_run_host: run until such an event, the end of the queue or sim_end; for FLOW_DONE the flow is
+ *   still alive when the host sees it (flow_done_cleaner runs on the next call), like HNDR_USER
+ *   between HNDR_DEFAULT and HNDR_CLEANER (data.h:126-130).
+ * ns_dev_exec: what a handler may do to the core — NS_OP_CREATE (sim_establish_flow; on return .a is the
+ *   flow's creation ordinal or -1), NS_OP_SCHED (event_add of a USER event; .a is a host token that
+ *   comes back in ns_host_event.token), NS_OP_CLOSE (flow_close), NS_OP_END (sim_end). */
+struct ns_host_event { int32_t type, flow_ord, dir, token; double time, speed, now; int32_t stopped, status, exited, pad; };
+struct ns_flow_info { int32_t alive, src, dst; uint32_t flow_id, resource_id; int32_t pad; double ub, delay, speed[2]; int64_t drng_start; double drng_len; };
+struct ns_range_info { int64_t start, total_len; double len; int32_t producer_ord, pad; };
+struct ns_sc_op;
+int  ns_dev_set_host_mask(ns_dev *d, uint32_t mask);
+int  ns_dev_run_host(ns_dev *d, struct ns_host_event *ev);
+int  ns_dev_exec(ns_dev *d, struct ns_sc_op *ops, int n);
+int  ns_dev_flow_info(ns_dev *d, int ord, struct ns_flow_info *out);
+int  ns_dev_node_ranges(ns_dev *d, int node, uint32_t rid, struct ns_range_info *out, int max, int *n);
+int  ns_dev_node_id(ns_dev *d, int node, uint32_t *id);
+int  ns_dev_resource_id(ns_dev *d, int res, uint32_t *id);
+
 /* leader-thread nanoseconds per engine phase of the grid-parallel path:
  * {argmin, extract, sequential, group, solve, commit} — a profiling aid */
 int  ns_dev_phase_ns(ns_dev *d, uint64_t out[16]);

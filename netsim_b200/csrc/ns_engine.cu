@@ -41,6 +41,45 @@ __global__ void __launch_bounds__(32) k_init_groups(const Sim *sims, int n){
 	ctx_flush(c);
 }
 
+// operations injected by a host-side module handler, at the current simulation time
+__global__ void __launch_bounds__(32) k_exec_ops(const Sim *sp, int n_ops){
+	Ctx c;
+	ctx_load(c, sp, threadIdx.x);
+	run_host_ops(c, n_ops);
+	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
+	ctx_flush(c);
+}
+
+struct FlowInfoDev { int alive, src, dst, pad; unsigned flow_id, resource_id; double ub, delay, speed0, speed1; long long drng_start; double drng_len; };
+__global__ void k_flow_info(const Sim *sp, int ord, FlowInfoDev *out){
+	const Sim &S = *sp;
+	FlowInfoDev r;
+	memset(&r, 0, sizeof r);
+	int f = (ord >= 0 && ord < S.st->n_ord) ? S.ord2flow[ord] : -1;
+	if (f >= 0) {
+		r.alive = 1; r.src = S.f_peer[0][f]; r.dst = S.f_peer[1][f]; r.flow_id = S.f_id[f];
+		r.ub = S.f_ub[f]; r.delay = S.f_delay[f]; r.speed0 = S.f_speed[0][f]; r.speed1 = S.f_speed[1][f];
+		int dr = S.f_drng[f];
+		if (dr >= 0) { r.drng_start = S.r_start[dr]; r.drng_len = S.r_len[dr]; r.resource_id = S.s_id[S.r_res[dr]]; }
+	}
+	*out = r;
+}
+struct RangeInfoDev { long long start, total_len; double len; int producer_ord, pad; };
+__global__ void k_node_ranges(const Sim *sp, int node, unsigned rid, RangeInfoDev *out, int max, int *n_out){
+	const Sim &S = *sp;
+	int n = 0;
+	for (int r = S.n_res_head[node]; r >= 0; r = S.s_next[r]) {
+		if (S.s_id[r] != rid) continue;
+		for (int g = S.s_first[r]; g >= 0 && n < max; g = S.r_next[g]) {
+			out[n].start = S.r_start[g]; out[n].total_len = S.r_total[g]; out[n].len = S.r_len[g];
+			out[n].producer_ord = S.r_prod[g] >= 0 ? S.f_ord[S.r_prod[g]] : -1; out[n].pad = 0;
+			n++;
+		}
+		break;
+	}
+	*n_out = n;
+}
+
 // one warp per simulation, strictly sequential event handling
 __global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n){
 	int s = blockIdx.x;
@@ -194,6 +233,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	DA(d_ops, H.n_ops); DA(d_goff, H.n_groups+1); DA(d_od, H.n_ondone); DA(d_rids, H.n_resources);
 	S.ops = d_ops; S.group_off = d_goff; S.ondone = d_od; S.rids = d_rids;
 	DA(S.ord2flow, S.cap_ord);
+	S.host_ops_cap = 256; DA(S.host_ops, S.host_ops_cap);
 	DA(S.b_seq, S.batch_cap); DA(S.b_ref, 8);
 	DA(h.scr.lb_seq, S.n_l); DA(h.scr.lb_ref, S.n_l); DA(h.scr.lb_tmp_seq, S.n_l); DA(h.scr.lb_tmp_ref, S.n_l);
 	if (S.rec_cap) DA(S.rec, S.rec_cap);
@@ -280,6 +320,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 
 	memcpy(st.rnd, g.st, sizeof st.rnd); st.rf = g.f; st.rr = g.r;
 	st.free_flow = st.free_range = st.free_user = -1;
+	st.pending_close = -1;
 	st.hi_range = nrng0; st.hi_res = nres0;
 	st.rec_len = rec.size();
 	st.cnt[NS_CNT_DRAWS] = draws;
@@ -444,6 +485,76 @@ extern "C" int ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size
 	if (n) *n = k;
 	return 0;
 }
+// ---- host-callback mode (modules whose own handlers must run on the host) ----
+extern "C" int ns_dev_set_host_mask(ns_dev *d, uint32_t mask){
+	if (!d) return NS_E_ARG;
+	CK(cudaMemcpy(&d->h.S.st->host_mask, &mask, 4, cudaMemcpyHostToDevice));
+	return 0;
+}
+extern "C" int ns_dev_run_host(ns_dev *d, ns_host_event *ev){
+	if (!d || !ev) return NS_E_ARG;
+	CK(cudaSetDevice(d->device));
+	int zero = 0; uint64_t nomax = 0;
+	CK(cudaMemcpyAsync(&d->h.S.st->host_stop, &zero, 4, cudaMemcpyHostToDevice, d->stream));
+	CK(cudaMemcpyAsync(&d->h.S.st->max_events, &nomax, 8, cudaMemcpyHostToDevice, d->stream));
+	k_run_seq<<<1, 32, 0, d->stream>>>(d->d_sim, d->d_scr, 1);       // callbacks serialise the run anyway
+	d->launches++;
+	CK(cudaGetLastError());
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	ev->type = st.le_type; ev->flow_ord = st.le_ord; ev->dir = st.le_dir; ev->token = st.le_token;
+	ev->time = st.le_time; ev->speed = st.le_speed; ev->stopped = st.host_stop; ev->status = st.status;
+	ev->now = st.now; ev->exited = st.exit_flag;
+	return st.status;
+}
+extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
+	if (!d || !ops || n < 0 || n > d->h.S.host_ops_cap) return NS_E_ARG;
+	if (n == 0) return 0;
+	CK(cudaSetDevice(d->device));
+	CK(cudaMemcpyAsync(d->h.S.host_ops, ops, (size_t)n*sizeof *ops, cudaMemcpyHostToDevice, d->stream));
+	k_exec_ops<<<1, 32, 0, d->stream>>>(d->d_sim, n);
+	d->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(ops, d->h.S.host_ops, (size_t)n*sizeof *ops, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	return ns_dev_status(d);
+}
+extern "C" int ns_dev_flow_info(ns_dev *d, int ord, ns_flow_info *out){
+	if (!d || !out) return NS_E_ARG;
+	FlowInfoDev *tmp, h;
+	CK(cudaMalloc(&tmp, sizeof *tmp));
+	k_flow_info<<<1, 1, 0, d->stream>>>(d->d_sim, ord, tmp); d->launches++;
+	CK(cudaMemcpyAsync(&h, tmp, sizeof h, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	cudaFree(tmp);
+	out->alive = h.alive; out->src = h.src; out->dst = h.dst; out->flow_id = h.flow_id; out->resource_id = h.resource_id;
+	out->ub = h.ub; out->delay = h.delay; out->speed[0] = h.speed0; out->speed[1] = h.speed1;
+	out->drng_start = h.drng_start; out->drng_len = h.drng_len;
+	return 0;
+}
+extern "C" int ns_dev_node_ranges(ns_dev *d, int node, uint32_t rid, ns_range_info *out, int max, int *n){
+	if (!d || !out || !n || node < 0 || node >= d->h.S.n_nodes || max <= 0) return NS_E_ARG;
+	RangeInfoDev *tmp; int *dn;
+	CK(cudaMalloc(&tmp, sizeof(RangeInfoDev)*max)); CK(cudaMalloc(&dn, 4));
+	k_node_ranges<<<1, 1, 0, d->stream>>>(d->d_sim, node, rid, tmp, max, dn); d->launches++;
+	std::vector<RangeInfoDev> h(max);
+	CK(cudaMemcpyAsync(h.data(), tmp, sizeof(RangeInfoDev)*max, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaMemcpyAsync(n, dn, 4, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	cudaFree(tmp); cudaFree(dn);
+	for (int i = 0; i < *n; i++) { out[i].start = h[i].start; out[i].total_len = h[i].total_len; out[i].len = h[i].len; out[i].producer_ord = h[i].producer_ord; out[i].pad = 0; }
+	return 0;
+}
+extern "C" int ns_dev_node_id(ns_dev *d, int node, uint32_t *id){
+	if (!d || !id || node < 0 || node >= d->h.S.n_nodes) return NS_E_ARG;
+	CK(cudaMemcpy(id, d->h.S.n_id+node, 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+extern "C" int ns_dev_resource_id(ns_dev *d, int res, uint32_t *id){
+	if (!d || !id || res < 0 || res >= d->h.S.n_rids) return NS_E_ARG;
+	CK(cudaMemcpy(id, d->h.S.rids+res, 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 extern "C" int ns_dev_phase_ns(ns_dev *d, uint64_t out[16]){
 	if (!d || !out) return NS_E_ARG;
 	SimState st; int rc = read_state(d, &st); if (rc) return rc;

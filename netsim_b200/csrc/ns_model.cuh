@@ -806,6 +806,11 @@ __device__ void handle_flow_done(Ctx &c, int f){
 		if (g >= 0) run_group(c, g);
 	}
 	if (c.st->status) return;
+	if (c.st->host_mask & (1u << EV_FLOW_DONE)) {                     // module handler runs between the DEFAULT
+		L0 c.st->pending_close = f;                                   // and CLEANER handlers (data.h:126-130)
+		WSYNC();
+		return;
+	}
 	flow_close(c, f);
 }
 
@@ -873,6 +878,60 @@ __device__ void run_group(Ctx &c, int g){
 			break; }
 		case NS_OP_END:
 			L0 c.st->exit_flag = 1;                                   // sim.h:42-45
+			WSYNC();
+			break;
+		}
+	}
+}
+
+// operations injected by a host-side module handler (sim_establish_flow / event_add / flow_close /
+// sim_end called from inside a handler), executed at the current `now`
+__device__ void run_host_ops(Ctx &c, int n){
+	const Sim &S = *c.S;
+	for (int i = 0; i < n; i++) {
+		if (c.st->status) return;
+		ns_sc_op op = S.host_ops[i];
+		switch (op.kind) {
+		case NS_OP_CREATE: {
+			int f = sim_establish_flow(c, S.rids[op.c], op.start, op.a, op.b, op.x, op.y);
+			int ord = c.st->n_ord;
+			if (ord >= S.cap_ord) { set_status(c, NS_E_TABLE_FULL); return; }
+			WSYNC();
+			L0 {
+				S.ord2flow[ord] = f;
+				c.st->n_ord = ord+1;
+				S.host_ops[i].a = f >= 0 ? ord : -1;                  // result: creation ordinal or -1
+				if (f >= 0) {
+					S.f_ord[f] = ord;
+					c.st->cnt[NS_CNT_CREATES] += 1;
+					u64 live = ++c.st->cnt[NS_CNT_LIVE_FLOWS];
+					if (live > c.st->cnt[NS_CNT_PEAK_FLOWS]) c.st->cnt[NS_CNT_PEAK_FLOWS] = live;
+				}
+			}
+			WSYNC();
+			break; }
+		case NS_OP_SCHED: {                                            // a = host token of the USER event
+			int u = c.st->free_user;
+			if (u >= 0) { WSYNC(); L0 c.st->free_user = S.u_next_free[u]; }
+			else {
+				u = c.st->hi_user;
+				if (u >= S.cap_users) { set_status(c, NS_E_TABLE_FULL); return; }
+				WSYNC();
+				L0 c.st->hi_user = u+1;
+			}
+			double t = op.c ? c.now+op.x : op.x;
+			if (ev_time_ok(c, t)) {
+				u64 seq = seq_reserve(c, 1);
+				L0 { S.u_group[u] = -(op.a+1); l_put(c, 2*S.cap_flows+u, seq, t); }
+			}
+			WSYNC();
+			break; }
+		case NS_OP_CLOSE: {
+			int f = (op.a >= 0 && op.a < c.st->n_ord) ? S.ord2flow[op.a] : -1;
+			if (f >= 0) flow_close(c, f);
+			break; }
+		case NS_OP_END:
+			L0 c.st->exit_flag = 1;
 			WSYNC();
 			break;
 		}

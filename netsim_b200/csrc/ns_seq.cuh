@@ -137,6 +137,18 @@ __device__ int seq_collect_l(Ctx &c, double m, const SeqScratch &sc){
 	return nl;
 }
 
+// host-callback mode: remember the event and stop after it when its type is in the mask
+__device__ __forceinline__ void host_report(Ctx &c, int type, int f, int dir, double speed, int token){
+	SimState *st = c.st;
+	if (!(st->host_mask & (1u << type))) return;
+	L0 {
+		st->le_type = type; st->le_flow = f; st->le_ord = f >= 0 ? c.S->f_ord[f] : -1; st->le_dir = dir;
+		st->le_token = token; st->le_time = c.now; st->le_speed = speed;
+		st->host_stop = 1;
+	}
+	WSYNC();
+}
+
 // handle one long-lived event (FLOW_DONE / FLOW_DRAIN / FLOW_SPEED_THROTTLE / USER); returns false
 // when it had been cancelled or re-timed after extraction.
 __device__ bool seq_handle_l(Ctx &c, double m, u64 seq, int slot){
@@ -148,15 +160,21 @@ __device__ bool seq_handle_l(Ctx &c, double m, u64 seq, int slot){
 	cnt_add(c, NS_CNT_EVENTS, 1);
 	if (slot < 2*S.cap_flows) {
 		int f = slot >> 1;
-		if (!(slot & 1)) { cnt_add(c, NS_CNT_FLOW_DONE, 1); handle_flow_done(c, f); }
-		else if (S.f_drain_type[f] == EV_FLOW_SPEED_THROTTLE) { cnt_add(c, NS_CNT_THROTTLE, 1); handle_throttle(c, f); }
-		else { cnt_add(c, NS_CNT_DRAIN, 1); trace_row(c, EV_FLOW_DRAIN, S.f_ord[f], 0, 0); }   // no handler (main.c:44-48)
+		if (!(slot & 1)) { cnt_add(c, NS_CNT_FLOW_DONE, 1); handle_flow_done(c, f); host_report(c, EV_FLOW_DONE, f, 0, 0, -1); }
+		else if (S.f_drain_type[f] == EV_FLOW_SPEED_THROTTLE) { cnt_add(c, NS_CNT_THROTTLE, 1); handle_throttle(c, f); host_report(c, EV_FLOW_SPEED_THROTTLE, f, 0, 0, -1); }
+		else { cnt_add(c, NS_CNT_DRAIN, 1); trace_row(c, EV_FLOW_DRAIN, S.f_ord[f], 0, 0); host_report(c, EV_FLOW_DRAIN, f, 0, 0, -1); }   // no default handler (main.c:44-48)
 	} else {
 		int u = slot-2*S.cap_flows;
 		int g = S.u_group[u];
 		L0 { S.u_next_free[u] = c.st->free_user; c.st->free_user = u; }
 		__syncwarp();
 		cnt_add(c, NS_CNT_USER, 1);
+		if (g < 0) {                                                  // a host-owned USER event: its handler runs on the host
+			L0 { c.st->le_type = EV_USER; c.st->le_flow = -1; c.st->le_ord = -1; c.st->le_dir = 0; c.st->le_token = -g-1;
+			     c.st->le_time = c.now; c.st->le_speed = 0; c.st->host_stop = 1; }
+			WSYNC();
+			return true;
+		}
 		trace_row(c, EV_USER, g, 0, 0);
 		run_group(c, g);
 	}
@@ -179,12 +197,13 @@ __device__ bool seq_handle_ring(Ctx &c, double m, u64 seq){
 	cnt_add(c, NS_CNT_EVENTS, 1);
 	cnt_add(c, NS_CNT_SPEED_CHANGE, 1);
 	handle_speed_change(c, f, dir, speed);
+	host_report(c, EV_SPEED_CHANGE, f, dir, speed, -1);
 	return true;
 }
 
 __device__ __forceinline__ bool seq_should_stop(Ctx &c){
 	SimState *st = c.st;
-	if (st->status || st->exit_flag) return true;
+	if (st->status || st->exit_flag || st->host_stop) return true;
 	if (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events) return true;
 	return false;
 }
@@ -219,6 +238,13 @@ __device__ void seq_process(Ctx &c, double m, int i, int nr, int j, int nl, cons
 __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 	Ctx c;
 	ctx_load(c, Sp, lane);
+	if (c.st->pending_close >= 0) {                                   // flow_done_cleaner of the event the host just saw
+		int f = c.st->pending_close;
+		WSYNC();
+		L0 c.st->pending_close = -1;
+		WSYNC();
+		flow_close(c, f);
+	}
 	while (true) {
 		if (seq_should_stop(c)) break;
 		double m = seq_find_tmin(c);

@@ -45,6 +45,12 @@ struct SimState {                 // mutable scalars of one simulation
 	u64 max_events;
 	u64 seed;
 	u64 phase_ns[16];             // leader-thread wall time per engine phase (profiling aid)
+	// host-callback mode (modules with their own handlers)
+	unsigned host_mask;           // bit t set: stop after every handled event of type t
+	int host_stop;                // set by the engine when it stopped for the host
+	int pending_close;            // FLOW_DONE: flow whose flow_close (HNDR_CLEANER) runs on resume
+	int le_type, le_flow, le_ord, le_dir, le_token;   // the event the host must see
+	double le_time, le_speed;
 };
 
 struct Sim {
@@ -75,6 +81,7 @@ struct Sim {
 	// script
 	const ns_sc_op *ops; const int *group_off; const ns_sc_ondone *ondone; const uint32_t *rids;
 	int *ord2flow;
+	ns_sc_op *host_ops; int host_ops_cap;   // operations injected by host-side handlers (ns_dev_exec)
 	// per-timestamp batch scratch
 	u64 *b_seq; int *b_ref;       // ring entries: ref = -1; L entries: ref = slot
 	// outputs

@@ -45,3 +45,18 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def stderr_goldens():
+    """stderr of the reference's own modules (what a user of `netsim modules/test0x` reads)."""
+    import subprocess
+    import tempfile
+    for t in ("test00", "test01", "test02", "test03", "test04", "test05"):
+        with tempfile.TemporaryDirectory() as d:
+            p = subprocess.run([os.path.join(refrun.REF, "netsim"), os.path.join(refrun.REF, "modules", t)], cwd=d,
+                               capture_output=True)
+            open(os.path.join(OUT, t + ".stderr.txt"), "wb").write(p.stderr)
+
+
+if __name__ == "__main__":
+    stderr_goldens()
