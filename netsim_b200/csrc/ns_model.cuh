@@ -240,6 +240,44 @@ struct Retime { double drain_t, done_t; int add_drain, add_done; };
 #define SP_U1 8     // chunks of 32 flows in flight in pass 1 of a full spread
 #define SP_U2 4     // ... in pass 2
 
+// the arithmetic of range.c:28-78 on values (shared by the table-driven and the register-resident paths)
+__device__ __forceinline__ int retime_math(double now, double fbw, bool has_prod, double sgrow, double prod_done_t,
+		double slen, double dlen, long long dstart, long long sstart, int npos, Retime &p, int &dtype){
+	double drng_start = (double)dstart+dlen-(double)sstart;           // :36
+	double drain_time = (slen-drng_start)/(fbw-sgrow);                // :38
+	double drain_active = NS_INF;                                     // time of f->drain if active
+	bool bad = false;
+	if (!has_prod) {                                                  // :40-44
+		double t = now+(slen-drng_start)/fbw;
+		dtype = EV_FLOW_DRAIN;
+		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+		if (isnan(t)) bad = true;
+		if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
+	} else if (!is_later_than(drain_time+now, prod_done_t) && sgrow < fbw) {   // :45-61
+		dtype = EV_FLOW_SPEED_THROTTLE;
+		double d0 = slen-drng_start;
+		if (d0 > -NS_EPS && d0 < NS_EPS) {
+			double d1 = sgrow-fbw;
+			if (!(d1 > -NS_EPS && d1 < NS_EPS)) { p.add_drain = 1; p.drain_t = now; drain_active = now; }
+		} else {
+			double t = now+drain_time;
+			if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+			if (isnan(t)) bad = true;
+			if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
+		}
+	}
+	if (bad) return isnan(drain_time) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME;
+	double done_time = ((double)(u64)((u64)(long long)npos-(u64)dstart)-dlen)/fbw;  // :70
+	if (!is_later_than(now+done_time, drain_active)) {                // :73-78
+		double t = now+done_time;
+		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+		if (isnan(t)) bad = true;
+		if (bad) return isnan(t) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME;
+		p.add_done = 1; p.done_t = t;
+	}
+	return 0;
+}
+
 __device__ __forceinline__ void retime_plan_1(const Sim &S, SimState *st, int f, double now, Retime &p){
 	p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
 	S.l_time[2*f] = NS_INF;                                           // range.c:19-20 event_remove
@@ -252,42 +290,13 @@ __device__ __forceinline__ void retime_plan_1(const Sim &S, SimState *st, int f,
 	if (fbw < NS_EPS) return;                                         // :26-27
 	int prod = S.r_prod[sr];
 	double sgrow = prod >= 0 ? S.f_speed[1][prod] : 0;                // :33
-	double slen = S.r_len[sr], dlen = S.r_len[dr];
-	long long dstart = S.r_start[dr], sstart = S.r_start[sr];
-	double drng_start = (double)dstart+dlen-(double)sstart;           // :36
-	double drain_time = (slen-drng_start)/(fbw-sgrow);                // :38
-	double drain_active = NS_INF;                                     // time of f->drain if active
-	bool bad = false;
-	if (prod < 0) {                                                   // :40-44
-		double t = now+(slen-drng_start)/fbw;
-		S.f_drain_type[f] = EV_FLOW_DRAIN;
-		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
-		if (isnan(t)) bad = true;
-		if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
-	} else if (!is_later_than(drain_time+now, S.l_time[2*prod]) && sgrow < fbw) {   // :45-61
-		S.f_drain_type[f] = EV_FLOW_SPEED_THROTTLE;
-		double d0 = slen-drng_start;
-		if (d0 > -NS_EPS && d0 < NS_EPS) {
-			double d1 = sgrow-fbw;
-			if (!(d1 > -NS_EPS && d1 < NS_EPS)) { p.add_drain = 1; p.drain_t = now; drain_active = now; }
-		} else {
-			double t = now+drain_time;
-			if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
-			if (isnan(t)) bad = true;
-			if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
-		}
-	}
-	if (bad) { if (st->status == 0) st->status = isnan(drain_time) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; return; }
 	int nx = S.r_next[dr];                                            // :64-69 (int npos)
 	int npos = nx >= 0 ? (int)S.r_start[nx] : (int)S.r_total[dr];
-	double done_time = ((double)(u64)((u64)(long long)npos-(u64)dstart)-dlen)/fbw;  // :70
-	if (!is_later_than(now+done_time, drain_active)) {                // :73-78
-		double t = now+done_time;
-		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
-		if (isnan(t)) bad = true;
-		if (bad) { if (st->status == 0) st->status = isnan(t) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME; return; }
-		p.add_done = 1; p.done_t = t;
-	}
+	int dtype = -1;
+	int err = retime_math(now, fbw, prod >= 0, sgrow, prod >= 0 ? S.l_time[2*prod] : NS_INF, S.r_len[sr], S.r_len[dr],
+			      S.r_start[dr], S.r_start[sr], npos, p, dtype);
+	if (dtype >= 0) S.f_drain_type[f] = (uint8_t)dtype;
+	if (err) { if (st->status == 0) st->status = err; }
 }
 // sequence numbers: drain first, then done; a drain superseded by done keeps its burned number.
 __device__ __forceinline__ void retime_commit_1(Ctx &c, int f, const Retime &p, u64 seq){
@@ -936,4 +945,84 @@ __device__ void run_host_ops(Ctx &c, int n){
 			break;
 		}
 	}
+}
+
+// ---------------------------------------------------------------- register-resident event chains
+// A batch can hold thousands of SPEED_CHANGE events for ONE (node, direction) (every full spread at a
+// neighbour re-notifies all its flows): that chain is strictly sequential and sets the critical path
+// of the batch.  For nodes with <= 32 flows each lane keeps one flow of the node in registers
+// (write-through), so an O(1) solve of the chain costs a ballot, the owner lane's arithmetic and a few
+// stores instead of a walk through the tables.  Events that need a full spread go through bwspread()
+// above and the lanes reload.  Only used inside relay-free parallel segments (source ranges static).
+struct GFlow {
+	int nf, ord; unsigned id;
+	double ub, sp, delay;
+	int dr, sr, npos;
+	long long d_start, s_start;
+	double d_len, d_lenc, d_last, s_len, s_last;
+};
+__device__ __forceinline__ void ge_load(const Sim &S, GFlow &g, int off, int len, int lane, int dir){
+	g.nf = lane < len ? S.adj_arena[off+lane] : -1;
+	if (g.nf < 0) return;
+	int f = g.nf;
+	g.ord = S.f_ord[f]; g.id = S.f_id[f]; g.ub = S.f_ub[f]; g.sp = S.f_speed[dir][f]; g.delay = S.f_delay[f];
+	if (dir == RCV) {
+		g.dr = S.f_drng[f]; g.sr = S.f_srng[f];
+		g.d_start = S.r_start[g.dr]; g.s_start = S.r_start[g.sr];
+		g.d_len = S.r_len[g.dr]; g.d_lenc = S.r_lenc[g.dr]; g.d_last = S.r_last[g.dr];
+		g.s_len = S.r_len[g.sr]; g.s_last = S.r_last[g.sr];
+		int nx = S.r_next[g.dr];
+		g.npos = nx >= 0 ? (int)S.r_start[nx] : (int)S.r_total[g.dr];
+	}
+}
+// one O(1) SPEED_CHANGE (handle_speed_change with every bwspread exit of flow.c:64-124) executed by the
+// owner lane alone; lc is that lane's private staging context (scalar mode)
+__device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g, double &usage, double total, double mx,
+		int n, int type, double speed){
+	const double now = lc.now;
+	const int f = g.nf;
+	lc.lc[LC_EVENTS] += 1; lc.lc[LC_SPEED_CHANGE] += 1; lc.lc[LC_SOLVES] += 1;
+	if (type == RCV) {                                                // flow.c:355-357 -> range.h:91-125
+		if (now != g.s_last) { g.s_last = now; S.r_last[g.sr] = now; }
+		if (now != g.d_last) {
+			double delta = g.sp*(now-g.d_last), t;
+			delta = delta-g.d_lenc;
+			t = delta+g.d_len;
+			g.d_lenc = (t-g.d_len)-delta;
+			g.d_len = t;
+			g.d_last = now;
+			S.r_lenc[g.dr] = g.d_lenc; S.r_len[g.dr] = g.d_len; S.r_last[g.dr] = now;
+		}
+	}
+	double fs = g.sp;
+	const double delta0 = speed-fs;                                   // flow.c:359
+	double amount = delta0;
+	const double share = total > mx ? g.ub*mx/total : g.ub;           // flow.c:61
+	bool done_bw = false;
+	if (amount > NS_EPS && fs+amount > share) {                       // flow.c:64-78
+		if (fs > share) { queue_speed_event(lc, f, !type, fs); done_bw = true; }
+		else { queue_speed_event(lc, f, !type, share); amount = share-fs; }
+	}
+	if (!done_bw && !(amount > -NS_EPS && amount < NS_EPS)) {         // flow.c:80-124, the O(1) exits
+		fs += amount;
+		g.sp = fs; S.f_speed[type][f] = fs;
+		usage += amount; S.n_usage[type][n] = usage;
+		write_usage(lc, type, n, usage);
+	}
+	if (type == RCV) {                                                // flow.c:367-370 -> range.c:16-79
+		lc.lc[LC_RETIMES] += 1;
+		Retime p; p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
+		S.l_time[2*f] = NS_INF; S.l_time[2*f+1] = NS_INF;
+		if (!(g.sp < NS_EPS)) {
+			int dtype = -1;
+			int err = retime_math(now, g.sp, false, 0.0, NS_INF, g.s_len, g.d_len, g.d_start, g.s_start, g.npos, p, dtype);
+			if (dtype >= 0) S.f_drain_type[f] = (uint8_t)dtype;
+			if (err) atomicCAS(&lc.st->status, 0, err);
+		}
+		int k = p.add_drain+p.add_done;
+		if (k) { u64 seq = seq_reserve(lc, k); retime_commit_1(lc, f, p, seq); }
+	} else if (delta0 > 0)
+		queue_speed_event(lc, f, RCV, g.sp);                          // flow.c:371-374
+	write_record(lc, R_SPD|type, g.id, -1, 0, speed);                 // flow.c:383
+	trace_row(lc, EV_SPEED_CHANGE|(type << 8), g.ord, speed, g.sp);
 }

@@ -136,6 +136,82 @@ __device__ void par_handle_event(Ctx &c, const ParScratch &P, int seg_lo, int e,
 	WSYNC();
 }
 
+// a chain of events of one small (node,dir) group with the node's flows held in registers (ns_model.cuh)
+#define GE_MIN_CHAIN 6
+__device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off, int j, int cnt, double m){
+	const Sim &S = *c.S;
+	const int lane = c.lane, n = g >> 1, dir = g & 1;
+	const u64 smask = S.ring_cap-1;
+	const int a_off = S.adj_off[g], a_len = S.adj_len[g];
+	const double total = S.n_total[dir][n], mx = S.n_max[dir][n];
+	double usage = S.n_usage[dir][n];
+	GFlow gf;
+	ge_load(S, gf, a_off, a_len, lane, dir);
+	Ctx lc = c;                                                       // the owner lane's private staging context
+	lc.scalar = 1; lc.lane = 0;
+	for (int q = 0; q < LC_N; q++) lc.lc[q] = 0;
+	for (int j0 = j; j0 < cnt; j0 += 32) {
+		// fetch up to 32 events of the chain at once
+		int my_e = -1, my_fd = 0; double my_speed = 0; u64 my_slot = 0;
+		if (j0+lane < cnt) {
+			my_e = P.grp_items[off+j0+lane];
+			my_slot = S.b_seq[seg_lo+my_e] & smask;
+			my_fd = S.q_fd[my_slot]; my_speed = S.q_speed[my_slot];
+		}
+		int nev = cnt-j0 < 32 ? cnt-j0 : 32;
+		for (int k = 0; k < nev; k++) {
+			int e = __shfl_sync(FULLMASK, my_e, k);
+			int fd = __shfl_sync(FULLMASK, my_fd, k);
+			double speed = __shfl_sync(FULLMASK, my_speed, k);
+			u64 slot = __shfl_sync(FULLMASK, my_slot, k);
+			int f = fd >> 1;
+			unsigned own = __ballot_sync(FULLMASK, gf.nf == f);
+			int owner = __ffs(own)-1;
+			bool full = true;
+			if (owner >= 0) {
+				// same decision sequence as sc_needs_full_spread(), on the cached values
+				double fs = __shfl_sync(FULLMASK, gf.sp, owner), ub = __shfl_sync(FULLMASK, gf.ub, owner);
+				double amount = speed-fs;
+				double share = total > mx ? ub*mx/total : ub;
+				full = true;
+				if (amount > NS_EPS && fs+amount > share) { if (fs > share) full = false; else amount = share-fs; }
+				if (full) {
+					if (amount > -NS_EPS && amount < NS_EPS) full = false;
+					else if (amount < NS_EPS && amount > -64) full = false;
+					else if (total < mx+NS_EPS) full = false;
+					else if (amount > -NS_EPS && usage+amount < mx+NS_EPS) full = false;
+				}
+			}
+			if (full) {
+				// a full spread (or a flow this lane set does not hold): the table-driven warp handler;
+				// the cache is write-through, so the tables are current; reload afterwards
+				__syncwarp();
+				par_handle_event(c, P, seg_lo, e, m);
+				ge_load(S, gf, a_off, a_len, lane, dir);
+				usage = S.n_usage[dir][n];
+				continue;
+			}
+			if (lane == owner) {
+				lc.ev = (unsigned)e; lc.lseq = 0; lc.rec_n = 0; lc.tr_n = 0; lc.ovf_base = -1;
+				ge_simple_event(lc, S, gf, usage, total, mx, n, dir, speed);
+				const ParStage &ps = *lc.ps;
+				ps.ev_nins[e] = lc.lseq; ps.ev_ovf[e] = -1;
+				ps.ev_nrec[e] = (uint8_t)lc.rec_n; ps.ev_ntr[e] = (uint8_t)lc.tr_n;
+				S.q_time[slot] = NS_INF;                              // event_pop
+			}
+			usage = __shfl_sync(FULLMASK, usage, owner);
+		}
+		__syncwarp();
+	}
+	// the lanes' private counters
+	for (int q = 0; q < LC_N; q++) {
+		u64 v = lc.lc[q];
+		for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+		c.lc[q] += v;
+	}
+	__syncwarp();
+}
+
 // copy the staged outputs of segment-local event e to their final places
 __device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep){
 	unsigned nins = ps.ev_nins[e];
@@ -393,7 +469,8 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 					u64 t_g0 = gtimer();
 					if (j < 0) { warp_sort_global(P.grp_items+off, cnt, lane); j = 0; }
 					int j0 = j;
-					for (; j < cnt; j++) par_handle_event(c, P, seg_lo, P.grp_items[off+j], m);
+					if (cnt-j >= GE_MIN_CHAIN && S.adj_len[g] <= 32) ge_chain(c, P, g, seg_lo, off, j, cnt, m);
+					else for (; j < cnt; j++) par_handle_event(c, P, seg_lo, P.grp_items[off+j], m);
 					if (lane == 0) {
 						P.grp_cnt[g] = 0;                             // ready for the next segment
 						u64 dt = gtimer()-t_g0;                       // profiling aid: the slowest group of the segment
