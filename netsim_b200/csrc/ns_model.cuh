@@ -956,16 +956,17 @@ __device__ void run_host_ops(Ctx &c, int n){
 // above and the lanes reload.  Only used inside relay-free parallel segments (source ranges static).
 struct GFlow {
 	int nf, ord; unsigned id;
-	double ub, sp, delay;
+	double ub, sp, delay, share;      // share = get_share(f, dir): constant inside a segment (flow.c:61)
 	int dr, sr, npos;
 	long long d_start, s_start;
 	double d_len, d_lenc, d_last, s_len, s_last;
 };
-__device__ __forceinline__ void ge_load(const Sim &S, GFlow &g, int off, int len, int lane, int dir){
+__device__ __forceinline__ void ge_load(const Sim &S, GFlow &g, int off, int len, int lane, int dir, double total, double mx){
 	g.nf = lane < len ? S.adj_arena[off+lane] : -1;
 	if (g.nf < 0) return;
 	int f = g.nf;
 	g.ord = S.f_ord[f]; g.id = S.f_id[f]; g.ub = S.f_ub[f]; g.sp = S.f_speed[dir][f]; g.delay = S.f_delay[f];
+	g.share = total > mx ? g.ub*mx/total : g.ub;
 	if (dir == RCV) {
 		g.dr = S.f_drng[f]; g.sr = S.f_srng[f];
 		g.d_start = S.r_start[g.dr]; g.s_start = S.r_start[g.sr];
@@ -975,9 +976,16 @@ __device__ __forceinline__ void ge_load(const Sim &S, GFlow &g, int off, int len
 		g.npos = nx >= 0 ? (int)S.r_start[nx] : (int)S.r_total[g.dr];
 	}
 }
+// queue_speed_event (flow.c:16-29) with the delay taken from the lane's registers
+__device__ __forceinline__ void ge_emit(Ctx &lc, const GFlow &g, int dir, double speed){
+	double t = lc.now+g.delay;
+	if (!ev_time_ok(lc, t)) return;
+	u64 seq = seq_reserve(lc, 1);
+	ring_put(lc, seq, t, speed, g.nf, dir);
+}
 // one O(1) SPEED_CHANGE (handle_speed_change with every bwspread exit of flow.c:64-124) executed by the
 // owner lane alone; lc is that lane's private staging context (scalar mode)
-__device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g, double &usage, double total, double mx,
+__device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g, double &usage, unsigned node_id,
 		int n, int type, double speed){
 	const double now = lc.now;
 	const int f = g.nf;
@@ -997,17 +1005,17 @@ __device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g,
 	double fs = g.sp;
 	const double delta0 = speed-fs;                                   // flow.c:359
 	double amount = delta0;
-	const double share = total > mx ? g.ub*mx/total : g.ub;           // flow.c:61
+	const double share = g.share;                                     // flow.c:61
 	bool done_bw = false;
 	if (amount > NS_EPS && fs+amount > share) {                       // flow.c:64-78
-		if (fs > share) { queue_speed_event(lc, f, !type, fs); done_bw = true; }
-		else { queue_speed_event(lc, f, !type, share); amount = share-fs; }
+		if (fs > share) { ge_emit(lc, g, !type, fs); done_bw = true; }
+		else { ge_emit(lc, g, !type, share); amount = share-fs; }
 	}
 	if (!done_bw && !(amount > -NS_EPS && amount < NS_EPS)) {         // flow.c:80-124, the O(1) exits
 		fs += amount;
 		g.sp = fs; S.f_speed[type][f] = fs;
 		usage += amount; S.n_usage[type][n] = usage;
-		write_usage(lc, type, n, usage);
+		write_record(lc, R_USAGE|type, node_id, -1, 0, usage);        // record_wrapper.h:6-9
 	}
 	if (type == RCV) {                                                // flow.c:367-370 -> range.c:16-79
 		lc.lc[LC_RETIMES] += 1;
@@ -1022,7 +1030,7 @@ __device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g,
 		int k = p.add_drain+p.add_done;
 		if (k) { u64 seq = seq_reserve(lc, k); retime_commit_1(lc, f, p, seq); }
 	} else if (delta0 > 0)
-		queue_speed_event(lc, f, RCV, g.sp);                          // flow.c:371-374
+		ge_emit(lc, g, RCV, g.sp);                                    // flow.c:371-374
 	write_record(lc, R_SPD|type, g.id, -1, 0, speed);                 // flow.c:383
 	trace_row(lc, EV_SPEED_CHANGE|(type << 8), g.ord, speed, g.sp);
 }

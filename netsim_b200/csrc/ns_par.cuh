@@ -145,8 +145,9 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 	const int a_off = S.adj_off[g], a_len = S.adj_len[g];
 	const double total = S.n_total[dir][n], mx = S.n_max[dir][n];
 	double usage = S.n_usage[dir][n];
+	const unsigned node_id = S.n_id[n];
 	GFlow gf;
-	ge_load(S, gf, a_off, a_len, lane, dir);
+	ge_load(S, gf, a_off, a_len, lane, dir, total, mx);
 	Ctx lc = c;                                                       // the owner lane's private staging context
 	lc.scalar = 1; lc.lane = 0;
 	for (int q = 0; q < LC_N; q++) lc.lc[q] = 0;
@@ -170,9 +171,8 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 			bool full = true;
 			if (owner >= 0) {
 				// same decision sequence as sc_needs_full_spread(), on the cached values
-				double fs = __shfl_sync(FULLMASK, gf.sp, owner), ub = __shfl_sync(FULLMASK, gf.ub, owner);
+				double fs = __shfl_sync(FULLMASK, gf.sp, owner), share = __shfl_sync(FULLMASK, gf.share, owner);
 				double amount = speed-fs;
-				double share = total > mx ? ub*mx/total : ub;
 				full = true;
 				if (amount > NS_EPS && fs+amount > share) { if (fs > share) full = false; else amount = share-fs; }
 				if (full) {
@@ -187,13 +187,13 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 				// the cache is write-through, so the tables are current; reload afterwards
 				__syncwarp();
 				par_handle_event(c, P, seg_lo, e, m);
-				ge_load(S, gf, a_off, a_len, lane, dir);
+				ge_load(S, gf, a_off, a_len, lane, dir, total, mx);
 				usage = S.n_usage[dir][n];
 				continue;
 			}
 			if (lane == owner) {
 				lc.ev = (unsigned)e; lc.lseq = 0; lc.rec_n = 0; lc.tr_n = 0; lc.ovf_base = -1;
-				ge_simple_event(lc, S, gf, usage, total, mx, n, dir, speed);
+				ge_simple_event(lc, S, gf, usage, node_id, n, dir, speed);
 				const ParStage &ps = *lc.ps;
 				ps.ev_nins[e] = lc.lseq; ps.ev_ovf[e] = -1;
 				ps.ev_nrec[e] = (uint8_t)lc.rec_n; ps.ev_ntr[e] = (uint8_t)lc.tr_n;
@@ -224,7 +224,8 @@ __device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &p
 			u64 slot = seq & (S.ring_cap-1);
 			double t = ps.st_time[si];
 			S.q_time[slot] = t; S.q_speed[slot] = ps.st_speed[si]; S.q_fd[slot] = fd; S.q_gen[slot] = S.f_gen[fd >> 1];
-			tmin_lower(&S.q_tmin[slot >> NS_TILE_SHIFT], t);
+			double *tm = &S.q_tmin[slot >> NS_TILE_SHIFT];
+			if (*(volatile double *)tm > t) tmin_lower(tm, t);            // minima only fall during a commit
 		} else if (fd != NS_HOLE_PURE) {
 			int ls = -fd-1;
 			u64 prov = NS_SEQ_PROV | ((u64)e << 24) | j;
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			int cnt = 0;
 			if (S.q_tmin[at & tmask] == m) {
 				u64 base = at << NS_TILE_SHIFT;
-				for (int i = lane; i < NS_TILE; i += 32) { u64 s = base+i; cnt += (S.q_time[s & smask] == m && s >= head && s < tail); }
+				#pragma unroll
+				for (int i = 0; i < NS_TILE; i += 32) { u64 s = base+i+lane; cnt += (S.q_time[s & smask] == m && s >= head && s < tail); }
 				for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, d);
 			}
 			if (lane == 0) P.tile_cnt[k] = cnt;
@@ -330,14 +332,20 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			u64 base = at << NS_TILE_SHIFT;
 			int off = P.tile_off[k];
 			double nm = NS_INF;
-			for (int i = 0; i < NS_TILE; i += 32) {
-				u64 s = base+i+lane;
-				double t = S.q_time[s & smask];
-				bool match = t == m && s >= head && s < tail;
-				unsigned mm = __ballot_sync(FULLMASK, match);
-				if (match) S.b_seq[off+__popc(mm & ((1u << lane)-1))] = s;
-				off += __popc(mm);
-				if (!match) nm = fmin(nm, t);
+			for (int i0 = 0; i0 < NS_TILE; i0 += 32*8) {                 // 8 independent loads in flight per lane
+				double tv[8];
+				#pragma unroll
+				for (int u = 0; u < 8; u++) tv[u] = S.q_time[(base+i0+32*u+lane) & smask];
+				#pragma unroll
+				for (int u = 0; u < 8; u++) {
+					u64 s = base+i0+32*u+lane;
+					double t = tv[u];
+					bool match = t == m && s >= head && s < tail;
+					unsigned mm = __ballot_sync(FULLMASK, match);
+					if (match) S.b_seq[off+__popc(mm & ((1u << lane)-1))] = s;
+					off += __popc(mm);
+					if (!match) nm = fmin(nm, t);
+				}
 			}
 			nm = warp_min_d(nm);
 			if (lane == 0) S.q_tmin[at & tmask] = nm;

@@ -52,6 +52,23 @@ if __name__ == "__main__":
         probe(10000, 32, 2000000, both, n_catalogue=32, seeds_per_peer=6)
     elif which == "mid":
         probe(10000, 32, 5000000, [("auto", E.MODE_AUTO)], n_catalogue=32, seeds_per_peer=6)
+    elif which == "ensemble":
+        nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+        npeers = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
+        maxev = int(sys.argv[4]) if len(sys.argv) > 4 else 200000
+        scs = [S.swarm_fast(npeers, max(2, npeers // 250), n_catalogue=16, seeds_per_peer=4, seed=100 + i, rand_seed=1 + i).to_bytes() for i in range(nrep)]
+        t0 = time.time()
+        ens = E.Ensemble(scs, records=True, ring_cap=1 << 22, record_cap=maxev * 48 + (16 << 20))
+        t1 = time.time()
+        ens.run(maxev)
+        t2 = time.time()
+        dg = ens.digests()
+        ev = sum(d["events"] for d in dg)
+        bad = [d["status"] for d in dg if d["status"] != 0]
+        print(f"ensemble {nrep} x swarm{npeers}: create+init {t1-t0:.1f}s run device {ens.device_ms:.1f} ms -> {ev/(ens.device_ms/1e3):.0f} ev/s aggregate; events {ev}; bad status {bad[:5]}", flush=True)
+        o = pyoracle.Oracle(scs[3], trace=False); o.run(maxev)
+        print("   replica 3 digest ok:", dg[3]["record_hash"] == E.stream_hash(o.records()), dg[3]["events"], o.counters()["events"])
+        ens.close()
     elif which == "windows":
         sc = S.swarm_fast(100032, 320, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
         e = E.Engine(sc.to_bytes(), mode=E.MODE_AUTO, records=True, record_cap=4 << 30)

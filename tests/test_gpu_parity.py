@@ -157,3 +157,25 @@ def test_pick_batch_matches_qselect(built):
         assert oc[q] == (1 if i >= 0 else 0)
         if i >= 0:
             assert on[lo] == node[lo + i]
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+@pytest.mark.parametrize("kw", [
+    dict(n_peers=300, n_hubs=4, n_catalogue=6, seeds_per_peer=3, mean_strips=3.0, res_len=20000),
+    dict(n_peers=600, n_hubs=4, n_catalogue=6, seeds_per_peer=3, mean_strips=3.0, res_len=40000, arrival_window=5.0),
+], ids=["complete300", "arrivals600"])
+def test_engine_runs_swarm_to_completion(kw, mname, mode, built):
+    """File distribution to completion: every flow finishes (FLOW_DONE, range merges, closes with
+    full spreads), arrivals come as USER events between speed-change batches."""
+    sc = S.swarm(**kw)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(0) == 0
+    e, st = run_engine(b, mode, 0, trace_cap=200000)
+    assert st == 0
+    assert e.records() == o.records()
+    assert e.trace().tobytes() == o.trace().tobytes()
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    assert ce["live_flows"] == 0 and ce["flow_done"] == co["closes"]
+    e.close()
