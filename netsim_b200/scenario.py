@@ -386,3 +386,44 @@ def swarm_fast(n_peers: int = 100032, n_hubs: int = 320, n_catalogue: int = 64, 
     sc._ops = ops
     sc._group_off = np.array([0, len(ops)], dtype="<i4")
     return sc
+
+
+def churn(n_users: int = 5000, n_servers: int = 16, rate: float = 1000.0, mean_session: float = 6.0,
+          quantum: float = 0.01, res_len: int = 4000000, seed: int = 2024, sim_end: float | None = None) -> Scenario:
+    """SURVEY §8d config 4 (test_client3-style churn) as a script: `n_users` clients arrive as a Poisson
+    process of `rate`/s, each fetching the file from one of `n_servers` servers (server_picker1,
+    client_behaviour.c:333-345: first server it is not connected to, here round-robin over zones) and
+    leaving after an exponential session (its flow is closed if still alive).  Timestamps are quantised
+    to `quantum` so that equal-timestamp batches hold several arrivals/departures plus the speed events
+    they trigger (modules/test_client3.c:39-45 is one such arrival)."""
+    rng = np.random.default_rng(seed)
+    n = n_servers + n_users
+    idx = np.arange(n)
+    is_srv = idx < n_servers
+    tz = np.where(is_srv, _tz(idx, n_servers), _tz(idx - n_servers, n_users))
+    mu = np.where(is_srv, 160000.0, 8000.0)
+    md = np.where(is_srv, 160000.0, 40000.0)
+    res = np.zeros(1, dtype=RES_DTYPE)
+    res["owner"] = 0
+    res["len"] = res_len
+    res["bit_rate"] = 2000
+    cp = np.zeros(n_servers - 1, dtype=COPY_DTYPE)
+    cp["node"] = np.arange(1, n_servers)
+    cp["res"] = 0
+    t_arr = np.floor(np.cumsum(rng.exponential(1.0 / rate, n_users)) / quantum) * quantum
+    t_dep = np.floor((t_arr + rng.exponential(mean_session, n_users)) / quantum + 1) * quantum
+    srv = rng.integers(0, n_servers, n_users)
+    ub, dl = _ub_delay(tz[srv], tz[n_servers + np.arange(n_users)])
+    groups: List[List[tuple]] = [[]]
+    events = [(float(t_arr[u]), 0, u) for u in range(n_users)] + [(float(t_dep[u]), 1, u) for u in range(n_users)]
+    events.sort()
+    for t, kind, u in events:
+        if kind == 0:
+            groups.append([create(int(srv[u]), n_servers + u, 0, 0, float(ub[u]), float(dl[u]))])
+        else:
+            groups.append([close(u)])          # flow ordinal == arrival index (arrivals are created in time order)
+        groups[0].append(sched(len(groups) - 1, t))
+    if sim_end is not None:
+        groups.append([end()])
+        groups[0].append(sched(len(groups) - 1, sim_end))
+    return Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, groups, {}, seed=1)

@@ -179,3 +179,20 @@ def test_engine_runs_swarm_to_completion(kw, mname, mode, built):
     assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
     assert ce["live_flows"] == 0 and ce["flow_done"] == co["closes"]
     e.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+def test_engine_churn_arrivals_departures(mname, mode, built):
+    """SURVEY §8d config 4 shape at test scale: Poisson arrivals/departures on a 10 ms grid —
+    equal-timestamp batches mixing USER events (creates, closes) with the speed events they trigger."""
+    sc = S.churn(2000, 8, rate=500.0, mean_session=4.0, sim_end=12.0)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(0) == 0
+    e, st = run_engine(b, mode, 0, trace_cap=400000)
+    assert st == 0
+    assert e.records() == o.records()
+    assert e.trace().tobytes() == o.trace().tobytes()
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    e.close()
