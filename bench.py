@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -107,7 +107,7 @@ def run_reference(args, sc_bytes, steps, warmup, events_per_step):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--peers", type=int, default=100032)
@@ -192,11 +192,11 @@ def main():
         rec_off += got
         return dev_ms, time.perf_counter() - t_a, got
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # the windows are tens of ms: sample from the warm-up on
     for i in range(args.warmup):
         step(i)
     c0 = eng.counters()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     dev_ms_sum, wall_sum, d2h = 0.0, 0.0, 0
     t_region = time.perf_counter()
@@ -243,6 +243,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (dev_ms_sum / 1e3) / 1e9
+    traffic = None                       # dram bytes per launch from the committed ncu --set full capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("peers") == args.peers and tr.get("events_per_step") == eps:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     config.update({"events_per_step": eps, "flows": c_init["creates"], "create_init_s": round(create_s, 2),
                    "pending_events_at_end": c1["seq"] - c1["events"], "batches_timed": d["batches"], "max_batch": c1["max_batch"],
                    "parallel_fraction": d["par_events"] / max(1, events), "solves_per_s": solves_all / (dev_ms_max / 1e3),
@@ -256,7 +263,7 @@ def main():
                     "note": "wall clock per window through ns_dev_run + ns_dev_records into pinned host memory; the script upload "
                             "and init (create_init_s) happen once before the windows, like the reference's untimed module init"},
             "gpu_launches": args.steps * 1 + 1,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_run_par (persistent, one launch per window)", "algorithmic_bytes_per_launch": alg_bytes / args.steps}}
     if not args.no_cpu_baseline and world == 1:
         r = run_reference(args, sc_bytes, 2, 1, args.ref_events_per_step)

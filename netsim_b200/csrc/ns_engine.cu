@@ -208,7 +208,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	S.adj_arena_cap = 16*F+8*N+64;
 	S.batch_cap = (int)std::min<u64>(S.ring_cap/2, 1ull << 30);
 	S.want_rec = o.want_records; S.want_tr = o.want_trace;
-	S.rec_cap = o.want_records ? (o.record_cap ? o.record_cap : std::max<u64>(1u << 20, 64ull*N+4096ull*F)) : 0;
+	S.rec_cap = o.want_records ? (o.record_cap ? o.record_cap : std::max<u64>(64u << 20, 64ull*N+4096ull*F)) : 0;
 	S.tr_cap = o.want_trace ? (o.trace_cap ? o.trace_cap : (1u << 20)) : 0;
 
 	int rc;

@@ -189,7 +189,7 @@ def test_engine_churn_arrivals_departures(mname, mode, built):
     b = sc.to_bytes()
     o = pyoracle.Oracle(b)
     assert o.run(0) == 0
-    e, st = run_engine(b, mode, 0, trace_cap=400000)
+    e, st = run_engine(b, mode, 0, trace_cap=400000, record_cap=64 << 20)
     assert st == 0
     assert e.records() == o.records()
     assert e.trace().tobytes() == o.trace().tobytes()
