@@ -238,7 +238,15 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	DA(h.scr.lb_seq, S.n_l); DA(h.scr.lb_ref, S.n_l); DA(h.scr.lb_tmp_seq, S.n_l); DA(h.scr.lb_tmp_ref, S.n_l);
 	if (S.rec_cap) DA(S.rec, S.rec_cap);
 	if (S.tr_cap) DA(S.tr, S.tr_cap);
-	if ((rc = par_alloc(h.par, S, parallel_scratch, [&](void **pp, size_t b){ return dev_alloc(h, pp, b); }))) return rc;
+	// parallel module init: group 0 made only of CREATE ops (flows established by the module's *_init)
+	int n_init = 0;
+	if (parallel_scratch && goff[1]-goff[0] >= 256) {
+		n_init = goff[1]-goff[0];
+		for (int i = goff[0]; i < goff[1]; i++) if (ops[i].kind != NS_OP_CREATE) { n_init = 0; break; }
+		if (goff[0] != 0) n_init = 0;
+	}
+	if ((rc = par_alloc(h.par, S, parallel_scratch, n_init, [&](void **pp, size_t b){ return dev_alloc(h, pp, b); }))) return rc;
+	if (n_init && (rc = par_plan_init(h.par, ops, n_init, N))) return rc;
 #undef DA
 
 	// ---- host-side init: sim_create_node (sim.c:113-125), sim_node_new_resource (:129-140),

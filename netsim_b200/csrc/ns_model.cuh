@@ -15,7 +15,7 @@
 // sequence numbers / record offset, so its event_adds, records and trace row are parked here under
 // LOCAL indices and committed in batch order by a prefix scan (ns_par.cuh).
 #define NS_STAGE_INLINE 4
-#define NS_STAGE_REC 40
+#define NS_STAGE_REC 56
 #define NS_SEQ_PROV (1ull << 63)
 #define NS_HOLE_PURE (-2147483647-1)
 struct ParStage {
@@ -23,6 +23,7 @@ struct ParStage {
 	u64 inline_n, ovf_cap; u64 *ovf_top;
 	uint8_t *st_rec; ns_trace_row32 *st_tr;
 	unsigned *ev_nins; long long *ev_ovf; uint8_t *ev_nrec, *ev_ntr;
+	unsigned *ev_idpos;           // parallel creates: event_adds of the op before its flow-id draw (flow.c:327)
 };
 enum { LC_EVENTS = 0, LC_SPEED_CHANGE, LC_SOLVES, LC_FULL_SPREADS, LC_FLOW_VISITS, LC_RETIMES, LC_N };
 
@@ -33,6 +34,8 @@ struct Ctx {
 	u64 burns, rec_len, tr_len;
 	int par;               // 1 inside the grid-parallel path: emissions are staged
 	int scalar;            // 1 when ONE thread runs the handler alone (O(1) solves, ns_par.cuh phase E1)
+	int pre_slot;          // >= 0 while a CREATE op runs in the parallel init: its flow slot / ordinal (ns_par.cuh)
+	unsigned id_pos;       // ... and where in the op's draws the flow id falls
 	const ParStage *ps; unsigned ev, lseq, rec_n, tr_n; long long ovf_base;
 	u64 lc[LC_N];
 };
@@ -41,7 +44,7 @@ struct Ctx {
 #define WSYNC() do { if (!c.scalar) __syncwarp(); } while (0)
 
 __device__ __forceinline__ void ctx_load(Ctx &c, const Sim *S, int lane){
-	c.S = S; c.st = S->st; c.lane = lane; c.par = 0; c.scalar = 0; c.ps = nullptr;
+	c.S = S; c.st = S->st; c.lane = lane; c.par = 0; c.scalar = 0; c.ps = nullptr; c.pre_slot = -1; c.id_pos = 0;
 	c.now = c.st->now; c.head = c.st->head; c.tail = c.st->tail; c.burns = c.st->burns;
 	c.rec_len = c.st->rec_len; c.tr_len = c.st->tr_len;
 }
@@ -378,7 +381,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 	WSYNC();
 	const int g = n*2+dir;
 	const int off = S.adj_off[g], len = S.adj_len[g];
-	stage_ensure(c, 3ull*(u64)S.adj_live[g]+8);
+	stage_ensure(c, (dir == RCV ? 3ull : 1ull)*(u64)S.adj_live[g]+8);   // RCV victims may also re-time (drain+done)
 	cnt_add(c, NS_CNT_FULL_SPREADS, 1);
 	cnt_add(c, NS_CNT_FLOW_VISITS, 2ull*(u64)S.adj_live[g]);
 	const bool dec = amount < NS_EPS, inc = !dec && amount > NS_EPS;
@@ -505,7 +508,9 @@ __device__ void adj_append(Ctx &c, int g, int f, int dir){
 			len = live;
 		} else {
 			int ncap = cap ? cap*2 : 4;
-			int top = c.st->adj_top;
+			int top = 0;
+			if (c.pre_slot >= 0) { L0 top = atomicAdd(&c.st->adj_top, ncap); top = __shfl_sync(FULLMASK, top, 0); }
+			else top = c.st->adj_top;
 			if (top+ncap > S.adj_arena_cap) { set_status(c, NS_E_TABLE_FULL); return; }
 			WSYNC();
 			// move live entries to the new block, lanes strided; positions recomputed serially
@@ -516,7 +521,7 @@ __device__ void adj_append(Ctx &c, int g, int f, int dir){
 					if (x >= 0) { S.adj_arena[top+w] = x; S.f_pos[dir][x] = w; w++; }
 				}
 				S.adj_off[g] = top; S.adj_cap[g] = ncap; S.adj_len[g] = w;
-				c.st->adj_top = top+ncap;
+				if (c.pre_slot < 0) c.st->adj_top = top+ncap;
 			}
 			WSYNC();
 			off = top; len = live;
@@ -543,6 +548,7 @@ __device__ __forceinline__ void adj_remove(Ctx &c, int g, int f, int dir){
 
 // ---------------------------------------------------------------- random draws (sim.c:117, flow.c:327)
 __device__ __forceinline__ uint32_t draw_random(Ctx &c){
+	if (c.pre_slot >= 0) { c.id_pos = c.lseq; return 0; }            // drawn in op order by the init commit
 	uint32_t v = 0;
 	L0 {
 		SimState *st = c.st;
@@ -564,14 +570,18 @@ __device__ __forceinline__ int store_get(const Sim &S, int node, uint32_t rid){ 
 }
 __device__ int resource_new(Ctx &c, int node, uint32_t rid, long long len){          // data.h:241-249, store.h:25-35
 	const Sim &S = *c.S;
-	int i = c.st->hi_res;
+	int i = 0;
+	if (c.pre_slot >= 0) { L0 i = atomicAdd(&c.st->hi_res, 1); i = __shfl_sync(FULLMASK, i, 0); }
+	else i = c.st->hi_res;
 	if (i >= S.cap_res) { set_status(c, NS_E_TABLE_FULL); return -1; }
 	WSYNC();
 	L0 {
 		S.s_id[i] = rid; S.s_len[i] = len; S.s_node[i] = node; S.s_first[i] = -1;
 		S.s_nprod[i] = 0; S.s_ncons[i] = 0;
-		S.s_next[i] = S.n_res_head[node]; S.n_res_head[node] = i;
-		c.st->hi_res = i+1;
+		S.s_next[i] = S.n_res_head[node];
+		__threadfence();                                              // concurrent store_get() of another op may walk this list
+		S.n_res_head[node] = i;
+		if (c.pre_slot < 0) c.st->hi_res = i+1;
 	}
 	WSYNC();
 	return i;
@@ -593,8 +603,9 @@ __device__ int range_get(const Sim &S, int res, int start){
 // resource_new_range, range.h:71-82: sorted insert by start; the skip-list insert burns one random()
 __device__ int resource_new_range(Ctx &c, int res, long long start, double len, double last){
 	const Sim &S = *c.S;
-	int i = c.st->free_range;
-	if (i >= 0) { WSYNC(); L0 c.st->free_range = S.r_next_free[i]; }
+	int i = c.pre_slot >= 0 ? c.st->hi_range+c.pre_slot : c.st->free_range;      // parallel init: slot = base + ordinal
+	if (c.pre_slot >= 0) { if (i >= S.cap_ranges) { set_status(c, NS_E_TABLE_FULL); return -1; } }
+	else if (i >= 0) { WSYNC(); L0 c.st->free_range = S.r_next_free[i]; }
 	else {
 		i = c.st->hi_range;
 		if (i >= S.cap_ranges) { set_status(c, NS_E_TABLE_FULL); return -1; }
@@ -660,8 +671,9 @@ __device__ void range_merge_with_next(Ctx &c, int r){
 // flow_create, flow.c:296-337
 __device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
 	const Sim &S = *c.S;
-	int f = c.st->free_flow;
-	if (f >= 0) { WSYNC(); L0 c.st->free_flow = S.f_next_free[f]; }
+	int f = c.pre_slot >= 0 ? c.pre_slot : c.st->free_flow;
+	if (c.pre_slot >= 0) { if (f >= S.cap_flows) { set_status(c, NS_E_TABLE_FULL); return -1; } }
+	else if (f >= 0) { WSYNC(); L0 c.st->free_flow = S.f_next_free[f]; }
 	else {
 		f = c.st->hi_flow;
 		if (f >= S.cap_flows) { set_status(c, NS_E_TABLE_FULL); return -1; }
