@@ -48,6 +48,7 @@ struct ParScratch {
 	struct Ctl {
 		u64 tmin_bits, first_live;
 		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
+		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
 		u64 dbg_key;
 		u64 tot_ins; unsigned tot_rec, tot_tr;
 		u64 lc[LC_N];
@@ -248,6 +249,69 @@ __device__ __forceinline__ u64 gtimer(){ u64 t; asm volatile("mov.u64 %0, %globa
 enum { PH_ARGMIN = 0, PH_EXTRACT, PH_SEQ, PH_GROUP, PH_SOLVE, PH_COMMIT, PH_TAIL, PH_KERNEL, PH_SOLVE1, PH_N };
 #define PHASE_MARK(id) do { if (leader) { u64 t_ = gtimer(); st->phase_ns[id] += t_-t_ph; t_ph = t_; } } while (0)
 
+// ---------------------------------------------------------------- pieces of one batch
+// A batch is handled as a sequence of pieces in sequence-number order: long runs of SPEED_CHANGE events
+// go through the parallel phases D-F, everything else (FLOW_DONE / USER / THROTTLE / DRAIN events and
+// the short runs between them, relay simulations, the last events before a max_events bound)
+// through the single-warp path.  The leader thread plans one piece at a time because a sequential
+// piece may change what follows (flow_close cancels events, a USER group may create a relay).
+enum { PIECE_END = 0, PIECE_SEQ = 1, PIECE_PAR = 2 };
+__device__ __forceinline__ int lower_bound_seq(const u64 *a, int lo, int hi, u64 key){
+	while (lo < hi) { int mid = (lo+hi) >> 1; if (a[mid] < key) lo = mid+1; else hi = mid; }
+	return lo;
+}
+__device__ void par_finish_piece(const Sim &S, SimState *st, ParScratch::Ctl *ctl, const ParScratch &P){
+	st->tail += ctl->tot_ins; st->burns += ctl->tot_ins;
+	st->rec_len += S.want_rec ? ctl->tot_rec : 0;
+	u64 ntr = st->tr_len+ctl->tot_tr;
+	st->tr_len = S.want_tr ? (ntr < S.tr_cap ? ntr : S.tr_cap) : 0;
+	st->cnt[NS_CNT_EVENTS] += ctl->lc[LC_EVENTS]; st->cnt[NS_CNT_SPEED_CHANGE] += ctl->lc[LC_SPEED_CHANGE];
+	st->cnt[NS_CNT_SOLVES] += ctl->lc[LC_SOLVES]; st->cnt[NS_CNT_FULL_SPREADS] += ctl->lc[LC_FULL_SPREADS];
+	st->cnt[NS_CNT_FLOW_VISITS] += ctl->lc[LC_FLOW_VISITS]; st->cnt[NS_CNT_PAR_EVENTS] += ctl->lc[LC_EVENTS];
+	st->cnt[NS_CNT_RETIMES] += ctl->lc[LC_RETIMES];
+	st->cnt[NS_CNT_WAVES] += 1;
+	{ u64 k_ = ctl->dbg_key; st->phase_ns[13] += k_ >> 20; if ((k_ >> 20) > st->phase_ns[10]) { st->phase_ns[10] = k_ >> 20; st->phase_ns[11] = ctl->dbg_deg; st->phase_ns[12] = k_ & 0xfffff; } ctl->dbg_key = 0; st->phase_ns[14] += ctl->n_deferred; }
+	st->cnt[NS_CNT_SEQ] = st->tail;
+	for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
+	ctl->pos = ctl->seg_hi;
+	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
+	ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
+	*P.stage.ovf_top = 0;
+}
+__device__ void par_plan_piece(const Sim &S, SimState *st, ParScratch::Ctl *ctl, const ParScratch &P, const SeqScratch &sc, int nb, int nl){
+	if (ctl->piece == PIECE_PAR) par_finish_piece(S, st, ctl, P);
+	ctl->piece = PIECE_END; ctl->last = 0;
+	const u64 ev_max = st->max_events, evn = st->cnt[NS_CNT_EVENTS];
+	if (st->status || st->exit_flag || st->host_stop || (ev_max && evn >= ev_max)) return;
+	const int pos = ctl->pos, li = ctl->li;
+	if (pos >= nb && li >= nl) return;
+	const u64 budget = ev_max ? ev_max-evn : ~0ull;
+	const bool no_par = st->relay_seen || budget < PAR_MIN_BATCH;
+	const u64 ls = li < nl ? sc.lb_seq[li] : ~0ull;
+	int end = pos;
+	if (pos < nb && S.b_seq[pos] < ls) end = lower_bound_seq(S.b_seq, pos, nb, ls);
+	if (!no_par && end-pos >= PAR_MIN_BATCH) {
+		u64 lim = budget < (u64)P.seg_cap ? budget : (u64)P.seg_cap;
+		int hi = (u64)(end-pos) <= lim ? end : pos+(int)lim;
+		ctl->piece = PIECE_PAR; ctl->seg_lo = pos; ctl->seg_hi = hi;
+		ctl->last = hi == nb && li >= nl;
+		return;
+	}
+	int e2 = end, l2 = li;
+	if (no_par) { e2 = nb; l2 = nl; }
+	else while (true) {
+		if (l2 >= nl) { e2 = nb; break; }
+		l2++;                                                         // the next long-lived event
+		u64 ls2 = l2 < nl ? sc.lb_seq[l2] : ~0ull;
+		int nx = lower_bound_seq(S.b_seq, e2, nb, ls2);
+		if (nx-e2 >= PAR_MIN_BATCH) break;                            // a long run follows: it gets its own parallel piece
+		e2 = nx;
+		if (l2 >= nl && e2 >= nb) break;
+	}
+	ctl->piece = PIECE_SEQ; ctl->seg_lo = pos; ctl->seg_hi = e2; ctl->l_lo = li; ctl->l_hi = l2;
+	ctl->last = e2 == nb && l2 == nl;
+}
+
 // ---------------------------------------------------------------- the persistent kernel
 __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const Sim *sp, const SeqScratch *scrp, ParScratch P){
 	cgp::grid_group grid = cgp::this_grid();
@@ -361,41 +425,39 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 		grid.sync();
 		PHASE_MARK(PH_EXTRACT);
 		if (nb+nl == 0) continue;                                     // only stale lower bounds surfaced
-		// ---- C: legality --------------------------------------------------------------------
-		// (a run bounded by max_events must stop at an exact event count: the parallel prefix is
-		//  clipped to the remaining budget and the rest goes through the sequential path)
-		const u64 ev_now = st->cnt[NS_CNT_EVENTS], ev_max = st->max_events;
-		const u64 budget = ev_max ? (ev_max > ev_now ? ev_max-ev_now : 0) : ~0ull;
-		const bool parallel = nl == 0 && !st->relay_seen && nb >= PAR_MIN_BATCH && budget >= PAR_MIN_BATCH;
-		if (!parallel) {
-			if (blockIdx.x == 0 && warp == 0) {
-				Ctx c; ctx_load(c, sp, lane);
-				c.now = m;
-				cnt_add(c, NS_CNT_BATCHES, 1);
-				L0 { if ((u64)(nb+nl) > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb+nl; }
-				seq_process(c, m, 0, nb, 0, nl, sc);
-				L0 st->cnt[NS_CNT_SEQ] = c.tail;
-				ctx_flush(c);
-			}
-			PHASE_MARK(PH_SEQ);
-			continue;                                                 // next iteration starts with a grid.sync
-		}
+		// ---- C: the batch as a sequence of pieces (par_plan_piece) -----------------------------------
 		if (leader) {
 			st->now = m;
 			st->cnt[NS_CNT_BATCHES] += 1;
-			if ((u64)nb > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb;
-			u64 lim = budget < (u64)P.seg_cap ? budget : (u64)P.seg_cap;
-			ctl->seg_lo = 0; ctl->seg_hi = (u64)nb < lim ? nb : (int)lim;
+			if ((u64)(nb+nl) > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb+nl;
+			ctl->pos = 0; ctl->li = 0; ctl->piece = PIECE_END;
 			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
 			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 			*P.stage.ovf_top = 0;
 		}
-		grid.sync();
-		// ---- segments of at most seg_cap events, in order --------------------------------------
+		bool done_all = false;                                        // the last piece covered the rest of the batch
 		while (true) {
+			if (leader) par_plan_piece(S, st, ctl, P, sc, nb, nl);
+			grid.sync();
+			const int piece = ctl->piece, last = ctl->last;
+			if (piece == PIECE_END) break;
+			if (piece == PIECE_SEQ) {
+				if (blockIdx.x == 0 && warp == 0) {
+					Ctx c; ctx_load(c, sp, lane);
+					c.now = m;
+					int pi = ctl->seg_lo, pj = ctl->l_lo;
+					const int pe = ctl->seg_hi, le = ctl->l_hi;
+					seq_process(c, m, pi, pe, pj, le, sc);
+					if (last && (pi < pe || pj < le)) seq_restore(c, m, pi, pe, pj, le, sc);   // stopped inside the last piece
+					L0 { st->cnt[NS_CNT_SEQ] = c.tail; ctl->pos = last ? nb : pi; ctl->li = last ? nl : pj; }
+					ctx_flush(c);
+				}
+				PHASE_MARK(PH_SEQ);
+				if (last) { done_all = true; break; }
+				continue;
+			}
 			const int seg_lo = ctl->seg_lo, seg_hi = ctl->seg_hi;
 			const int ns = seg_hi-seg_lo;
-			if (ns <= 0 || st->status) break;
 			// ---- D1: group of every event; cancelled events drop out ---------------------------
 			for (u64 e = gtid; e < (u64)ns; e += gth) {
 				u64 s = S.b_seq[seg_lo+e];
@@ -564,50 +626,23 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				}
 			}
 			grid.sync();
-			if (leader) {
-				st->tail += ctl->tot_ins; st->burns += ctl->tot_ins;
-				st->rec_len += S.want_rec ? ctl->tot_rec : 0;
-				u64 ntr = st->tr_len+ctl->tot_tr;
-				st->tr_len = S.want_tr ? (ntr < S.tr_cap ? ntr : S.tr_cap) : 0;
-				st->cnt[NS_CNT_EVENTS] += ctl->lc[LC_EVENTS]; st->cnt[NS_CNT_SPEED_CHANGE] += ctl->lc[LC_SPEED_CHANGE];
-				st->cnt[NS_CNT_SOLVES] += ctl->lc[LC_SOLVES]; st->cnt[NS_CNT_FULL_SPREADS] += ctl->lc[LC_FULL_SPREADS];
-				st->cnt[NS_CNT_FLOW_VISITS] += ctl->lc[LC_FLOW_VISITS]; st->cnt[NS_CNT_PAR_EVENTS] += ctl->lc[LC_EVENTS];
-				st->cnt[NS_CNT_RETIMES] += ctl->lc[LC_RETIMES];
-				st->cnt[NS_CNT_WAVES] += 1;
-				{ u64 k_ = ctl->dbg_key; st->phase_ns[13] += k_ >> 20; if ((k_ >> 20) > st->phase_ns[10]) { st->phase_ns[10] = k_ >> 20; st->phase_ns[11] = ctl->dbg_deg; st->phase_ns[12] = k_ & 0xfffff; } ctl->dbg_key = 0; st->phase_ns[14] += ctl->n_deferred; }
-				st->cnt[NS_CNT_SEQ] = st->tail;
-				for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
-				// next segment, clipped to the remaining event budget
-				u64 evn = st->cnt[NS_CNT_EVENTS];
-				u64 bud = ev_max ? (ev_max > evn ? ev_max-evn : 0) : ~0ull;
-				u64 lim = bud < (u64)P.seg_cap ? bud : (u64)P.seg_cap;
-				int nlo = seg_hi, left = nb-seg_hi;
-				ctl->seg_lo = nlo;
-				ctl->seg_hi = (left <= 0 || lim < PAR_MIN_BATCH) ? nlo : nlo+((u64)left < lim ? left : (int)lim);
-				ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
-				ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
-				*P.stage.ovf_top = 0;
-			}
-			grid.sync();
 			PHASE_MARK(PH_COMMIT);
+			if (last) { if (leader) { par_finish_piece(S, st, ctl, P); ctl->piece = PIECE_END; } done_all = true; break; }
 		}
-		// whatever the parallel prefix left goes back under the tile minima (event budget exhausted:
-		// the whole grid lowers one minimum per touched tile) or, if events were cancelled and budget
-		// remains, through the sequential path, which stops at the exact count
-		if (ctl->seg_lo < nb) {
-			const int lo = ctl->seg_lo;
-			const u64 evn = st->cnt[NS_CNT_EVENTS];
-			if (st->status == 0 && ev_max && evn >= ev_max) {
+		// a stop condition hit inside the batch: what was extracted but not handled goes back under the
+		// tile minima (the whole grid lowers one minimum per touched ring tile; the few long-lived
+		// events are re-armed by the leader)
+		if (!done_all) {
+			const int lo = ctl->pos, l0 = ctl->li;
+			if (lo < nb) {
 				for (u64 k = lo+gtid; k < (u64)nb; k += gth) {
 					u64 tl = S.b_seq[k] >> NS_TILE_SHIFT;
 					if (k == (u64)lo || (S.b_seq[k-1] >> NS_TILE_SHIFT) != tl) tmin_lower(&S.q_tmin[tl & tmask], m);
 				}
-			} else if (blockIdx.x == 0 && warp == 0) {
-				Ctx c; ctx_load(c, sp, lane);
-				c.now = m;
-				seq_process(c, m, lo, nb, 0, 0, sc);
-				L0 st->cnt[NS_CNT_SEQ] = c.tail;
-				ctx_flush(c);
+			}
+			if (leader) for (int k = l0; k < nl; k++) {
+				int slot = sc.lb_ref[k];
+				if (S.l_time[slot] == m && S.l_seq[slot] == sc.lb_seq[k]) tmin_lower(&S.l_tmin[slot >> NS_TILE_SHIFT], m);
 			}
 			PHASE_MARK(PH_TAIL);
 		}

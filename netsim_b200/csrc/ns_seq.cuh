@@ -223,11 +223,12 @@ __device__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, cons
 	__syncwarp();
 }
 
-// process batch entries [i0,nr) x [j0,nl) in sequence order, strictly sequentially
-__device__ void seq_process(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
+// process batch entries [i,nr) x [j,nl) in sequence order, strictly sequentially; stops early on
+// status / sim_end / max_events / host stop and reports how far it got
+__device__ void seq_process(Ctx &c, double m, int &i, int nr, int &j, int nl, const SeqScratch &sc){
 	const Sim &S = *c.S;
 	while (i < nr || j < nl) {
-		if (seq_should_stop(c)) { seq_restore(c, m, i, nr, j, nl, sc); return; }
+		if (seq_should_stop(c)) return;
 		u64 sr = i < nr ? S.b_seq[i] : ~0ull;
 		u64 sl = j < nl ? sc.lb_seq[j] : ~0ull;
 		if (sr < sl) { seq_handle_ring(c, m, sr); i++; }
@@ -256,7 +257,9 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 		c.now = m;                                                    // main.c:60
 		cnt_add(c, NS_CNT_BATCHES, 1);
 		L0 { if ((u64)(nr+nl) > c.st->cnt[NS_CNT_MAX_BATCH]) c.st->cnt[NS_CNT_MAX_BATCH] = nr+nl; }
-		seq_process(c, m, 0, nr, 0, nl, sc);
+		int pi = 0, pj = 0;
+		seq_process(c, m, pi, nr, pj, nl, sc);
+		if (pi < nr || pj < nl) seq_restore(c, m, pi, nr, pj, nl, sc);   // max_events / sim_end mid-batch
 		__syncwarp();
 	}
 	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;

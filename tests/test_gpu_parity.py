@@ -196,3 +196,22 @@ def test_engine_churn_arrivals_departures(mname, mode, built):
     ce, co = e.counters(), o.counters()
     assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
     e.close()
+
+
+def test_engine_mixed_batches_use_parallel_pieces(built):
+    """Arrivals on a 20 ms grid land on the same timestamps as the speed-change cascades: one batch then
+    holds USER events (flow creations) between long runs of SPEED_CHANGE events.  The engine must split
+    it into pieces — parallel for the runs, sequential for the USER events — and stay bit-identical."""
+    sc = S.swarm(1500, 6, n_catalogue=8, seeds_per_peer=3, mean_strips=5.0, arrival_window=1.0, arrival_quantum=0.02)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(400000) == 0
+    e = E.Engine(b, mode=E.MODE_AUTO, records=True, trace=True, trace_cap=500000, record_cap=64 << 20)
+    assert e.run(123457) == 0                      # stop inside a batch, resume
+    assert e.run(400000) == 0
+    assert e.records() == o.records()
+    assert e.trace().tobytes() == o.trace().tobytes()
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    assert ce["user"] > 100 and ce["par_events"] > 10000
+    e.close()
