@@ -490,7 +490,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 
 // ---------------------------------------------------------------- adjacency arrays (node->conns[dir])
 // list_add at head (flow.c:311-312) == append; list_del (flow.c:251-252) == tombstone.
-__device__ void adj_append(Ctx &c, int g, int f, int dir){
+__device__ __noinline__ void adj_append(Ctx &c, int g, int f, int dir){
 	const Sim &S = *c.S;
 	int off = S.adj_off[g], cap = S.adj_cap[g], len = S.adj_len[g], live = S.adj_live[g];
 	if (len == cap) {
@@ -568,7 +568,7 @@ __device__ __forceinline__ int store_get(const Sim &S, int node, uint32_t rid){ 
 		if (S.s_id[r] == rid) return r;
 	return -1;
 }
-__device__ int resource_new(Ctx &c, int node, uint32_t rid, long long len){          // data.h:241-249, store.h:25-35
+__device__ __noinline__ int resource_new(Ctx &c, int node, uint32_t rid, long long len){          // data.h:241-249, store.h:25-35
 	const Sim &S = *c.S;
 	int i = 0;
 	if (c.pre_slot >= 0) { L0 i = atomicAdd(&c.st->hi_res, 1); i = __shfl_sync(FULLMASK, i, 0); }
@@ -601,7 +601,7 @@ __device__ int range_get(const Sim &S, int res, int start){
 	return r;
 }
 // resource_new_range, range.h:71-82: sorted insert by start; the skip-list insert burns one random()
-__device__ int resource_new_range(Ctx &c, int res, long long start, double len, double last){
+__device__ __noinline__ int resource_new_range(Ctx &c, int res, long long start, double len, double last){
 	const Sim &S = *c.S;
 	int i = c.pre_slot >= 0 ? c.st->hi_range+c.pre_slot : c.st->free_range;      // parallel init: slot = base + ordinal
 	if (c.pre_slot >= 0) { if (i >= S.cap_ranges) { set_status(c, NS_E_TABLE_FULL); return -1; } }
@@ -627,7 +627,7 @@ __device__ int resource_new_range(Ctx &c, int res, long long start, double len, 
 }
 
 // range_merge_with_next, range.c:83-124
-__device__ void range_merge_with_next(Ctx &c, int r){
+__device__ __noinline__ void range_merge_with_next(Ctx &c, int r){
 	const Sim &S = *c.S;
 	int nr = S.r_next[r];
 	if (nr < 0) return;
@@ -669,7 +669,7 @@ __device__ void range_merge_with_next(Ctx &c, int r){
 
 // ---------------------------------------------------------------- flows
 // flow_create, flow.c:296-337
-__device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
+__device__ __noinline__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
 	const Sim &S = *c.S;
 	int f = c.pre_slot >= 0 ? c.pre_slot : c.st->free_flow;
 	if (c.pre_slot >= 0) { if (f >= S.cap_flows) { set_status(c, NS_E_TABLE_FULL); return -1; } }
@@ -705,7 +705,7 @@ __device__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
 }
 
 // flow_close, flow.c:241-292
-__device__ void flow_close(Ctx &c, int f){
+__device__ __noinline__ void flow_close(Ctx &c, int f){
 	const Sim &S = *c.S;
 	int src = S.f_peer[0][f], dst = S.f_peer[1][f];
 	double ub = S.f_ub[f];
@@ -739,7 +739,7 @@ __device__ void flow_close(Ctx &c, int f){
 }
 
 // sim_establish_flow, sim.c:42-94
-__device__ int sim_establish_flow(Ctx &c, uint32_t rid, long long start, int src, int dst, double ub, double delay){
+__device__ __noinline__ int sim_establish_flow(Ctx &c, uint32_t rid, long long start, int src, int dst, double ub, double delay){
 	const Sim &S = *c.S;
 	int sr = store_get(S, src, rid);
 	if (sr < 0) return -1;                                            // :49-53
@@ -805,7 +805,7 @@ __device__ void handle_speed_change(Ctx &c, int f, int type, double speed){
 __device__ void run_group(Ctx &c, int g);
 
 // flow_done_handler (flow.c:391-401), the script's HNDR_USER slot, flow_done_cleaner (flow.c:403-406)
-__device__ void handle_flow_done(Ctx &c, int f){
+__device__ __noinline__ void handle_flow_done(Ctx &c, int f){
 	const Sim &S = *c.S;
 	flow_range_update(c, f);
 	int drng = S.f_drng[f];
@@ -836,7 +836,7 @@ __device__ void handle_flow_done(Ctx &c, int f){
 }
 
 // flow_throttle_handler, flow.c:408-423
-__device__ void handle_throttle(Ctx &c, int f){
+__device__ __noinline__ void handle_throttle(Ctx &c, int f){
 	const Sim &S = *c.S;
 	int prod = S.r_prod[S.f_srng[f]];
 	if (prod < 0) { set_status(c, NS_E_NO_PRODUCER); return; }
@@ -853,7 +853,7 @@ __device__ void handle_throttle(Ctx &c, int f){
 }
 
 // one group of script operations == what oracle/ref_scenario.c run_group() does through the module API
-__device__ void run_group(Ctx &c, int g){
+__device__ __noinline__ void run_group(Ctx &c, int g){
 	const Sim &S = *c.S;
 	int lo = S.group_off[g], hi = S.group_off[g+1];
 	for (int i = lo; i < hi; i++) {
@@ -907,7 +907,7 @@ __device__ void run_group(Ctx &c, int g){
 
 // operations injected by a host-side module handler (sim_establish_flow / event_add / flow_close /
 // sim_end called from inside a handler), executed at the current `now`
-__device__ void run_host_ops(Ctx &c, int n){
+__device__ __noinline__ void run_host_ops(Ctx &c, int n){
 	const Sim &S = *c.S;
 	for (int i = 0; i < n; i++) {
 		if (c.st->status) return;
@@ -969,6 +969,7 @@ __device__ void run_host_ops(Ctx &c, int n){
 struct GFlow {
 	int nf, ord; unsigned id;
 	double ub, sp, delay, share;      // share = get_share(f, dir): constant inside a segment (flow.c:61)
+	double rshare;                    // get_share(f, !dir), the share at the flow's other end (flow.c:140,165)
 	int dr, sr, npos;
 	long long d_start, s_start;
 	double d_len, d_lenc, d_last, s_len, s_last;
@@ -979,6 +980,7 @@ __device__ __forceinline__ void ge_load(const Sim &S, GFlow &g, int off, int len
 	int f = g.nf;
 	g.ord = S.f_ord[f]; g.id = S.f_id[f]; g.ub = S.f_ub[f]; g.sp = S.f_speed[dir][f]; g.delay = S.f_delay[f];
 	g.share = total > mx ? g.ub*mx/total : g.ub;
+	g.rshare = get_share(S, f, !dir);
 	if (dir == RCV) {
 		g.dr = S.f_drng[f]; g.sr = S.f_srng[f];
 		g.d_start = S.r_start[g.dr]; g.s_start = S.r_start[g.sr];
@@ -987,6 +989,28 @@ __device__ __forceinline__ void ge_load(const Sim &S, GFlow &g, int off, int len
 		int nx = S.r_next[g.dr];
 		g.npos = nx >= 0 ? (int)S.r_start[nx] : (int)S.r_total[g.dr];
 	}
+}
+// range_calc_and_requeue_events (range.c:16-79) of the lane's own flow on its registers (source range
+// static: relay-free segment), write-through; fills the plan, the caller assigns sequence numbers
+__device__ __forceinline__ void ge_retime_regs(const Sim &S, SimState *st, GFlow &g, double now, Retime &p){
+	const int f = g.nf;
+	p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
+	S.l_time[2*f] = NS_INF; S.l_time[2*f+1] = NS_INF;                 // range.c:19-20
+	if (now != g.s_last) { g.s_last = now; S.r_last[g.sr] = now; }    // range.c:21 -> range.h:91-118
+	if (now != g.d_last) {
+		double delta = g.sp*(now-g.d_last), t;
+		delta = delta-g.d_lenc;
+		t = delta+g.d_len;
+		g.d_lenc = (t-g.d_len)-delta;
+		g.d_len = t;
+		g.d_last = now;
+		S.r_lenc[g.dr] = g.d_lenc; S.r_len[g.dr] = g.d_len; S.r_last[g.dr] = now;
+	}
+	if (g.sp < NS_EPS) return;                                        // range.c:26-27
+	int dtype = -1;
+	int err = retime_math(now, g.sp, false, 0.0, NS_INF, g.s_len, g.d_len, g.d_start, g.s_start, g.npos, p, dtype);
+	if (dtype >= 0) S.f_drain_type[f] = (uint8_t)dtype;
+	if (err) atomicCAS(&st->status, 0, err);
 }
 // queue_speed_event (flow.c:16-29) with the delay taken from the lane's registers
 __device__ __forceinline__ void ge_emit(Ctx &lc, const GFlow &g, int dir, double speed){
@@ -1031,18 +1055,133 @@ __device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g,
 	}
 	if (type == RCV) {                                                // flow.c:367-370 -> range.c:16-79
 		lc.lc[LC_RETIMES] += 1;
-		Retime p; p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
-		S.l_time[2*f] = NS_INF; S.l_time[2*f+1] = NS_INF;
-		if (!(g.sp < NS_EPS)) {
-			int dtype = -1;
-			int err = retime_math(now, g.sp, false, 0.0, NS_INF, g.s_len, g.d_len, g.d_start, g.s_start, g.npos, p, dtype);
-			if (dtype >= 0) S.f_drain_type[f] = (uint8_t)dtype;
-			if (err) atomicCAS(&lc.st->status, 0, err);
-		}
+		Retime p;
+		ge_retime_regs(S, lc.st, g, now, p);
 		int k = p.add_drain+p.add_done;
 		if (k) { u64 seq = seq_reserve(lc, k); retime_commit_1(lc, f, p, seq); }
 	} else if (delta0 > 0)
 		ge_emit(lc, g, RCV, g.sp);                                    // flow.c:371-374
 	write_record(lc, R_SPD|type, g.id, -1, 0, speed);                 // flow.c:383
 	trace_row(lc, EV_SPEED_CHANGE|(type << 8), g.ord, speed, g.sp);
+}
+
+// one SPEED_CHANGE that reaches bwspread's full spread (flow.c:126-203), on the register-resident
+// group: lane p holds the flow at list position p (newest = highest p), so the reference's in-order
+// sums run from lane 31 down to lane 0.  Warp-uniform; `owner` is the lane holding the event's flow.
+__device__ void ge_full_event(Ctx &c, const Sim &S, GFlow &g, double &usage, double total, double mx, unsigned node_id,
+		int n, int dir, double speed, int owner){
+	const int lane = c.lane;
+	const double now = c.now;
+	const bool me = lane == owner;
+	const int live = __popc(__ballot_sync(FULLMASK, g.nf >= 0));
+	cnt_add(c, NS_CNT_EVENTS, 1); cnt_add(c, NS_CNT_SPEED_CHANGE, 1); cnt_add(c, NS_CNT_SOLVES, 1);
+	cnt_add(c, NS_CNT_FULL_SPREADS, 1); cnt_add(c, NS_CNT_FLOW_VISITS, 2ull*(u64)live);
+	if (dir == RCV && me) {                                           // flow.c:355-357, with the OLD speed
+		if (now != g.s_last) { g.s_last = now; S.r_last[g.sr] = now; }
+		if (now != g.d_last) {
+			double delta = g.sp*(now-g.d_last), t;
+			delta = delta-g.d_lenc;
+			t = delta+g.d_len;
+			g.d_lenc = (t-g.d_len)-delta;
+			g.d_len = t;
+			g.d_last = now;
+			S.r_lenc[g.dr] = g.d_lenc; S.r_len[g.dr] = g.d_len; S.r_last[g.dr] = now;
+		}
+	}
+	double fs = __shfl_sync(FULLMASK, g.sp, owner);
+	const double share = __shfl_sync(FULLMASK, g.share, owner), odelay = __shfl_sync(FULLMASK, g.delay, owner);
+	const int of = __shfl_sync(FULLMASK, g.nf, owner);
+	const double delta0 = speed-fs;                                   // flow.c:359
+	double amount = delta0;
+	if (amount > NS_EPS && fs+amount > share) {                       // flow.c:64-78 (fs <= share here)
+		double t = now+odelay;
+		if (ev_time_ok(c, t)) { u64 seq = seq_reserve(c, 1); if (me) ring_put(c, seq, t, share, of, !dir); }
+		amount = share-fs;
+	}
+	fs += amount;                                                     // flow.c:85
+	if (me) { g.sp = fs; S.f_speed[dir][of] = fs; }
+	double spread_amount = amount;                                    // flow.c:112-124
+	if (amount > -NS_EPS) spread_amount = amount-mx+usage;
+	stage_ensure(c, (dir == RCV ? 3ull : 1ull)*(u64)live+8);
+	const bool dec = amount < NS_EPS, inc = !dec && amount > NS_EPS;
+	double term = 0.0;                                                // flow.c:128-145
+	if (g.nf >= 0 && !me) {
+		if (dec) { if (g.sp < g.rshare) term = g.rshare-g.sp; }
+		else if (inc) { if (g.sp > g.share) term = g.sp-g.share; }
+	}
+	double e = 0;
+	#pragma unroll
+	for (int l = 31; l >= 0; l--) e += __shfl_sync(FULLMASK, term, l);
+	if (dec && -amount > e) amount = -e;                              // flow.c:149-154
+	const bool dec2 = amount < NS_EPS, inc2 = !dec2 && amount > NS_EPS;
+	double val = 0.0, emit_speed = 0;                                 // flow.c:156-200
+	int adj = 0;
+	Retime rp; rp.add_drain = rp.add_done = 0;
+	if (me) val = fs;
+	else if (g.nf >= 0) {
+		const double sp = g.sp;
+		val = sp;
+		if (dec2) {
+			if (sp < g.rshare) {
+				double delta = g.rshare-sp;
+				double new_speed = sp-amount*delta/e;                 // :171
+				if (dir == SND) { g.sp = new_speed; S.f_speed[dir][g.nf] = new_speed; val = new_speed; }
+				adj = 1; emit_speed = new_speed;
+			}
+		} else if (inc2) {
+			if (sp > g.share) {
+				double delta = sp-g.share;
+				double ns = sp-spread_amount*delta/e;                 // :187
+				g.sp = ns; S.f_speed[dir][g.nf] = ns; val = ns;
+				adj = 1; emit_speed = ns;
+			}
+		}
+	}
+	double et = 0; int ok = 0;
+	if (adj) {
+		et = now+g.delay;
+		ok = 1;
+		if (et < now) { if (et < now-NS_EPS) ok = 0; else et = now; }
+		if (isnan(et)) ok = 0;
+		if (!ok) atomicCAS(&c.st->status, 0, isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME);
+		if (dir == RCV && inc2) ge_retime_regs(S, c.st, g, now, rp);  // :193-194, with the NEW speed
+	}
+	if (dir == RCV && inc2) cnt_add(c, NS_CNT_RETIMES, __popc(__ballot_sync(FULLMASK, adj)));
+	{
+		int k = ok+rp.add_drain+rp.add_done;
+		int incl = k;                                                 // suffix sum: list order is descending lane
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { int t = __shfl_down_sync(FULLMASK, incl, d); if (lane+d < 32) incl += t; }
+		int tot = __shfl_sync(FULLMASK, incl, 0);
+		if (tot) {
+			u64 seq0 = seq_reserve(c, tot);
+			u64 seq = seq0+(u64)(incl-k);
+			if (ok) { ring_put(c, seq, et, emit_speed, g.nf, !dir); seq++; }
+			if (adj) retime_commit_1(c, g.nf, rp, seq);
+		}
+	}
+	double new_use = 0;
+	#pragma unroll
+	for (int l = 31; l >= 0; l--) new_use += __shfl_sync(FULLMASK, val, l);   // :199
+	usage = new_use;                                                  // :201-202
+	if (lane == 0) S.n_usage[dir][n] = usage;
+	write_record(c, R_USAGE|dir, node_id, -1, 0, usage);
+	// the rest of handle_speed_change (flow.c:367-383)
+	if (dir == RCV) {
+		cnt_add(c, NS_CNT_RETIMES, 1);
+		Retime p; p.add_drain = p.add_done = 0;
+		if (me) ge_retime_regs(S, c.st, g, now, p);
+		p.add_drain = __shfl_sync(FULLMASK, p.add_drain, owner);
+		p.add_done = __shfl_sync(FULLMASK, p.add_done, owner);
+		int k = p.add_drain+p.add_done;
+		if (k) { u64 seq = seq_reserve(c, k); if (me) retime_commit_1(c, of, p, seq); }
+	} else if (delta0 > 0) {
+		double t = now+odelay;
+		if (ev_time_ok(c, t)) { u64 seq = seq_reserve(c, 1); if (me) ring_put(c, seq, t, g.sp, of, RCV); }
+	}
+	const unsigned oid = __shfl_sync(FULLMASK, g.id, owner);
+	const int oord = __shfl_sync(FULLMASK, g.ord, owner);
+	const double osp = __shfl_sync(FULLMASK, g.sp, owner);
+	write_record(c, R_SPD|dir, oid, -1, 0, speed);
+	trace_row(c, EV_SPEED_CHANGE|(dir << 8), oord, speed, osp);
 }

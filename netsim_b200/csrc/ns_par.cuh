@@ -103,7 +103,7 @@ __device__ __forceinline__ double block_min_d(double v, double *sh){
 
 // ascending in-place sort of a[0..n) by one warp (bitonic network with mirrored first stage, so a
 // virtual +inf padding needs no storage)
-__device__ void warp_sort_global(int *a, int n, int lane){
+__device__ __noinline__ void warp_sort_global(int *a, int n, int lane){
 	int np = 1; while (np < n) np <<= 1;
 	for (int k = 2; k <= np; k <<= 1) {
 		for (int i = lane; i < np; i += 32) {
@@ -187,13 +187,24 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 					else if (amount > -NS_EPS && usage+amount < mx+NS_EPS) full = false;
 				}
 			}
-			if (full) {
-				// a full spread (or a flow this lane set does not hold): the table-driven warp handler;
-				// the cache is write-through, so the tables are current; reload afterwards
+			if (full && owner < 0) {
+				// a flow this lane set does not hold (cannot happen for a consistent group): table-driven
+				// handler; the cache is write-through, so the tables are current; reload afterwards
 				__syncwarp();
 				par_handle_event(c, P, seg_lo, e, m);
 				ge_load(S, gf, a_off, a_len, lane, dir, total, mx);
 				usage = S.n_usage[dir][n];
+				continue;
+			}
+			if (full) {
+				c.ev = (unsigned)e; c.lseq = 0; c.rec_n = 0; c.tr_n = 0; c.ovf_base = -1;
+				ge_full_event(c, S, gf, usage, total, mx, node_id, n, dir, speed, owner);
+				if (lane == 0) {
+					const ParStage &ps = *c.ps;
+					ps.ev_nins[e] = c.lseq; ps.ev_ovf[e] = c.ovf_base;
+					ps.ev_nrec[e] = (uint8_t)c.rec_n; ps.ev_ntr[e] = (uint8_t)c.tr_n;
+					S.q_time[slot] = NS_INF;                          // event_pop
+				}
 				continue;
 			}
 			if (lane == owner) {
@@ -260,7 +271,7 @@ __device__ __forceinline__ int lower_bound_seq(const u64 *a, int lo, int hi, u64
 	while (lo < hi) { int mid = (lo+hi) >> 1; if (a[mid] < key) lo = mid+1; else hi = mid; }
 	return lo;
 }
-__device__ void par_finish_piece(const Sim &S, SimState *st, ParScratch::Ctl *ctl, const ParScratch &P){
+__device__ __noinline__ void par_finish_piece(const Sim &S, SimState *st, ParScratch::Ctl *ctl, const ParScratch &P){
 	st->tail += ctl->tot_ins; st->burns += ctl->tot_ins;
 	st->rec_len += S.want_rec ? ctl->tot_rec : 0;
 	u64 ntr = st->tr_len+ctl->tot_tr;
@@ -278,7 +289,7 @@ __device__ void par_finish_piece(const Sim &S, SimState *st, ParScratch::Ctl *ct
 	ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 	*P.stage.ovf_top = 0;
 }
-__device__ void par_plan_piece(const Sim &S, SimState *st, ParScratch::Ctl *ctl, const ParScratch &P, const SeqScratch &sc, int nb, int nl){
+__device__ __noinline__ void par_plan_piece(const Sim &S, SimState *st, ParScratch::Ctl *ctl, const ParScratch &P, const SeqScratch &sc, int nb, int nl){
 	if (ctl->piece == PIECE_PAR) par_finish_piece(S, st, ctl, P);
 	ctl->piece = PIECE_END; ctl->last = 0;
 	const u64 ev_max = st->max_events, evn = st->cnt[NS_CNT_EVENTS];

@@ -86,7 +86,7 @@ __device__ int seq_collect_ring(Ctx &c, double m){
 }
 
 // Step 2b: long-lived events with time == m, sorted by sequence number.
-__device__ int seq_collect_l(Ctx &c, double m, const SeqScratch &sc){
+__device__ __noinline__ int seq_collect_l(Ctx &c, double m, const SeqScratch &sc){
 	const Sim &S = *c.S;
 	const int lane = c.lane;
 	int nl = 0;
@@ -151,7 +151,7 @@ __device__ __forceinline__ void host_report(Ctx &c, int type, int f, int dir, do
 
 // handle one long-lived event (FLOW_DONE / FLOW_DRAIN / FLOW_SPEED_THROTTLE / USER); returns false
 // when it had been cancelled or re-timed after extraction.
-__device__ bool seq_handle_l(Ctx &c, double m, u64 seq, int slot){
+__device__ __noinline__ bool seq_handle_l(Ctx &c, double m, u64 seq, int slot){
 	const Sim &S = *c.S;
 	if (!(S.l_time[slot] == m && S.l_seq[slot] == seq)) return false;
 	__syncwarp();
@@ -209,7 +209,7 @@ __device__ __forceinline__ bool seq_should_stop(Ctx &c){
 }
 
 // put the unprocessed tail of a batch back under the tile minima (max_events / sim_end mid-batch)
-__device__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
+__device__ __noinline__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
 	const Sim &S = *c.S;
 	for (int k = i+c.lane; k < nr; k += 32) {
 		u64 seq = S.b_seq[k];
@@ -225,7 +225,7 @@ __device__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, cons
 
 // process batch entries [i,nr) x [j,nl) in sequence order, strictly sequentially; stops early on
 // status / sim_end / max_events / host stop and reports how far it got
-__device__ void seq_process(Ctx &c, double m, int &i, int nr, int &j, int nl, const SeqScratch &sc){
+__device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &j, int nl, const SeqScratch &sc){
 	const Sim &S = *c.S;
 	while (i < nr || j < nl) {
 		if (seq_should_stop(c)) return;
