@@ -1013,27 +1013,34 @@ __device__ __forceinline__ void ge_retime_regs(const Sim &S, SimState *st, GFlow
 	if (err) atomicCAS(&st->status, 0, err);
 }
 // queue_speed_event (flow.c:16-29) with the delay taken from the lane's registers
-__device__ __forceinline__ void ge_emit(Ctx &lc, const GFlow &g, int dir, double speed){
-	double t = lc.now+g.delay;
-	if (!ev_time_ok(lc, t)) return;
-	u64 seq = seq_reserve(lc, 1);
-	ring_put(lc, seq, t, speed, g.nf, dir);
+// staging pointers and flags of a chain, read once and kept in registers
+struct GeStage {
+	double *st_time, *st_speed; int *st_fd; uint8_t *st_rec; ns_trace_row32 *st_tr;
+	unsigned *ev_nins; long long *ev_ovf; uint8_t *ev_nrec, *ev_ntr;
+	int want_rec, want_tr;
+};
+__device__ __forceinline__ void ge_stage_load(GeStage &t, const Sim &S, const ParStage &ps){
+	t.st_time = ps.st_time; t.st_speed = ps.st_speed; t.st_fd = ps.st_fd; t.st_rec = ps.st_rec; t.st_tr = ps.st_tr;
+	t.ev_nins = ps.ev_nins; t.ev_ovf = ps.ev_ovf; t.ev_nrec = ps.ev_nrec; t.ev_ntr = ps.ev_ntr;
+	t.want_rec = S.want_rec; t.want_tr = S.want_tr;
 }
 // one O(1) SPEED_CHANGE (handle_speed_change with every bwspread exit of flow.c:64-124) executed by the
-// owner lane alone; lc is that lane's private staging context (scalar mode)
-__device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g, double &usage, unsigned node_id,
-		int n, int type, double speed){
-	const double now = lc.now;
+// owner lane alone, everything it needs in registers; e = the event's index in the segment (its
+// staging slot: at most 3 event_adds, 2 records, 1 trace row)
+__device__ __forceinline__ void ge_simple_event(const GeStage &t, const Sim &S, SimState *st, GFlow &g, double &usage,
+		unsigned node_id, int n, int type, double speed, double now, unsigned e, unsigned &n_ret){
 	const int f = g.nf;
-	lc.lc[LC_EVENTS] += 1; lc.lc[LC_SPEED_CHANGE] += 1; lc.lc[LC_SOLVES] += 1;
+	unsigned lseq = 0, rec_n = 0;
+	const u64 sbase = (u64)e*NS_STAGE_INLINE;
+	uint8_t *rbase = t.st_rec+(u64)e*NS_STAGE_REC;
 	if (type == RCV) {                                                // flow.c:355-357 -> range.h:91-125
 		if (now != g.s_last) { g.s_last = now; S.r_last[g.sr] = now; }
 		if (now != g.d_last) {
-			double delta = g.sp*(now-g.d_last), t;
+			double delta = g.sp*(now-g.d_last), tt;
 			delta = delta-g.d_lenc;
-			t = delta+g.d_len;
-			g.d_lenc = (t-g.d_len)-delta;
-			g.d_len = t;
+			tt = delta+g.d_len;
+			g.d_lenc = (tt-g.d_len)-delta;
+			g.d_len = tt;
 			g.d_last = now;
 			S.r_lenc[g.dr] = g.d_lenc; S.r_len[g.dr] = g.d_len; S.r_last[g.dr] = now;
 		}
@@ -1042,27 +1049,44 @@ __device__ __forceinline__ void ge_simple_event(Ctx &lc, const Sim &S, GFlow &g,
 	const double delta0 = speed-fs;                                   // flow.c:359
 	double amount = delta0;
 	const double share = g.share;                                     // flow.c:61
+	const double et = now+g.delay;                                    // queue_speed_event, flow.c:22
+	if (!(et >= now)) atomicCAS(&st->status, 0, isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME);
 	bool done_bw = false;
 	if (amount > NS_EPS && fs+amount > share) {                       // flow.c:64-78
-		if (fs > share) { ge_emit(lc, g, !type, fs); done_bw = true; }
-		else { ge_emit(lc, g, !type, share); amount = share-fs; }
+		double es = share;
+		if (fs > share) { es = fs; done_bw = true; } else amount = share-fs;
+		t.st_time[sbase+lseq] = et; t.st_speed[sbase+lseq] = es; t.st_fd[sbase+lseq] = f*2+(!type); lseq++;
 	}
 	if (!done_bw && !(amount > -NS_EPS && amount < NS_EPS)) {         // flow.c:80-124, the O(1) exits
 		fs += amount;
 		g.sp = fs; S.f_speed[type][f] = fs;
 		usage += amount; S.n_usage[type][n] = usage;
-		write_record(lc, R_USAGE|type, node_id, -1, 0, usage);        // record_wrapper.h:6-9
+		if (t.want_rec) rec_n += rec_encode(rbase+rec_n, now, R_USAGE|type, node_id, -1, 0, usage);   // record_wrapper.h:6-9
 	}
 	if (type == RCV) {                                                // flow.c:367-370 -> range.c:16-79
-		lc.lc[LC_RETIMES] += 1;
+		n_ret++;
 		Retime p;
-		ge_retime_regs(S, lc.st, g, now, p);
-		int k = p.add_drain+p.add_done;
-		if (k) { u64 seq = seq_reserve(lc, k); retime_commit_1(lc, f, p, seq); }
-	} else if (delta0 > 0)
-		ge_emit(lc, g, RCV, g.sp);                                    // flow.c:371-374
-	write_record(lc, R_SPD|type, g.id, -1, 0, speed);                 // flow.c:383
-	trace_row(lc, EV_SPEED_CHANGE|(type << 8), g.ord, speed, g.sp);
+		ge_retime_regs(S, st, g, now, p);
+		if (p.add_done) {
+			if (p.add_drain) { t.st_fd[sbase+lseq] = NS_HOLE_PURE; lseq++; }
+			S.l_time[2*f] = p.done_t; S.l_seq[2*f] = NS_SEQ_PROV | ((u64)e << 24) | lseq;
+			tmin_lower(&S.l_tmin[(2*f) >> NS_TILE_SHIFT], p.done_t);
+			t.st_fd[sbase+lseq] = -(2*f+1); lseq++;
+		} else if (p.add_drain) {
+			S.l_time[2*f+1] = p.drain_t; S.l_seq[2*f+1] = NS_SEQ_PROV | ((u64)e << 24) | lseq;
+			tmin_lower(&S.l_tmin[(2*f+1) >> NS_TILE_SHIFT], p.drain_t);
+			t.st_fd[sbase+lseq] = -(2*f+1+1); lseq++;
+		}
+	} else if (delta0 > 0) {                                          // flow.c:371-374
+		t.st_time[sbase+lseq] = et; t.st_speed[sbase+lseq] = g.sp; t.st_fd[sbase+lseq] = f*2+RCV; lseq++;
+	}
+	if (t.want_rec) rec_n += rec_encode(rbase+rec_n, now, R_SPD|type, g.id, -1, 0, speed);   // flow.c:383
+	unsigned ntr = 0;
+	if (t.want_tr) {
+		ns_trace_row32 r; r.type = EV_SPEED_CHANGE|(type << 8); r.ord = g.ord; r.time = now; r.v0 = speed; r.v1 = g.sp;
+		t.st_tr[e] = r; ntr = 1;
+	}
+	t.ev_nins[e] = lseq; t.ev_ovf[e] = -1; t.ev_nrec[e] = (uint8_t)rec_n; t.ev_ntr[e] = (uint8_t)ntr;
 }
 
 // one SPEED_CHANGE that reaches bwspread's full spread (flow.c:126-203), on the register-resident

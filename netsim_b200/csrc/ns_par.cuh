@@ -153,9 +153,9 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 	const unsigned node_id = S.n_id[n];
 	GFlow gf;
 	ge_load(S, gf, a_off, a_len, lane, dir, total, mx);
-	Ctx lc = c;                                                       // the owner lane's private staging context
-	lc.scalar = 1; lc.lane = 0;
-	for (int q = 0; q < LC_N; q++) lc.lc[q] = 0;
+	GeStage stg;
+	ge_stage_load(stg, S, *c.ps);
+	unsigned n_simple = 0, n_ret = 0;                                 // this lane's O(1) events / their re-times
 	for (int j0 = j; j0 < cnt; j0 += 32) {
 		// fetch up to 32 events of the chain at once
 		int my_e = -1, my_fd = 0; double my_speed = 0; u64 my_slot = 0;
@@ -208,11 +208,8 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 				continue;
 			}
 			if (lane == owner) {
-				lc.ev = (unsigned)e; lc.lseq = 0; lc.rec_n = 0; lc.tr_n = 0; lc.ovf_base = -1;
-				ge_simple_event(lc, S, gf, usage, node_id, n, dir, speed);
-				const ParStage &ps = *lc.ps;
-				ps.ev_nins[e] = lc.lseq; ps.ev_ovf[e] = -1;
-				ps.ev_nrec[e] = (uint8_t)lc.rec_n; ps.ev_ntr[e] = (uint8_t)lc.tr_n;
+				ge_simple_event(stg, S, c.st, gf, usage, node_id, n, dir, speed, m, (unsigned)e, n_ret);
+				n_simple++;
 				S.q_time[slot] = NS_INF;                              // event_pop
 			}
 			usage = __shfl_sync(FULLMASK, usage, owner);
@@ -220,11 +217,8 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 		__syncwarp();
 	}
 	// the lanes' private counters
-	for (int q = 0; q < LC_N; q++) {
-		u64 v = lc.lc[q];
-		for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
-		c.lc[q] += v;
-	}
+	for (int d = 16; d; d >>= 1) { n_simple += __shfl_xor_sync(FULLMASK, n_simple, d); n_ret += __shfl_xor_sync(FULLMASK, n_ret, d); }
+	c.lc[LC_EVENTS] += n_simple; c.lc[LC_SPEED_CHANGE] += n_simple; c.lc[LC_SOLVES] += n_simple; c.lc[LC_RETIMES] += n_ret;
 	__syncwarp();
 }
 
