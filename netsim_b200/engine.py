@@ -182,8 +182,12 @@ class Engine:
     def phase_ms(self) -> dict:
         a = (C.c_uint64 * 16)()
         self.L.ns_dev_phase_ns(self.h, a)
-        names = ["argmin", "extract", "sequential", "group", "solve_warp", "commit", "tail", "kernel", "solve_thread", "p9", "slowest_group_ms", "slowest_group_degree_x1e6", "slowest_group_events_x1e6", "sum_slowest_ms", "deferred_groups_x1e6"]
-        return {n: a[i] / 1e6 for i, n in enumerate(names)}
+        ms = ["argmin", "extract", "sequential", "group", "solve_warp", "commit", "tail", "kernel", "solve_thread"]
+        out = {n: a[i] / 1e6 for i, n in enumerate(ms)}
+        # profiling aid of the warp pass: the slowest (node,dir) group seen in one segment
+        out.update({"slowest_group_ms": a[10] / 1e6, "slowest_group_degree": int(a[11]), "slowest_group_events": int(a[12]),
+                    "sum_slowest_ms": a[13] / 1e6, "deferred_groups": int(a[14])})
+        return out
 
     @property
     def launches(self) -> int:

@@ -72,13 +72,13 @@ if __name__ == "__main__":
     elif which == "windows":
         sc = S.swarm_fast(100032, 320, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
         e = E.Engine(sc.to_bytes(), mode=E.MODE_AUTO, records=True, record_cap=4 << 30)
-        last = {k: 0.0 for k in e.phase_ms()}
+        last = {k: 0 for k in e.phase_ms()}
         for i in range(1, 11):
             t0 = time.time()
             e.run(i * 2000000)
             w = time.time() - t0
             ph = e.phase_ms()
-            print(f"window {i}: device {e.device_ms:.1f} ms", {k: (round(ph[k] - last[k], 1) if 'x1e6' not in k else int(ph[k] * 1e6)) for k in ph if k not in ('p9', 'sequential', 'tail')}, flush=True)
+            print(f"window {i}: device {e.device_ms:.1f} ms", {k: (round(ph[k] - last[k], 1) if k.endswith('_ms') or k in ('argmin', 'extract', 'group', 'solve_warp', 'solve_thread', 'commit', 'kernel') else ph[k]) for k in ph if k not in ('sequential', 'tail')}, flush=True)
             last = ph
         e.close()
     elif which == "big":
