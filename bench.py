@@ -104,6 +104,17 @@ def run_reference(args, sc_bytes, steps, warmup, events_per_step):
             "init_seconds": wall - st["loop_seconds"], "record_file_bytes": rec_bytes, "total_events": st["events"]}
 
 
+def emit(line: dict) -> None:
+    """the ONE JSON line, on the process's real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# libraries (NCCL's version banner, nvcc/make chatter) must not reach stdout: keep the real stdout for the
+# JSON line and point fd 1 at stderr for everything else
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -135,7 +146,7 @@ def main():
         eps = args.ref_events_per_step
         r = run_reference(args, sc.to_bytes(), args.steps, args.warmup, eps)
         if r is None or "error" in r:
-            print(json.dumps({"impl": "reference", "unavailable": (r or {}).get("error", "oracle/_ref not built")}))
+            emit({"impl": "reference", "unavailable": (r or {}).get("error", "oracle/_ref not built")})
             return 0
         val = r["events_per_s"]
         config["events_per_step"] = eps
@@ -146,7 +157,7 @@ def main():
                                  "sample": f"{r['steps']} windows of {eps} events after {args.warmup} warm-up windows of the same script; "
                                            f"unmodified reference core, single-threaded by design; init {r['init_seconds']:.1f}s untimed"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -273,7 +284,7 @@ def main():
                                               f"{args.ref_events_per_step} events after 1 warm-up window; init {r['init_seconds']:.1f}s untimed"}
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": (r or {}).get("error", "oracle/_ref missing")}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
