@@ -44,7 +44,8 @@ enum ns_err {
 	NS_E_NO_PRODUCER = -5,   /* flow.c:411 */
 	NS_E_RING_FULL = -6,     /* pending-event ring too small: recreate with a larger ring_cap */
 	NS_E_TABLE_FULL = -7,    /* flow/range/resource/adjacency capacity exhausted */
-	NS_E_RECORDS_FULL = -8,  /* record buffer full: drain with ns_dev_records, then run again */
+	NS_E_RECORDS_FULL = -8,  /* ns_dev_run stopped BEFORE a batch whose records might not fit: copy the records
+	                            out, ns_dev_records_drain, run again (nothing is lost) */
 	NS_E_NO_DEVICE = -9,
 	NS_E_ARG = -10,
 	NS_E_BATCH_FULL = -11,
@@ -96,9 +97,15 @@ int  ns_dev_run(ns_dev *d, uint64_t max_events, float *device_ms);
 int  ns_dev_status(ns_dev *d);
 double ns_dev_now(ns_dev *d);
 int  ns_dev_counters(ns_dev *d, uint64_t out[NS_CNT_COUNT]);
-/* copy record bytes [offset, offset+cap) of the stream produced so far; *len = bytes copied,
- * *total = bytes produced so far. */
+/* copy record bytes [offset, offset+cap) of the STREAM (offsets keep counting across drains); *len = bytes
+ * copied, *total = bytes produced so far. */
 int  ns_dev_records(ns_dev *d, void *dst, size_t cap, size_t offset, size_t *len, size_t *total);
+/* the same copy issued on a side stream (dst: pinned host memory): it overlaps the next ns_dev_run, which
+ * only appends beyond the span; ns_dev_records_wait blocks until every issued copy has landed.
+ * This is the pinned record ring of the host's record writer (record.c:27-117 stays on the host). */
+int  ns_dev_records_async(ns_dev *d, void *dst, size_t cap, size_t offset, size_t *len, size_t *total);
+int  ns_dev_records_wait(ns_dev *d);
+int  ns_dev_records_drain(ns_dev *d);   /* all records produced so far were copied: reuse the buffer */
 int  ns_dev_digest(ns_dev *d, struct ns_digest *out);
 int  ns_dev_trace(ns_dev *d, struct ns_trace_row32 *dst, size_t cap_rows, size_t *rows);
 /* per creation ordinal {alive, speed[0], speed[1], drng->len}; per node {usage[0], usage[1],

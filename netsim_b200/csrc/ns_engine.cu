@@ -342,10 +342,12 @@ struct ns_dev {
 	int device = 0, mode = 0;
 	HostSim h;
 	Sim *d_sim = nullptr; SeqScratch *d_scr = nullptr;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;   // records leave on a side stream (ns_dev_records_async)
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e_run = nullptr;
 	uint64_t launches = 0;
 	int sm_count = 0;
+	size_t rec_total_host = 0;      // record bytes in the buffer when the last run returned
+	size_t rec_base_host = 0;       // ... and the stream offset of the buffer's first byte
 	u64 *d_hash = nullptr;
 };
 
@@ -376,8 +378,8 @@ extern "C" int ns_dev_create(ns_dev **out, const void *scenario, size_t len, con
 	d->sm_count = prop.multiProcessorCount;
 	int rc = build_sim(d->h, scenario, len, o, o.mode != NS_MODE_SEQ);
 	if (rc) { free_sim(d->h); delete d; return rc; }
-	CK(cudaStreamCreate(&d->stream));
-	CK(cudaEventCreate(&d->e0)); CK(cudaEventCreate(&d->e1));
+	CK(cudaStreamCreate(&d->stream)); CK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&d->e0)); CK(cudaEventCreate(&d->e1)); CK(cudaEventCreateWithFlags(&d->e_run, cudaEventDisableTiming));
 	CK(cudaMalloc(&d->d_sim, sizeof(Sim))); CK(cudaMalloc(&d->d_scr, sizeof(SeqScratch))); CK(cudaMalloc(&d->d_hash, 8));
 	CK(cudaMemcpy(d->d_sim, &d->h.S, sizeof(Sim), cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d->d_scr, &d->h.scr, sizeof(SeqScratch), cudaMemcpyHostToDevice));
@@ -401,6 +403,7 @@ extern "C" int ns_dev_run(ns_dev *d, uint64_t max_events, float *device_ms){
 	if (!d) return NS_E_ARG;
 	CK(cudaSetDevice(d->device));
 	CK(cudaMemcpyAsync(&d->h.S.st->max_events, &max_events, 8, cudaMemcpyHostToDevice, d->stream));
+	{ int zero = 0; CK(cudaMemcpyAsync(&d->h.S.st->host_stop, &zero, 4, cudaMemcpyHostToDevice, d->stream)); }
 	CK(cudaEventRecord(d->e0, d->stream));
 	if (d->mode == NS_MODE_SEQ) {
 		k_run_seq<<<1, 32, 0, d->stream>>>(d->d_sim, d->d_scr, 1);
@@ -413,7 +416,11 @@ extern "C" int ns_dev_run(ns_dev *d, uint64_t max_events, float *device_ms){
 	CK(cudaEventRecord(d->e1, d->stream));
 	CK(cudaStreamSynchronize(d->stream));
 	if (device_ms) CK(cudaEventElapsedTime(device_ms, d->e0, d->e1));
-	return ns_dev_status(d);
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	d->rec_total_host = st.rec_len;
+	d->rec_base_host = st.rec_base;
+	if (st.status == 0 && st.host_stop == 2) return NS_E_RECORDS_FULL;   // soft: drain the records, run again
+	return st.status;
 }
 
 extern "C" int ns_dev_status(ns_dev *d){
@@ -437,11 +444,40 @@ extern "C" int ns_dev_counters(ns_dev *d, uint64_t out[NS_CNT_COUNT]){
 extern "C" int ns_dev_records(ns_dev *d, void *dst, size_t cap, size_t offset, size_t *len, size_t *total){
 	if (!d) return NS_E_ARG;
 	SimState st; int rc = read_state(d, &st); if (rc) return rc;
-	if (total) *total = st.rec_len;
+	const size_t end = st.rec_base+st.rec_len;                   // offsets are positions in the whole stream
+	if (total) *total = end;
 	size_t n = 0;
-	if (offset < st.rec_len) n = std::min<size_t>(cap, st.rec_len-offset);
-	if (n && dst) CK(cudaMemcpy(dst, d->h.S.rec+offset, n, cudaMemcpyDeviceToHost));
+	if (offset >= st.rec_base && offset < end) n = std::min<size_t>(cap, end-offset);
+	if (n && dst) CK(cudaMemcpy(dst, d->h.S.rec+(offset-st.rec_base), n, cudaMemcpyDeviceToHost));
 	if (len) *len = n;
+	return 0;
+}
+// everything produced so far has been copied out: the buffer starts over (after NS_E_RECORDS_FULL)
+extern "C" int ns_dev_records_drain(ns_dev *d){
+	if (!d) return NS_E_ARG;
+	CK(cudaStreamSynchronize(d->copy_stream));
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	u64 nb = st.rec_base+st.rec_len, zero = 0;
+	CK(cudaMemcpy(&d->h.S.st->rec_base, &nb, 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(&d->h.S.st->rec_len, &zero, 8, cudaMemcpyHostToDevice));
+	d->rec_base_host = nb; d->rec_total_host = 0;
+	return 0;
+}
+// Records go back to the host on a side stream: the copy of the span produced by the last run overlaps
+// the next run (the engine only appends beyond it).  dst should be pinned host memory.
+extern "C" int ns_dev_records_async(ns_dev *d, void *dst, size_t cap, size_t offset, size_t *len, size_t *total){
+	if (!d || !dst) return NS_E_ARG;
+	const size_t base = d->rec_base_host, end = base+d->rec_total_host;
+	size_t n = 0;
+	if (offset >= base && offset < end) n = std::min<size_t>(cap, end-offset);
+	if (n) CK(cudaMemcpyAsync(dst, d->h.S.rec+(offset-base), n, cudaMemcpyDeviceToHost, d->copy_stream));
+	if (len) *len = n;
+	if (total) *total = end;
+	return 0;
+}
+extern "C" int ns_dev_records_wait(ns_dev *d){
+	if (!d) return NS_E_ARG;
+	CK(cudaStreamSynchronize(d->copy_stream));
 	return 0;
 }
 static int stream_hash(ns_dev *d, u64 rec_len, u64 *out){
@@ -456,8 +492,8 @@ extern "C" int ns_dev_digest(ns_dev *d, ns_digest *out){
 	if (!d || !out) return NS_E_ARG;
 	SimState st; int rc = read_state(d, &st); if (rc) return rc;
 	out->seed = st.seed; out->events = st.cnt[NS_CNT_EVENTS]; out->solves = st.cnt[NS_CNT_SOLVES];
-	out->record_bytes = st.rec_len; out->t_end = st.now; out->status = st.status;
-	return stream_hash(d, st.rec_len, (u64 *)&out->record_fnv1a);
+	out->record_bytes = st.rec_base+st.rec_len; out->t_end = st.now; out->status = st.status;
+	return stream_hash(d, st.rec_len, (u64 *)&out->record_fnv1a);   // digest of the bytes still in the buffer (the whole stream unless drained)
 }
 extern "C" int ns_dev_trace(ns_dev *d, ns_trace_row32 *dst, size_t cap_rows, size_t *rows){
 	if (!d) return NS_E_ARG;
@@ -580,6 +616,8 @@ extern "C" void ns_dev_destroy(ns_dev *d){
 	if (d->d_hash) cudaFree(d->d_hash);
 	if (d->e0) cudaEventDestroy(d->e0);
 	if (d->e1) cudaEventDestroy(d->e1);
+	if (d->e_run) cudaEventDestroy(d->e_run);
+	if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
 	if (d->stream) cudaStreamDestroy(d->stream);
 	delete d;
 }

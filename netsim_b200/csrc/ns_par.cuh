@@ -291,6 +291,12 @@ __device__ __noinline__ void par_plan_piece(const Sim &S, SimState *st, ParScrat
 	const int pos = ctl->pos, li = ctl->li;
 	if (pos >= nb && li >= nl) return;
 	const u64 budget = ev_max ? ev_max-evn : ~0ull;
+	if (S.want_rec) {                                                 // soft stop before a piece whose records might not fit
+		u64 reserve = S.rec_cap > 8ull*NS_REC_RESERVE ? NS_REC_RESERVE : S.rec_cap/8;
+		u64 left = (u64)(nb-pos)+(u64)(nl-li);
+		u64 next = left < (u64)P.seg_cap ? left : (u64)P.seg_cap;
+		if (st->rec_len+next*NS_REC_PER_EVENT+reserve > S.rec_cap) { st->host_stop = 2; return; }
+	}
 	const bool no_par = st->relay_seen || budget < PAR_MIN_BATCH;
 	const u64 ls = li < nl ? sc.lb_seq[li] : ~0ull;
 	int end = pos;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 		// ---- A: argmin over tile minima ------------------------------------------------------
 		if (leader) { ctl->tmin_bits = ~0ull; ctl->first_live = ~0ull; ctl->nl = 0; ctl->nb = 0; }
 		grid.sync();
-		if (st->status || st->exit_flag || (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events)) break;
+		if (st->status || st->exit_flag || st->host_stop || (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events)) break;
 		const u64 head = st->head, tail = st->tail;
 		const u64 t_first = head >> NS_TILE_SHIFT, t_last = tail ? (tail-1) >> NS_TILE_SHIFT : 0;
 		const u64 n_wt = tail > head ? t_last-t_first+1 : 0;

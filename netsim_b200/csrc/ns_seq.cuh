@@ -201,6 +201,16 @@ __device__ bool seq_handle_ring(Ctx &c, double m, u64 seq){
 	return true;
 }
 
+// records are appended by the handlers; a batch is only started when its worst case fits (two records
+// per SPEED_CHANGE, plus a reserve for the creates/closes of USER groups and FLOW_DONE handlers)
+#define NS_REC_PER_EVENT 64
+#define NS_REC_RESERVE (1u << 20)
+__device__ __forceinline__ bool rec_room_short(const Ctx &c, u64 n_events){
+	const Sim &S = *c.S;
+	if (!S.want_rec) return false;
+	u64 reserve = S.rec_cap > 8ull*NS_REC_RESERVE ? NS_REC_RESERVE : S.rec_cap/8;
+	return c.rec_len+n_events*NS_REC_PER_EVENT+reserve > S.rec_cap;
+}
 __device__ __forceinline__ bool seq_should_stop(Ctx &c){
 	SimState *st = c.st;
 	if (st->status || st->exit_flag || st->host_stop) return true;
@@ -254,6 +264,12 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 		if (nr < 0) { set_status(c, NS_E_BATCH_FULL); __syncwarp(); break; }
 		int nl = seq_collect_l(c, m, sc);
 		if (nr+nl == 0) continue;                                     // only stale lower bounds surfaced
+		if (rec_room_short(c, nr+nl)) {                               // soft stop BEFORE the batch: nothing is lost
+			seq_restore(c, m, 0, nr, 0, nl, sc);
+			L0 c.st->host_stop = 2;
+			__syncwarp();
+			break;
+		}
 		c.now = m;                                                    // main.c:60
 		cnt_add(c, NS_CNT_BATCHES, 1);
 		L0 { if ((u64)(nr+nl) > c.st->cnt[NS_CNT_MAX_BATCH]) c.st->cnt[NS_CNT_MAX_BATCH] = nr+nl; }

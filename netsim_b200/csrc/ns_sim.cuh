@@ -39,6 +39,7 @@ struct SimState {                 // mutable scalars of one simulation
 	int32_t rnd[31]; int32_t rf, rr;
 	int status, exit_flag, relay_seen, pad0;
 	u64 rec_len, tr_len;
+	u64 rec_base;                 // record bytes already drained by the host (ns_dev_records_drain)
 	u64 cnt[NS_CNT_COUNT];
 	int free_flow, hi_flow, free_range, hi_range, hi_res, free_user, hi_user, n_ord;
 	int adj_top, pad1;
@@ -47,7 +48,7 @@ struct SimState {                 // mutable scalars of one simulation
 	u64 phase_ns[16];             // leader-thread wall time per engine phase (profiling aid)
 	// host-callback mode (modules with their own handlers)
 	unsigned host_mask;           // bit t set: stop after every handled event of type t
-	int host_stop;                // set by the engine when it stopped for the host
+	int host_stop;                // 1: stopped for a host handler; 2: record buffer nearly full (drain, run again)
 	int pending_close;            // FLOW_DONE: flow whose flow_close (HNDR_CLEANER) runs on resume
 	int le_type, le_flow, le_ord, le_dir, le_token;   // the event the host must see
 	double le_time, le_speed;

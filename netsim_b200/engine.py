@@ -63,6 +63,9 @@ def lib():
         L.ns_dev_now.argtypes = [C.c_void_p]
         L.ns_dev_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ns_dev_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.ns_dev_records_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.ns_dev_records_wait.argtypes = [C.c_void_p]
+        L.ns_dev_records_drain.argtypes = [C.c_void_p]
         L.ns_dev_digest.argtypes = [C.c_void_p, C.POINTER(Digest)]
         L.ns_dev_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_flow_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -137,14 +140,32 @@ class Engine:
             raise NsError(rc, "ns_dev_counters")
         return dict(zip(COUNTERS, [int(x) for x in a]))
 
-    def records(self) -> bytes:
+    def records(self, offset: int = 0) -> bytes:
         n, tot = C.c_size_t(), C.c_size_t()
-        self.L.ns_dev_records(self.h, None, 0, 0, C.byref(n), C.byref(tot))
-        buf = C.create_string_buffer(max(1, tot.value))
-        rc = self.L.ns_dev_records(self.h, buf, tot.value, 0, C.byref(n), C.byref(tot))
+        self.L.ns_dev_records(self.h, None, 0, offset, C.byref(n), C.byref(tot))
+        want = max(0, tot.value - offset)
+        buf = C.create_string_buffer(max(1, want))
+        rc = self.L.ns_dev_records(self.h, buf, want, offset, C.byref(n), C.byref(tot))
         if rc:
             raise NsError(rc, "ns_dev_records")
         return buf.raw[:n.value]
+
+    def run_draining(self, max_events: int = 0) -> bytes:
+        """run to the end (or max_events) with a bounded record buffer: every NS_E_RECORDS_FULL stop is
+        answered by copying the records out and ns_dev_records_drain; returns the whole stream"""
+        out, off = [], 0
+        while True:
+            rc = self.run(max_events)
+            chunk = self.records(off)
+            out.append(chunk)
+            off += len(chunk)
+            if rc != -8:
+                if rc != 0:
+                    raise NsError(rc, "ns_dev_run")
+                return b"".join(out)
+            rc2 = self.L.ns_dev_records_drain(self.h)
+            if rc2:
+                raise NsError(rc2, "ns_dev_records_drain")
 
     def digest(self) -> dict:
         d = Digest()

@@ -215,3 +215,19 @@ def test_engine_mixed_batches_use_parallel_pieces(built):
     assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
     assert ce["user"] > 100 and ce["par_events"] > 10000
     e.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+def test_bounded_record_buffer_drains_without_loss(mname, mode, built):
+    """A record buffer far smaller than the stream: the engine stops BEFORE a batch that might not fit
+    (NS_E_RECORDS_FULL), the host drains and continues; the concatenated stream is the oracle's."""
+    sc = S.swarm(1500, 6, n_catalogue=8, seeds_per_peer=3, mean_strips=5.0)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b, trace=False)
+    assert o.run(200000) == 0
+    e = E.Engine(b, mode=mode, records=True, record_cap=3 << 20)
+    stream = e.run_draining(200000)
+    assert len(stream) > (3 << 20)                  # it really had to drain
+    assert stream == o.records()
+    assert e.counters()["events"] == 200000
+    e.close()
