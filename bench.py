@@ -211,6 +211,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     c0 = eng.counters()
+    launches0 = eng.launches
     barrier()
     dev_ms_sum, wall_sum, d2h = 0.0, 0.0, 0
     t_region = time.perf_counter()
@@ -280,7 +281,7 @@ def main():
                     "note": "wall clock per window through ns_dev_run + ns_dev_records_async (pinned two-slot record ring, side stream; the last "
                             "copy is waited for inside the timed region); script upload and init (create_init_s) happen once before "
                             "the windows, like the reference's untimed module init"},
-            "gpu_launches": args.steps * 1 + 1,
+            "gpu_launches": eng.launches - launches0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_run_par (persistent, one launch per window)", "algorithmic_bytes_per_launch": alg_bytes / args.steps}}
     if not args.no_cpu_baseline and world == 1:

@@ -29,6 +29,8 @@ namespace cgp = cooperative_groups;
 #endif
 #define PAR_WARPS (PAR_THREADS/32)
 #define PAR_MIN_BATCH 48          // smaller batches are cheaper on the single-warp path
+#define SPARSE_STREAK 6            // that many small batches in a row: the grid barriers cost more than the events
+#define SPARSE_MAX_TILES 4096     // ... provided one warp can scan the tile minima of both event stores
 
 struct ParScratch {
 	int enabled;
@@ -49,6 +51,7 @@ struct ParScratch {
 		u64 tmin_bits, first_live;
 		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
 		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
+		int small_streak;                          // consecutive small batches (sparse phase detection)
 		u64 dbg_key;
 		u64 tot_ins; unsigned tot_rec, tot_tr;
 		u64 lc[LC_N];
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 		// ---- A: argmin over tile minima ------------------------------------------------------
 		if (leader) { ctl->tmin_bits = ~0ull; ctl->first_live = ~0ull; ctl->nl = 0; ctl->nb = 0; }
 		grid.sync();
-		if (st->status || st->exit_flag || st->host_stop || (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events)) break;
+		if (st->status || st->exit_flag || st->host_stop || st->want_sparse || (st->max_events && st->cnt[NS_CNT_EVENTS] >= st->max_events)) break;
 		const u64 head = st->head, tail = st->tail;
 		const u64 t_first = head >> NS_TILE_SHIFT, t_last = tail ? (tail-1) >> NS_TILE_SHIFT : 0;
 		const u64 n_wt = tail > head ? t_last-t_first+1 : 0;
@@ -442,6 +445,9 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			st->cnt[NS_CNT_BATCHES] += 1;
 			if ((u64)(nb+nl) > st->cnt[NS_CNT_MAX_BATCH]) st->cnt[NS_CNT_MAX_BATCH] = nb+nl;
 			ctl->pos = 0; ctl->li = 0; ctl->piece = PIECE_END;
+			// sparse phase: many small batches in a row and event stores one warp can scan -> hand over to k_run_seq
+			ctl->small_streak = nb+nl < PAR_MIN_BATCH ? ctl->small_streak+1 : 0;
+			if (ctl->small_streak >= SPARSE_STREAK && n_wt+(u64)S.n_l_tiles <= SPARSE_MAX_TILES) { st->want_sparse = 1; ctl->small_streak = 0; }
 			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
 			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 			*P.stage.ovf_top = 0;
@@ -874,9 +880,28 @@ static int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm
 static int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){
 	int grid = 0, rc = par_grid((const void *)k_run_par, sm_count, &grid);
 	if (rc) return rc;
-	void *args[] = { (void *)&d_sim, (void *)&d_scr, (void *)&p };
-	cudaError_t e = cudaLaunchCooperativeKernel((void *)k_run_par, dim3(grid), dim3(PAR_THREADS), args, 0, stream);
-	if (e != cudaSuccess) return (int)e;
-	(*launches)++;
+	// The grid engine runs until it is done or asks for the single-warp engine (a sparse phase: many
+	// timestamps with a handful of events each, where six grid barriers per timestamp cost more than
+	// the events); that one hands back at the first timestamp that spans many ring tiles.
+	for (int round = 0; round < 1 << 20; round++) {
+		void *args[] = { (void *)&d_sim, (void *)&d_scr, (void *)&p };
+		cudaError_t e = cudaLaunchCooperativeKernel((void *)k_run_par, dim3(grid), dim3(PAR_THREADS), args, 0, stream);
+		if (e != cudaSuccess) return (int)e;
+		(*launches)++;
+		int flags[3];                                                     // sparse_mode, want_sparse, want_dense
+		if ((e = cudaMemcpyAsync(flags, &S.st->sparse_mode, sizeof flags, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return (int)e;
+		if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return (int)e;
+		if (!flags[1]) return 0;
+		int on[3] = { 1, 0, 0 };
+		if ((e = cudaMemcpyAsync(&S.st->sparse_mode, on, sizeof on, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)e;
+		k_run_seq<<<1, 32, 0, stream>>>(d_sim, d_scr, 1);
+		(*launches)++;
+		if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+		if ((e = cudaMemcpyAsync(flags, &S.st->sparse_mode, sizeof flags, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return (int)e;
+		if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return (int)e;
+		int off[3] = { 0, 0, 0 };
+		if ((e = cudaMemcpyAsync(&S.st->sparse_mode, off, sizeof off, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)e;
+		if (!flags[2]) return 0;                                          // it finished (or stopped) by itself
+	}
 	return 0;
 }

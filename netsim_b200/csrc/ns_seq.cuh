@@ -246,6 +246,7 @@ __device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &
 	}
 }
 
+#define NS_SPARSE_MAX_HIT_TILES 4
 __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 	Ctx c;
 	ctx_load(c, Sp, lane);
@@ -260,6 +261,17 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 		if (seq_should_stop(c)) break;
 		double m = seq_find_tmin(c);
 		if (m == NS_INF) break;                                       // queue empty (main.c:50)
+		if (c.st->sparse_mode && !c.st->relay_seen) {
+			// sparse phase of a big simulation: a timestamp spread over many ring tiles is a batch for
+			// the grid engine — leave it in place and hand back
+			const Sim &S = *c.S;
+			const u64 tmask = (u64)S.n_ring_tiles-1;
+			int hits = 0;
+			u64 first = c.head >> NS_TILE_SHIFT, last = c.tail ? (c.tail-1) >> NS_TILE_SHIFT : 0;
+			if (c.tail > c.head) for (u64 a = first+lane; a <= last; a += 32) hits += S.q_tmin[a & tmask] == m;
+			for (int d = 16; d; d >>= 1) hits += __shfl_xor_sync(FULLMASK, hits, d);
+			if (hits > NS_SPARSE_MAX_HIT_TILES) { L0 c.st->want_dense = 1; __syncwarp(); break; }
+		}
 		int nr = seq_collect_ring(c, m);
 		if (nr < 0) { set_status(c, NS_E_BATCH_FULL); __syncwarp(); break; }
 		int nl = seq_collect_l(c, m, sc);

@@ -50,6 +50,8 @@ struct SimState {                 // mutable scalars of one simulation
 	unsigned host_mask;           // bit t set: stop after every handled event of type t
 	int host_stop;                // 1: stopped for a host handler; 2: record buffer nearly full (drain, run again)
 	int pending_close;            // FLOW_DONE: flow whose flow_close (HNDR_CLEANER) runs on resume
+	int sparse_mode;              // k_run_seq launched by the grid engine's host loop for a sparse phase
+	int want_sparse, want_dense;  // engine hand-over requests between k_run_par and k_run_seq (ns_par.cuh)
 	int le_type, le_flow, le_ord, le_dir, le_token;   // the event the host must see
 	double le_time, le_speed;
 };

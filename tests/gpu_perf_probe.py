@@ -69,6 +69,25 @@ if __name__ == "__main__":
         o = pyoracle.Oracle(scs[3], trace=False); o.run(maxev)
         print("   replica 3 digest ok:", dg[3]["record_hash"] == E.stream_hash(o.records()), dg[3]["events"], o.counters()["events"])
         ens.close()
+    elif which == "sparse":
+        # small batches: a swarm run to completion (FLOW_DONE dominated tail) and a churn script
+        for name, sc in (("complete2000", S.swarm(2000, 8, n_catalogue=8, seeds_per_peer=3, mean_strips=4.0, res_len=40000)),
+                         ("churn5000", S.churn(5000, 16, rate=1000.0, mean_session=3.0, sim_end=10.0))):
+            b = sc.to_bytes()
+            t0 = time.time()
+            o = pyoracle.Oracle(b, trace=False)
+            o.run(0)
+            to = time.time() - t0
+            co = o.counters()
+            print(f"--- {name}: events {co['events']} done {co['flow_done']} user {co['user']} oracle {to:.2f}s -> {co['events']/to:.0f} ev/s", flush=True)
+            for mname, mode in both:
+                e = E.Engine(b, mode=mode, records=True, record_cap=256 << 20)
+                t1 = time.time()
+                st = e.run(0)
+                t2 = time.time()
+                c = e.counters()
+                print(f"{mname}: status {st} device {e.device_ms:.1f} ms -> {c['events']/(e.device_ms/1e3):.0f} ev/s; batches {c['batches']} par {c['par_events']} ok {e.records() == o.records()}", flush=True)
+                e.close()
     elif which == "windows":
         sc = S.swarm_fast(100032, 320, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
         e = E.Engine(sc.to_bytes(), mode=E.MODE_AUTO, records=True, record_cap=4 << 30)
