@@ -226,6 +226,7 @@ def main():
     barrier()
     t_region = time.perf_counter() - t_region
     sampler.stop_flag = True
+    launches1 = eng.launches
     c1 = eng.counters()
     dig = eng.digest()
     d = {k: c1[k] - c0[k] for k in c1}
@@ -281,7 +282,7 @@ def main():
                     "note": "wall clock per window through ns_dev_run + ns_dev_records_async (pinned two-slot record ring, side stream; the last "
                             "copy is waited for inside the timed region); script upload and init (create_init_s) happen once before "
                             "the windows, like the reference's untimed module init"},
-            "gpu_launches": eng.launches - launches0,
+            "gpu_launches": launches1 - launches0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_run_par (persistent, one launch per window)", "algorithmic_bytes_per_launch": alg_bytes / args.steps}}
     if not args.no_cpu_baseline and world == 1:
