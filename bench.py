@@ -45,32 +45,66 @@ def workload(args, rank):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region.  The windows are tens of milliseconds, so
+    the sampler polls NVML in-process every few ms (nvidia-smi takes longer to start than a window);
+    nvidia-smi is the fallback."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
 
-    def run(self):
+    def _nvml_sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _smi_sample(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        if len(r) >= 6:
+            self.sm.append(float(r[0]))
+            self.mx.append(float(r[1]))
+            for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if r[2 + i].lower() == "active":
+                    self.reasons.add(name)
+
+    def sample(self):
+        try:
+            if self.nv is not None:
+                self._nvml_sample()
+            else:
+                self._smi_sample()
+        except Exception:
+            pass
+
+    def run(self):
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.02)
+            self.sample()
+            time.sleep(0.005 if self.nv is not None else 0.05)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower() == "active"})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def run_reference(args, sc_bytes, steps, warmup, events_per_step):
@@ -217,6 +251,7 @@ def main():
     t_region = time.perf_counter()
     for i in range(args.warmup, total_steps):
         dm, w, got = step(i)
+        sampler.sample()                 # at least one reading per window, taken right after its kernel
         dev_ms_sum += dm
         wall_sum += w
         d2h += got
