@@ -88,6 +88,24 @@ if __name__ == "__main__":
                 c = e.counters()
                 print(f"{mname}: status {st} device {e.device_ms:.1f} ms -> {c['events']/(e.device_ms/1e3):.0f} ev/s; batches {c['batches']} par {c['par_events']} ok {e.records() == o.records()}", flush=True)
                 e.close()
+    elif which == "soak":
+        # everything at once, to completion: arrivals (USER) on the speed-change lattice, full downloads
+        # (FLOW_DONE, merges, closes), a record buffer that must be drained many times
+        sc = S.swarm(4000, 8, n_catalogue=8, seeds_per_peer=3, mean_strips=5.0, res_len=60000, arrival_window=10.0, arrival_quantum=0.02)
+        b = sc.to_bytes()
+        o = pyoracle.Oracle(b, trace=False)
+        o.run(0)
+        co = o.counters()
+        for mname, mode in both:
+            e = E.Engine(b, mode=mode, records=True, record_cap=6 << 20)
+            t0 = time.time()
+            stream = e.run_draining(0)
+            t1 = time.time()
+            c = e.counters()
+            bad = [k for k in ("events", "solves", "full_spreads", "flow_visits", "seq", "draws", "flow_done", "user", "closes") if c[k] != co[k]]
+            print(f"soak {mname}: wall {t1-t0:.2f}s events {c['events']} done {c['flow_done']} user {c['user']} par {c['par_events']} launches {e.launches} "
+                  f"records {len(stream)>>20} MB identical {stream == o.records()} counter mismatches {bad}", flush=True)
+            e.close()
     elif which == "windows":
         sc = S.swarm_fast(100032, 320, n_catalogue=64, seeds_per_peer=8, hub_frac=0.02)
         e = E.Engine(sc.to_bytes(), mode=E.MODE_AUTO, records=True, record_cap=4 << 30)
