@@ -682,7 +682,8 @@ extern "C" int ns_ens_digests(ns_ens *e, ns_digest *out, int n){
 		SimState st;
 		CK(cudaMemcpy(&st, e->sims[i].S.st, sizeof st, cudaMemcpyDeviceToHost));
 		out[i].seed = st.seed; out[i].events = st.cnt[NS_CNT_EVENTS]; out[i].solves = st.cnt[NS_CNT_SOLVES];
-		out[i].record_bytes = st.rec_len; out[i].t_end = st.now; out[i].status = st.status;
+		out[i].record_bytes = st.rec_base+st.rec_len; out[i].t_end = st.now;
+		out[i].status = st.status ? st.status : (st.host_stop == 2 ? NS_E_RECORDS_FULL : 0);   // a replica that ran out of record room did not finish
 		u64 hsum = 0;
 		CK(cudaMemsetAsync(e->d_hash, 0, 8, e->stream));
 		if (st.rec_len) { k_stream_hash<<<64, 256, 0, e->stream>>>(e->sims[i].S.rec, st.rec_len, e->d_hash); e->launches++; }
