@@ -427,3 +427,28 @@ def churn(n_users: int = 5000, n_servers: int = 16, rate: float = 1000.0, mean_s
         groups.append([end()])
         groups[0].append(sched(len(groups) - 1, sim_end))
     return Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, groups, {}, seed=1)
+
+
+def edge_cases() -> Dict[str, Scenario]:
+    """Hand-written corner cases of the module API (sim.c:42-67 error returns, main.c:50-52 exits)."""
+    L = 100000
+    t = {}
+    # nothing to do: no flows, no events (main.c:50 loop never runs)
+    t["empty"] = _mk([(1000, 1000), (1000, 1000)], [(0, L)], groups=[[]])
+    # the source does not hold the resource: sim_establish_flow returns NULL (sim.c:49-53), no draw burned;
+    # the second create (valid) must get the ids the reference gives it
+    t["missing_resource"] = _mk([(1000, 1000), (1000, 1000), (1000, 1000)], [(0, L)],
+                                groups=[[create(1, 2, 0, 0, 500, 0.1), create(0, 2, 0, 0, 500, 0.1)]])
+    # a second flow into a range that already exists (sim.c:62-67) is refused
+    t["existing_range"] = _mk([(4000, 4000), (4000, 4000), (1000, 1000)], [(0, L)], copies=[(1, 0)],
+                              groups=[[create(0, 2, 0, 0, 500, 0.1), create(1, 2, 0, 0, 700, 0.2)]])
+    # sim_end from a USER event while flows are still running; a relative USER event; closes of dead and
+    # never-created flows are no-ops
+    t["end_and_closes"] = _mk([(4000, 4000), (1000, 1000), (1000, 1000)], [(0, L)],
+                              groups=[[create(0, 1, 0, 0, 500, 0.1), create(0, 2, 0, 0, 300, 0.2), sched(1, 5.0), sched(3, 50.0)],
+                                      [close(0), close(0), close(7), sched(2, 2.5, relative=True)],
+                                      [create(0, 1, 0, 50000, 800, 0.1)],
+                                      [end()]])
+    # zero-capacity receiver: the flow never gets a speed, no completion is ever scheduled
+    t["zero_capacity"] = _mk([(1000, 1000), (0, 0)], [(0, L)], groups=[[create(0, 1, 0, 0, 500, 0.1)]])
+    return t

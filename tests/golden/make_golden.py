@@ -25,6 +25,8 @@ def cases():
         yield f"relay{seed}", S.random_small(seed, n_nodes=6 + seed % 7, n_flows=8 + seed % 17, relay=True), 0
     yield "swarm200", S.swarm(200, 3, n_catalogue=6, seeds_per_peer=3, mean_strips=3.0), 20000
     yield "churn150", S.churn(150, 4, rate=100.0, mean_session=1.5, sim_end=4.0), 0
+    for name, sc in S.edge_cases().items():
+        yield "edge_" + name, sc, 0
 
 
 def main():

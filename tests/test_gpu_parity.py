@@ -231,3 +231,20 @@ def test_bounded_record_buffer_drains_without_loss(mname, mode, built):
     assert stream == o.records()
     assert e.counters()["events"] == 200000
     e.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+@pytest.mark.parametrize("name", sorted(S.edge_cases()))
+def test_engine_edge_cases(name, mname, mode, built):
+    """Corner cases of the module API: refused flows (missing resource, existing range), an empty
+    script, sim_end with flows in flight, closes of dead flows, a receiver without capacity."""
+    b = S.edge_cases()[name].to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(0) == 0
+    e, st = run_engine(b, mode)
+    assert st == 0
+    assert e.records() == o.records()
+    assert e.trace().tobytes() == o.trace().tobytes()
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    e.close()
