@@ -206,11 +206,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc = workload(args, rank)
     sc_bytes = sc.to_bytes()
-    eps = args.events_per_step
     total_steps = args.steps + args.warmup
+    # the swarm's pending-event population grows by ~1.4 events per handled event in this phase of the
+    # simulation: keep the whole run inside the event ring (2^28 entries) whatever K and W are
+    eps = min(args.events_per_step, max(10000, 100_000_000 // max(1, total_steps)))
     t0 = time.time()
     rec_cap = int((total_steps * eps + 4 * sc.n_creates()) * 48 + (64 << 20))
-    eng = E.Engine(sc_bytes, device=local_rank, mode=E.MODE_AUTO, records=True, record_cap=rec_cap)
+    eng = E.Engine(sc_bytes, device=local_rank, mode=E.MODE_AUTO, records=True, record_cap=rec_cap, ring_cap=1 << 28)
     create_s = time.time() - t0
     c_init = eng.counters()
     import ctypes as C
