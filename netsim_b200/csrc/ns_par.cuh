@@ -3,13 +3,19 @@
 //
 //   A  argmin            min over the per-tile minima of both event stores        (event_pop, event.h:20-25)
 //   B  ordered extract   count / scan / write of the ring entries with time == t  (FIFO ties, event.h:27-31)
-//   C  legality          a batch segment made only of SPEED_CHANGE events in a relay-free simulation is
-//                        handled in parallel; anything else by one warp in sequence order (ns_seq.cuh)
+//   C  pieces            the batch is cut, in sequence-number order, into pieces (par_plan_piece): long
+//                        runs of SPEED_CHANGE events of a relay-free simulation go through D-F, everything
+//                        else (FLOW_DONE / USER / THROTTLE events, short runs, relay topologies, the last
+//                        events before a max_events bound) through the single-warp code of ns_seq.cuh
 //   D  grouping          events are bucketed by the (node, direction) whose rates they rewrite
 //                        (bwspread, flow.c:56-60): that is the unit of mutual exclusion;
 //                        different groups touch disjoint mutable state, same-group events keep FIFO order
-//   E  solve             one warp per group walks its events in order: handle_speed_change + bwspread +
-//                        byte progress + completion re-time, emissions staged under local indices
+//   E1 solve, threads    one THREAD per group for the events whose bwspread takes an O(1) exit
+//                        (sc_needs_full_spread decides before anything is touched); a group that meets a
+//                        full spread is handed over at that position
+//   E2 solve, warps      one WARP per handed-over group: full-spread loops over the lanes, the reference's
+//                        in-order fp64 sums reproduced from shuffled terms; nodes with <= 32 flows run their
+//                        whole event chain register-resident (ge_chain); emissions staged under local indices
 //   F  commit            prefix scan over the batch order of {event_adds, record bytes, trace rows}; staged
 //                        speed events are copied into the ring at their final sequence numbers, records
 //                        into the record stream — byte-identical to the sequential order
@@ -17,6 +23,9 @@
 // Reads of state owned by another group (get_share(nf,!dir), flow.c:140,165: the remote node's
 // total_bwupbound / maximum_bandwidth) are stable inside such a segment because only flow
 // create/close write them (flow.c:246-247,314-315), and those are never part of it.
+//
+// Around it: k_init_par runs a module init made of flow creations in conflict-free waves; par_run (host)
+// alternates this kernel with the single-warp k_run_seq when the simulation enters a sparse phase.
 #pragma once
 #include <cooperative_groups.h>
 #include "ns_seq.cuh"
