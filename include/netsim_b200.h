@@ -156,6 +156,15 @@ int  ns_dev_pick_batch(int device, int mode, int n_req, const int32_t *off, cons
 		       const int32_t *node, const int32_t *k, int32_t *out_val, int32_t *out_node,
 		       int32_t *out_cnt, float *device_ms);
 
+/* the same selection with the score map on the device too, against the LIVE node table of a simulation:
+ * metric 0 = distance_metric (modules/p2p_common.h:171-179), 1 = share_metric (:190-198: what the candidate's
+ * upload share would be with one more flow, from its current total_bwupbound[0] / maximum_bandwidth[0]).
+ * cand_node = device node index, cand_tz / client_tz = time zones (def_user.time_zone), usable (may be NULL)
+ * = server_picker_opt2's filters (is_resource_usable / is_connected, client_behaviour.h:98-105) per candidate. */
+int  ns_dev_pick_live(ns_dev *d, int mode, int metric, int n_req, const int32_t *off, const int32_t *cand_node,
+		      const int32_t *cand_tz, const int32_t *client_tz, const uint8_t *usable, const int32_t *k,
+		      int32_t *out_val, int32_t *out_node, int32_t *out_cnt, float *device_ms);
+
 /* glibc TYPE_3 random(): state is 31 words + two indices */
 struct ns_rand_state { int32_t st[31]; int32_t f, r; };
 void ns_rand_seed_host(struct ns_rand_state *g, uint32_t seed);

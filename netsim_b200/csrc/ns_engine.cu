@@ -119,6 +119,33 @@ __global__ void k_node_state(const Sim *sp, double *out4, int n){
 	}
 }
 
+// fetch metric of every candidate, evaluated against the LIVE node table of the simulation:
+// metric 0 = distance_metric (modules/p2p_common.h:171-179), metric 1 = share_metric (:190-198, with
+// distance_based_bw :181-189); unusable candidates (server_picker_opt2's filters) get INT32_MAX
+__global__ void k_pick_metric(const Sim *sp, int metric, int n_req, const int32_t *off, const int32_t *cand_node, const int32_t *cand_tz,
+			      const int32_t *client_tz, const uint8_t *usable, int32_t *val){
+	const Sim &S = *sp;
+	for (int q = blockIdx.x; q < n_req; q += gridDim.x) {
+		const int ctz = client_tz[q];
+		for (int i = off[q]+threadIdx.x; i < off[q+1]; i += blockDim.x) {
+			int d = cand_tz[i]-ctz;
+			if (d < 0) d = -d;
+			int v = d;
+			if (metric == 1) {
+				const int n = cand_node[i];
+				double bw = 4000-100*d;
+				double total = S.n_total[0][n]+bw;
+				double mx = S.n_max[0][n];
+				v = total > mx ? (int)(-bw*mx/total) : (int)(-bw);
+			}
+			if (usable && !usable[i]) v = INT32_MAX;
+			val[i] = v;
+		}
+	}
+}
+int ns_pick_launch(int mode, int n_req, const int32_t *d_off, const int32_t *d_val, const int32_t *d_node, const int32_t *d_k,
+		   int32_t *d_ov, int32_t *d_on, int32_t *d_oc, cudaStream_t stream);
+
 // ---------------------------------------------------------------- host-side simulation object
 struct HostSim {
 	Sim S;                         // device pointers
@@ -530,6 +557,43 @@ extern "C" int ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size
 	if (n) *n = k;
 	return 0;
 }
+// batched source selection against the live simulation state (the score map + the selection, on the device)
+extern "C" int ns_dev_pick_live(ns_dev *d, int mode, int metric, int n_req, const int32_t *off, const int32_t *cand_node,
+		const int32_t *cand_tz, const int32_t *client_tz, const uint8_t *usable, const int32_t *k,
+		int32_t *out_val, int32_t *out_node, int32_t *out_cnt, float *device_ms){
+	if (!d || n_req < 0 || !off || (mode != 1 && mode != 2) || (metric != 0 && metric != 1)) return NS_E_ARG;
+	if (n_req == 0) return 0;
+	CK(cudaSetDevice(d->device));
+	const int total = off[n_req];
+	for (int i = 0; i < total; i++) if (cand_node[i] < 0 || cand_node[i] >= d->h.S.n_nodes) return NS_E_ARG;
+	const size_t tb = (size_t)std::max(total, 1)*4;
+	int32_t *d_off, *d_node, *d_tz, *d_ctz, *d_val, *d_k, *d_ov, *d_on, *d_oc; uint8_t *d_us = nullptr;
+	CK(cudaMalloc(&d_off, (size_t)(n_req+1)*4)); CK(cudaMalloc(&d_node, tb)); CK(cudaMalloc(&d_tz, tb)); CK(cudaMalloc(&d_ctz, (size_t)n_req*4));
+	CK(cudaMalloc(&d_val, tb)); CK(cudaMalloc(&d_k, (size_t)n_req*4)); CK(cudaMalloc(&d_ov, tb)); CK(cudaMalloc(&d_on, tb)); CK(cudaMalloc(&d_oc, (size_t)n_req*4));
+	CK(cudaMemcpyAsync(d_off, off, (size_t)(n_req+1)*4, cudaMemcpyHostToDevice, d->stream));
+	CK(cudaMemcpyAsync(d_ctz, client_tz, (size_t)n_req*4, cudaMemcpyHostToDevice, d->stream));
+	if (total > 0) {
+		CK(cudaMemcpyAsync(d_node, cand_node, tb, cudaMemcpyHostToDevice, d->stream));
+		CK(cudaMemcpyAsync(d_tz, cand_tz, tb, cudaMemcpyHostToDevice, d->stream));
+		if (usable) { CK(cudaMalloc(&d_us, (size_t)total)); CK(cudaMemcpyAsync(d_us, usable, (size_t)total, cudaMemcpyHostToDevice, d->stream)); }
+	}
+	if (k) CK(cudaMemcpyAsync(d_k, k, (size_t)n_req*4, cudaMemcpyHostToDevice, d->stream)); else CK(cudaMemsetAsync(d_k, 0, (size_t)n_req*4, d->stream));
+	CK(cudaEventRecord(d->e0, d->stream));
+	k_pick_metric<<<std::min(n_req, 1184), 128, 0, d->stream>>>(d->d_sim, metric, n_req, d_off, d_node, d_tz, d_ctz, d_us, d_val);
+	CK(cudaGetLastError());
+	int rc = ns_pick_launch(mode, n_req, d_off, d_val, d_node, d_k, d_ov, d_on, d_oc, d->stream);
+	d->launches += 2;
+	CK(cudaEventRecord(d->e1, d->stream));
+	if (rc) return rc;
+	if (total > 0) { CK(cudaMemcpyAsync(out_val, d_ov, tb, cudaMemcpyDeviceToHost, d->stream)); CK(cudaMemcpyAsync(out_node, d_on, tb, cudaMemcpyDeviceToHost, d->stream)); }
+	CK(cudaMemcpyAsync(out_cnt, d_oc, (size_t)n_req*4, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	if (device_ms) CK(cudaEventElapsedTime(device_ms, d->e0, d->e1));
+	cudaFree(d_off); cudaFree(d_node); cudaFree(d_tz); cudaFree(d_ctz); cudaFree(d_val); cudaFree(d_k); cudaFree(d_ov); cudaFree(d_on); cudaFree(d_oc);
+	if (d_us) cudaFree(d_us);
+	return 0;
+}
+
 // ---- host-callback mode (modules whose own handlers must run on the host) ----
 extern "C" int ns_dev_set_host_mask(ns_dev *d, uint32_t mask){
 	if (!d) return NS_E_ARG;

@@ -75,6 +75,15 @@ __global__ void __launch_bounds__(128) k_pick(int mode, int n_req, const int32_t
 	if (in_smem) for (int i = lane; i < c; i += 32) { out_val[lo+i] = v[i]; out_node[lo+i] = nd[i]; }
 }
 
+// launch on device pointers (used by ns_dev_pick_live, which evaluates the metric on the device first)
+int ns_pick_launch(int mode, int n_req, const int32_t *d_off, const int32_t *d_val, const int32_t *d_node, const int32_t *d_k,
+		   int32_t *d_ov, int32_t *d_on, int32_t *d_oc, cudaStream_t stream){
+	if (n_req <= 0) return 0;
+	k_pick<<<(n_req+3)/4, 128, 0, stream>>>(mode, n_req, d_off, d_val, d_node, d_k, d_ov, d_on, d_oc);
+	cudaError_t e = cudaGetLastError();
+	return e == cudaSuccess ? 0 : (int)e;
+}
+
 #define CKP(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "netsim_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return (int)e_; } } while (0)
 
 extern "C" int ns_dev_pick_batch(int device, int mode, int n_req, const int32_t *off, const int32_t *val,

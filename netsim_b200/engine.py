@@ -81,6 +81,7 @@ def lib():
         L.ns_ens_launches.argtypes = [C.c_void_p]
         L.ns_ens_destroy.argtypes = [C.c_void_p]
         L.ns_dev_pick_batch.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_float)]
+        L.ns_dev_pick_live.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.POINTER(C.c_float)]
         L.ns_rand_seed_host.argtypes = [C.POINTER(RandState), C.c_uint32]
         L.ns_rand_next_host.restype = C.c_uint32
         L.ns_rand_next_host.argtypes = [C.POINTER(RandState)]
@@ -209,6 +210,26 @@ class Engine:
         out.update({"slowest_group_ms": a[10] / 1e6, "slowest_group_degree": int(a[11]), "slowest_group_events": int(a[12]),
                     "sum_slowest_ms": a[13] / 1e6, "deferred_groups": int(a[14])})
         return out
+
+    def pick_live(self, mode: int, metric: int, off, cand_node, cand_tz, client_tz, k=None, usable=None):
+        """ns_dev_pick_live: score map + selection on the device against this simulation's node table"""
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        cn = np.ascontiguousarray(cand_node, dtype=np.int32)
+        ct = np.ascontiguousarray(cand_tz, dtype=np.int32)
+        cl = np.ascontiguousarray(client_tz, dtype=np.int32)
+        n_req = len(off) - 1
+        kk = np.ascontiguousarray(k if k is not None else np.zeros(n_req), dtype=np.int32)
+        us = np.ascontiguousarray(usable, dtype=np.uint8) if usable is not None else None
+        ov = np.zeros(max(1, len(cn)), dtype=np.int32)
+        on = np.zeros(max(1, len(cn)), dtype=np.int32)
+        oc = np.zeros(max(1, n_req), dtype=np.int32)
+        ms = C.c_float()
+        rc = self.L.ns_dev_pick_live(self.h, mode, metric, n_req, off.ctypes.data, cn.ctypes.data, ct.ctypes.data, cl.ctypes.data,
+                                     us.ctypes.data if us is not None else None, kk.ctypes.data, ov.ctypes.data, on.ctypes.data,
+                                     oc.ctypes.data, C.byref(ms))
+        if rc:
+            raise NsError(rc, "ns_dev_pick_live")
+        return ov[:len(cn)], on[:len(cn)], oc[:n_req], float(ms.value)
 
     @property
     def launches(self) -> int:

@@ -6,7 +6,7 @@
  * (include/ns_scenario.h) exactly as oracle/ref_scenario.c drives the real core, and produces the
  * same record byte stream (record.c:27-117).
  *
- * PARITY PINNED: tests/test_oracle_vs_reference.py runs the compiled reference (oracle/_ref) on the
+ * PARITY PINNED: tests/test_oracle_golden.py runs the compiled reference (oracle/_ref) on the
  * restated test00..test05 modules and on randomized scripts and requires byte-identical record
  * payloads and bit-identical fp64 event traces; tests/golden/ holds the vectors for boxes
  * without /root/reference.
@@ -816,4 +816,15 @@ int ns_oracle_pick_opt2(const int32_t *val, const uint8_t *usable, int c){ /* cl
 		if (val[i] < min) { res = i; min = val[i]; }
 	}
 	return res;
+}
+
+/* distance_metric / share_metric, modules/p2p_common.h:171-198 (distance_based_bw :181-189) */
+int ns_oracle_metric(int metric, int tz_node, int tz_client, double total_up, double max_up){
+	int d = tz_node-tz_client;
+	if (d < 0) d = -d;
+	if (metric == 0) return d;
+	double bw = 4000-100*d;
+	double total = total_up+bw;
+	if (total > max_up) return -bw*max_up/total;
+	return -bw;
 }

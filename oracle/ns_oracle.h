@@ -53,4 +53,7 @@ int ns_oracle_pick_opt1(int32_t *val, int32_t *node, int c, int k);
 /* server_picker_opt2 (client_behaviour.h:90-124): first strict minimum, -1 if none usable */
 int ns_oracle_pick_opt2(const int32_t *val, const uint8_t *usable, int c);
 
+/* distance_metric (metric 0) / share_metric (metric 1), modules/p2p_common.h:171-198 */
+int ns_oracle_metric(int metric, int tz_node, int tz_client, double total_up, double max_up);
+
 #endif

@@ -48,6 +48,7 @@ def lib():
         L.ns_oracle_qselect.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
         L.ns_oracle_pick_opt1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ns_oracle_pick_opt2.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ns_oracle_metric.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         _lib = L
     return _lib
 

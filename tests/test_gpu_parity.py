@@ -248,3 +248,46 @@ def test_engine_edge_cases(name, mname, mode, built):
     ce, co = e.counters(), o.counters()
     assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
     e.close()
+
+
+def test_pick_live_uses_device_node_table(built):
+    """Score map + selection on the device against the running simulation's node table: share_metric
+    (p2p_common.h:190-198) depends on each candidate's CURRENT total_bwupbound[0]."""
+    sc = S.swarm(600, 6, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0)
+    e = E.Engine(sc.to_bytes(), mode=E.MODE_AUTO, records=False)
+    assert e.run(3000) == 0                            # stop while the flows are still up
+    ns = e.node_state(sc.n_nodes)                      # usage0 usage1 total0 total1
+    rng = np.random.default_rng(3)
+    tz_of = rng.integers(0, 24, sc.n_nodes)
+    offs, cn, ks, ctz = [0], [], [], []
+    for _ in range(300):
+        c = int(rng.integers(0, 40))
+        offs.append(offs[-1] + c)
+        cn.extend(rng.permutation(sc.n_nodes)[:c].tolist())
+        ks.append(int(rng.integers(1, 20)))
+        ctz.append(int(rng.integers(0, 24)))
+    off, cn, ks, ctz = (np.array(x, dtype=np.int32) for x in (offs, cn, ks, ctz))
+    ct = tz_of[cn].astype(np.int32)
+    L = pyoracle.lib()
+    for metric in (0, 1):
+        exp_val = np.array([L.ns_oracle_metric(metric, int(ct[i]), int(ctz[q]), float(ns[cn[i], 2]), float(sc.max_up[cn[i]]))
+                            for q in range(len(ks)) for i in range(off[q], off[q + 1])], dtype=np.int32)
+        ov, on, oc, ms = e.pick_live(1, metric, off, cn, ct, ctz, k=ks)
+        for q in range(len(ks)):
+            lo, hi = off[q], off[q + 1]
+            v, nd = exp_val[lo:hi].copy(), cn[lo:hi].copy()
+            cnt = L.ns_oracle_pick_opt1(v.ctypes.data, nd.ctypes.data, hi - lo, int(ks[q]))
+            assert oc[q] == cnt
+            assert (ov[lo:hi] == v).all() and (on[lo:hi] == nd).all()
+        usable = (rng.random(len(cn)) < 0.7).astype(np.uint8)
+        ov, on, oc, ms = e.pick_live(2, metric, off, cn, ct, ctz, usable=usable)
+        for q in range(len(ks)):
+            lo, hi = off[q], off[q + 1]
+            v = np.ascontiguousarray(exp_val[lo:hi])
+            u = np.ascontiguousarray(usable[lo:hi])
+            i = L.ns_oracle_pick_opt2(v.ctypes.data, u.ctypes.data, hi - lo)
+            assert oc[q] == (1 if i >= 0 else 0)
+            if i >= 0:
+                assert on[lo] == cn[lo + i]
+    assert (ns[:, 2] > 0).any()                        # the table really is live (flows add to total_bwupbound)
+    e.close()
