@@ -291,3 +291,24 @@ def test_pick_live_uses_device_node_table(built):
                 assert on[lo] == cn[lo + i]
     assert (ns[:, 2] > 0).any()                        # the table really is live (flows add to total_bwupbound)
     e.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+def test_engine_config1_shape_1k_clients_one_seeder(mname, mode, built):
+    """BASELINE.json configs[1] in script form: 1 000 clients + 1 cloud seeder, arrivals spread over 30 s,
+    every download runs to completion (234 k events, 4 036 flows, the seeder's 1 000-flow full spreads)."""
+    sc = S.swarm(1000, 1, n_catalogue=4, seeds_per_peer=1, mean_strips=3.0, hub_frac=0.3, res_len=30000,
+                 arrival_window=30.0, arrival_quantum=0.1)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b, trace=False)
+    assert o.run(0) == 0
+    e = E.Engine(b, mode=mode, records=True, record_cap=64 << 20)
+    assert e.run(0) == 0
+    assert e.records() == o.records()
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    assert ce["live_flows"] == 0 and ce["flow_done"] == 4036
+    if refrun.available():
+        r = refrun.run_reference(b, trace=False)
+        assert r["returncode"] == 0 and r["records"] == e.records()
+    e.close()
