@@ -247,29 +247,34 @@ struct Retime { double drain_t, done_t; int add_drain, add_done; };
 __device__ __forceinline__ int retime_math(double now, double fbw, bool has_prod, double sgrow, double prod_done_t,
 		double slen, double dlen, long long dstart, long long sstart, int npos, Retime &p, int &dtype){
 	double drng_start = (double)dstart+dlen-(double)sstart;           // :36
-	double drain_time = (slen-drng_start)/(fbw-sgrow);                // :38
 	double drain_active = NS_INF;                                     // time of f->drain if active
-	bool bad = false;
 	if (!has_prod) {                                                  // :40-44
 		double t = now+(slen-drng_start)/fbw;
 		dtype = EV_FLOW_DRAIN;
+		bool bad = false;
 		if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
-		if (isnan(t)) bad = true;
-		if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
-	} else if (!is_later_than(drain_time+now, prod_done_t) && sgrow < fbw) {   // :45-61
-		dtype = EV_FLOW_SPEED_THROTTLE;
-		double d0 = slen-drng_start;
-		if (d0 > -NS_EPS && d0 < NS_EPS) {
-			double d1 = sgrow-fbw;
-			if (!(d1 > -NS_EPS && d1 < NS_EPS)) { p.add_drain = 1; p.drain_t = now; drain_active = now; }
-		} else {
-			double t = now+drain_time;
-			if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
-			if (isnan(t)) bad = true;
-			if (!bad) { p.add_drain = 1; p.drain_t = t; drain_active = t; }
+		if (isnan(t)) return NS_E_NAN_TIME;
+		if (bad) return NS_E_BACK_IN_TIME;
+		p.add_drain = 1; p.drain_t = t; drain_active = t;
+	} else {
+		double drain_time = (slen-drng_start)/(fbw-sgrow);            // :38 (only read on this branch)
+		if (!is_later_than(drain_time+now, prod_done_t) && sgrow < fbw) {   // :45-61
+			dtype = EV_FLOW_SPEED_THROTTLE;
+			double d0 = slen-drng_start;
+			if (d0 > -NS_EPS && d0 < NS_EPS) {
+				double d1 = sgrow-fbw;
+				if (!(d1 > -NS_EPS && d1 < NS_EPS)) { p.add_drain = 1; p.drain_t = now; drain_active = now; }
+			} else {
+				double t = now+drain_time;
+				bool bad = false;
+				if (t < now) { if (t < now-NS_EPS) bad = true; t = now; }
+				if (isnan(t)) return NS_E_NAN_TIME;
+				if (bad) return NS_E_BACK_IN_TIME;
+				p.add_drain = 1; p.drain_t = t; drain_active = t;
+			}
 		}
 	}
-	if (bad) return isnan(drain_time) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME;
+	bool bad = false;
 	double done_time = ((double)(u64)((u64)(long long)npos-(u64)dstart)-dlen)/fbw;  // :70
 	if (!is_later_than(now+done_time, drain_active)) {                // :73-78
 		double t = now+done_time;
