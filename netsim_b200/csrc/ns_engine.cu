@@ -164,6 +164,16 @@ static int dev_alloc(HostSim &h, void **p, size_t bytes){
 	h.bytes += bytes;
 	return 0;
 }
+// short-lived device buffers of one call
+struct DevTmp {
+	std::vector<void *> p;
+	template <typename T> cudaError_t get(T **out, size_t bytes){
+		cudaError_t e = cudaMalloc((void **)out, bytes ? bytes : 8);
+		if (e == cudaSuccess) p.push_back(*out);
+		return e;
+	}
+	~DevTmp(){ for (void *q : p) cudaFree(q); }
+};
 template <typename T> static int dalloc(HostSim &h, T **p, size_t n){ return dev_alloc(h, (void **)p, n*sizeof(T)); }
 static int fill_f64(double *p, u64 n, double v){ if (!n) return 0; k_fill_f64<<<(unsigned)std::min<u64>((n+255)/256, 4096), 256>>>(p, n, v); CK(cudaGetLastError()); return 0; }
 static int fill_i32(int *p, u64 n, int v){ if (!n) return 0; k_fill_i32<<<(unsigned)std::min<u64>((n+255)/256, 4096), 256>>>(p, n, v); CK(cudaGetLastError()); return 0; }
@@ -390,6 +400,8 @@ static int read_state(ns_dev *d, SimState *st){
 	return 0;
 }
 
+static int dev_init(ns_dev *d, const void *scenario, size_t len, const ns_dev_opts &o);
+extern "C" void ns_dev_destroy(ns_dev *d);
 extern "C" int ns_dev_create(ns_dev **out, const void *scenario, size_t len, const ns_dev_opts *opts){
 	if (!out || !scenario) return NS_E_ARG;
 	*out = nullptr;
@@ -400,11 +412,17 @@ extern "C" int ns_dev_create(ns_dev **out, const void *scenario, size_t len, con
 	CK(cudaSetDevice(o.device));
 	ns_dev *d = new ns_dev();
 	d->device = o.device; d->mode = o.mode;
+	int rc = dev_init(d, scenario, len, o);
+	if (rc) { ns_dev_destroy(d); return rc; }          // releases whatever dev_init had built
+	*out = d;
+	return 0;
+}
+static int dev_init(ns_dev *d, const void *scenario, size_t len, const ns_dev_opts &o){
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, o.device));
 	d->sm_count = prop.multiProcessorCount;
 	int rc = build_sim(d->h, scenario, len, o, o.mode != NS_MODE_SEQ);
-	if (rc) { free_sim(d->h); delete d; return rc; }
+	if (rc) return rc;
 	CK(cudaStreamCreate(&d->stream)); CK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&d->e0)); CK(cudaEventCreate(&d->e1)); CK(cudaEventCreateWithFlags(&d->e_run, cudaEventDisableTiming));
 	CK(cudaMalloc(&d->d_sim, sizeof(Sim))); CK(cudaMalloc(&d->d_scr, sizeof(SeqScratch))); CK(cudaMalloc(&d->d_hash, 8));
@@ -418,11 +436,10 @@ extern "C" int ns_dev_create(ns_dev **out, const void *scenario, size_t len, con
 		d->launches++;
 	} else {
 		rc = par_init_group0(d->h.S, d->d_sim, d->h.par, d->sm_count, d->stream, &d->launches);
-		if (rc) { ns_dev_destroy(d); return rc; }
+		if (rc) return rc;
 	}
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(d->stream));
-	*out = d;
 	return 0;
 }
 
@@ -535,11 +552,10 @@ extern "C" int ns_dev_flow_state(ns_dev *d, double *out4, size_t max_flows, size
 	SimState st; int rc = read_state(d, &st); if (rc) return rc;
 	size_t k = std::min<size_t>(max_flows, (size_t)st.n_ord);
 	if (k) {
-		double *tmp; CK(cudaMalloc(&tmp, k*32));
+		double *tmp; DevTmp bufs; CK(bufs.get(&tmp, k*32));
 		k_flow_state<<<(unsigned)((k+255)/256), 256, 0, d->stream>>>(d->d_sim, tmp, (int)k); d->launches++;
 		CK(cudaMemcpyAsync(out4, tmp, k*32, cudaMemcpyDeviceToHost, d->stream));
 		CK(cudaStreamSynchronize(d->stream));
-		cudaFree(tmp);
 	}
 	if (n) *n = k;
 	return 0;
@@ -548,11 +564,10 @@ extern "C" int ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size
 	if (!d || !out4) return NS_E_ARG;
 	size_t k = std::min<size_t>(max_nodes, (size_t)d->h.S.n_nodes);
 	if (k) {
-		double *tmp; CK(cudaMalloc(&tmp, k*32));
+		double *tmp; DevTmp bufs; CK(bufs.get(&tmp, k*32));
 		k_node_state<<<(unsigned)((k+255)/256), 256, 0, d->stream>>>(d->d_sim, tmp, (int)k); d->launches++;
 		CK(cudaMemcpyAsync(out4, tmp, k*32, cudaMemcpyDeviceToHost, d->stream));
 		CK(cudaStreamSynchronize(d->stream));
-		cudaFree(tmp);
 	}
 	if (n) *n = k;
 	return 0;
@@ -568,14 +583,15 @@ extern "C" int ns_dev_pick_live(ns_dev *d, int mode, int metric, int n_req, cons
 	for (int i = 0; i < total; i++) if (cand_node[i] < 0 || cand_node[i] >= d->h.S.n_nodes) return NS_E_ARG;
 	const size_t tb = (size_t)std::max(total, 1)*4;
 	int32_t *d_off, *d_node, *d_tz, *d_ctz, *d_val, *d_k, *d_ov, *d_on, *d_oc; uint8_t *d_us = nullptr;
-	CK(cudaMalloc(&d_off, (size_t)(n_req+1)*4)); CK(cudaMalloc(&d_node, tb)); CK(cudaMalloc(&d_tz, tb)); CK(cudaMalloc(&d_ctz, (size_t)n_req*4));
-	CK(cudaMalloc(&d_val, tb)); CK(cudaMalloc(&d_k, (size_t)n_req*4)); CK(cudaMalloc(&d_ov, tb)); CK(cudaMalloc(&d_on, tb)); CK(cudaMalloc(&d_oc, (size_t)n_req*4));
+	DevTmp tmp;                                                          // freed on every way out
+	CK(tmp.get(&d_off, (size_t)(n_req+1)*4)); CK(tmp.get(&d_node, tb)); CK(tmp.get(&d_tz, tb)); CK(tmp.get(&d_ctz, (size_t)n_req*4));
+	CK(tmp.get(&d_val, tb)); CK(tmp.get(&d_k, (size_t)n_req*4)); CK(tmp.get(&d_ov, tb)); CK(tmp.get(&d_on, tb)); CK(tmp.get(&d_oc, (size_t)n_req*4));
 	CK(cudaMemcpyAsync(d_off, off, (size_t)(n_req+1)*4, cudaMemcpyHostToDevice, d->stream));
 	CK(cudaMemcpyAsync(d_ctz, client_tz, (size_t)n_req*4, cudaMemcpyHostToDevice, d->stream));
 	if (total > 0) {
 		CK(cudaMemcpyAsync(d_node, cand_node, tb, cudaMemcpyHostToDevice, d->stream));
 		CK(cudaMemcpyAsync(d_tz, cand_tz, tb, cudaMemcpyHostToDevice, d->stream));
-		if (usable) { CK(cudaMalloc(&d_us, (size_t)total)); CK(cudaMemcpyAsync(d_us, usable, (size_t)total, cudaMemcpyHostToDevice, d->stream)); }
+		if (usable) { CK(tmp.get(&d_us, (size_t)total)); CK(cudaMemcpyAsync(d_us, usable, (size_t)total, cudaMemcpyHostToDevice, d->stream)); }
 	}
 	if (k) CK(cudaMemcpyAsync(d_k, k, (size_t)n_req*4, cudaMemcpyHostToDevice, d->stream)); else CK(cudaMemsetAsync(d_k, 0, (size_t)n_req*4, d->stream));
 	CK(cudaEventRecord(d->e0, d->stream));
@@ -589,8 +605,6 @@ extern "C" int ns_dev_pick_live(ns_dev *d, int mode, int metric, int n_req, cons
 	CK(cudaMemcpyAsync(out_cnt, d_oc, (size_t)n_req*4, cudaMemcpyDeviceToHost, d->stream));
 	CK(cudaStreamSynchronize(d->stream));
 	if (device_ms) CK(cudaEventElapsedTime(device_ms, d->e0, d->e1));
-	cudaFree(d_off); cudaFree(d_node); cudaFree(d_tz); cudaFree(d_ctz); cudaFree(d_val); cudaFree(d_k); cudaFree(d_ov); cudaFree(d_on); cudaFree(d_oc);
-	if (d_us) cudaFree(d_us);
 	return 0;
 }
 
@@ -630,11 +644,11 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 extern "C" int ns_dev_flow_info(ns_dev *d, int ord, ns_flow_info *out){
 	if (!d || !out) return NS_E_ARG;
 	FlowInfoDev *tmp, h;
-	CK(cudaMalloc(&tmp, sizeof *tmp));
+	DevTmp bufs;
+	CK(bufs.get(&tmp, sizeof *tmp));
 	k_flow_info<<<1, 1, 0, d->stream>>>(d->d_sim, ord, tmp); d->launches++;
 	CK(cudaMemcpyAsync(&h, tmp, sizeof h, cudaMemcpyDeviceToHost, d->stream));
 	CK(cudaStreamSynchronize(d->stream));
-	cudaFree(tmp);
 	out->alive = h.alive; out->src = h.src; out->dst = h.dst; out->flow_id = h.flow_id; out->resource_id = h.resource_id;
 	out->ub = h.ub; out->delay = h.delay; out->speed[0] = h.speed0; out->speed[1] = h.speed1;
 	out->drng_start = h.drng_start; out->drng_len = h.drng_len;
@@ -643,13 +657,13 @@ extern "C" int ns_dev_flow_info(ns_dev *d, int ord, ns_flow_info *out){
 extern "C" int ns_dev_node_ranges(ns_dev *d, int node, uint32_t rid, ns_range_info *out, int max, int *n){
 	if (!d || !out || !n || node < 0 || node >= d->h.S.n_nodes || max <= 0) return NS_E_ARG;
 	RangeInfoDev *tmp; int *dn;
-	CK(cudaMalloc(&tmp, sizeof(RangeInfoDev)*max)); CK(cudaMalloc(&dn, 4));
+	DevTmp bufs;
+	CK(bufs.get(&tmp, sizeof(RangeInfoDev)*max)); CK(bufs.get(&dn, 4));
 	k_node_ranges<<<1, 1, 0, d->stream>>>(d->d_sim, node, rid, tmp, max, dn); d->launches++;
 	std::vector<RangeInfoDev> h(max);
 	CK(cudaMemcpyAsync(h.data(), tmp, sizeof(RangeInfoDev)*max, cudaMemcpyDeviceToHost, d->stream));
 	CK(cudaMemcpyAsync(n, dn, 4, cudaMemcpyDeviceToHost, d->stream));
 	CK(cudaStreamSynchronize(d->stream));
-	cudaFree(tmp); cudaFree(dn);
 	for (int i = 0; i < *n; i++) { out[i].start = h[i].start; out[i].total_len = h[i].total_len; out[i].len = h[i].len; out[i].producer_ord = h[i].producer_ord; out[i].pad = 0; }
 	return 0;
 }
@@ -696,6 +710,8 @@ struct ns_ens {
 	u64 *d_hash = nullptr;
 };
 
+static int ens_init(ns_ens *e, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts &o);
+extern "C" void ns_ens_destroy(ns_ens *e);
 extern "C" int ns_ens_create(ns_ens **out, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts *opts){
 	if (!out || !scenarios || !lens || n <= 0) return NS_E_ARG;
 	*out = nullptr;
@@ -706,11 +722,17 @@ extern "C" int ns_ens_create(ns_ens **out, const void *const *scenarios, const s
 	CK(cudaSetDevice(o.device));
 	ns_ens *e = new ns_ens();
 	e->device = o.device; e->n = n;
+	int rc = ens_init(e, scenarios, lens, n, o);
+	if (rc) { ns_ens_destroy(e); return rc; }          // releases whatever ens_init had built
+	*out = e;
+	return 0;
+}
+static int ens_init(ns_ens *e, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts &o){
 	e->sims.resize(n);
 	std::vector<Sim> hs(n); std::vector<SeqScratch> hscr(n);
 	for (int i = 0; i < n; i++) {
 		int rc = build_sim(e->sims[i], scenarios[i], lens[i], o, false);
-		if (rc) { for (auto &h : e->sims) free_sim(h); delete e; return rc; }
+		if (rc) return rc;
 		hs[i] = e->sims[i].S; hscr[i] = e->sims[i].scr;
 	}
 	CK(cudaStreamCreate(&e->stream));
@@ -723,7 +745,6 @@ extern "C" int ns_ens_create(ns_ens **out, const void *const *scenarios, const s
 	e->launches++;
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(e->stream));
-	*out = e;
 	return 0;
 }
 extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms){

@@ -97,13 +97,18 @@ extern "C" int ns_dev_pick_batch(int device, int mode, int n_req, const int32_t 
 	const int total = off[n_req];
 	int32_t *d_off, *d_val, *d_node, *d_k = nullptr, *d_ov, *d_on, *d_oc;
 	size_t tb = (size_t)(total > 0 ? total : 1)*4;
-	CKP(cudaMalloc(&d_off, (size_t)(n_req+1)*4)); CKP(cudaMalloc(&d_val, tb)); CKP(cudaMalloc(&d_node, tb));
-	CKP(cudaMalloc(&d_ov, tb)); CKP(cudaMalloc(&d_on, tb)); CKP(cudaMalloc(&d_oc, (size_t)n_req*4));
-	CKP(cudaMalloc(&d_k, (size_t)n_req*4));
+	struct Tmp {                                                         // released on every way out
+		void *p[8]; int n = 0; cudaEvent_t e0 = nullptr, e1 = nullptr;
+		cudaError_t get(int32_t **out, size_t bytes){ cudaError_t e = cudaMalloc((void **)out, bytes); if (e == cudaSuccess) p[n++] = *out; return e; }
+		~Tmp(){ for (int i = 0; i < n; i++) cudaFree(p[i]); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+	} tmp;
+	CKP(tmp.get(&d_off, (size_t)(n_req+1)*4)); CKP(tmp.get(&d_val, tb)); CKP(tmp.get(&d_node, tb));
+	CKP(tmp.get(&d_ov, tb)); CKP(tmp.get(&d_on, tb)); CKP(tmp.get(&d_oc, (size_t)n_req*4));
+	CKP(tmp.get(&d_k, (size_t)n_req*4));
 	CKP(cudaMemcpy(d_off, off, (size_t)(n_req+1)*4, cudaMemcpyHostToDevice));
 	if (total > 0) { CKP(cudaMemcpy(d_val, val, tb, cudaMemcpyHostToDevice)); CKP(cudaMemcpy(d_node, node, tb, cudaMemcpyHostToDevice)); }
 	if (k) CKP(cudaMemcpy(d_k, k, (size_t)n_req*4, cudaMemcpyHostToDevice)); else CKP(cudaMemset(d_k, 0, (size_t)n_req*4));
-	cudaEvent_t e0, e1;
+	cudaEvent_t &e0 = tmp.e0, &e1 = tmp.e1;
 	CKP(cudaEventCreate(&e0)); CKP(cudaEventCreate(&e1));
 	CKP(cudaEventRecord(e0));
 	k_pick<<<(n_req+3)/4, 128>>>(mode, n_req, d_off, d_val, d_node, d_k, d_ov, d_on, d_oc);
@@ -113,7 +118,5 @@ extern "C" int ns_dev_pick_batch(int device, int mode, int n_req, const int32_t 
 	if (device_ms) CKP(cudaEventElapsedTime(device_ms, e0, e1));
 	if (total > 0) { CKP(cudaMemcpy(out_val, d_ov, tb, cudaMemcpyDeviceToHost)); CKP(cudaMemcpy(out_node, d_on, tb, cudaMemcpyDeviceToHost)); }
 	CKP(cudaMemcpy(out_cnt, d_oc, (size_t)n_req*4, cudaMemcpyDeviceToHost));
-	cudaFree(d_off); cudaFree(d_val); cudaFree(d_node); cudaFree(d_k); cudaFree(d_ov); cudaFree(d_on); cudaFree(d_oc);
-	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	return 0;
 }
