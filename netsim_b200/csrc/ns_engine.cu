@@ -6,7 +6,6 @@
 // rate solves, byte progress, completion times, event selection — runs in the kernels.
 // There is no CPU fallback: every entry point fails with NS_E_NO_DEVICE when CUDA is unusable.
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,11 +13,7 @@
 #include <unordered_set>
 
 #include "ns_sim.cuh"
-#include "ns_model.cuh"
-#include "ns_seq.cuh"
-#include "ns_par.cuh"
-
-namespace cg = cooperative_groups;
+#include "ns_par_api.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "netsim_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return (int)e_; } } while (0)
 
@@ -28,26 +23,6 @@ __global__ void k_fill_f64(double *p, u64 n, double v){
 }
 __global__ void k_fill_i32(int *p, u64 n, int v){
 	for (u64 i = blockIdx.x*(u64)blockDim.x+threadIdx.x; i < n; i += (u64)gridDim.x*blockDim.x) p[i] = v;
-}
-
-// run the script's init group (module *_init: first flows and scheduled USER events)
-__global__ void __launch_bounds__(32) k_init_groups(const Sim *sims, int n){
-	int s = blockIdx.x;
-	if (s >= n) return;
-	Ctx c;
-	ctx_load(c, &sims[s], threadIdx.x);
-	run_group(c, 0);
-	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
-	ctx_flush(c);
-}
-
-// operations injected by a host-side module handler, at the current simulation time
-__global__ void __launch_bounds__(32) k_exec_ops(const Sim *sp, int n_ops){
-	Ctx c;
-	ctx_load(c, sp, threadIdx.x);
-	run_host_ops(c, n_ops);
-	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
-	ctx_flush(c);
 }
 
 struct FlowInfoDev { int alive, src, dst, pad; unsigned flow_id, resource_id; double ub, delay, speed0, speed1; long long drng_start; double drng_len; };
@@ -78,13 +53,6 @@ __global__ void k_node_ranges(const Sim *sp, int node, unsigned rid, RangeInfoDe
 		break;
 	}
 	*n_out = n;
-}
-
-// one warp per simulation, strictly sequential event handling
-__global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n){
-	int s = blockIdx.x;
-	if (s >= n) return;
-	seq_run(&sims[s], scr[s], threadIdx.x);
 }
 
 // order-sensitive, parallel digest of a byte stream: sum over little-endian 64-bit words w_j of
@@ -429,10 +397,10 @@ static int dev_init(ns_dev *d, const void *scenario, size_t len, const ns_dev_op
 	CK(cudaMemcpy(d->d_sim, &d->h.S, sizeof(Sim), cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d->d_scr, &d->h.scr, sizeof(SeqScratch), cudaMemcpyHostToDevice));
 	CK(cudaDeviceSynchronize());
-	{ cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_run_par)); CK(cudaFuncGetAttributes(&fa, k_run_seq)); }   // load the kernels now, not inside the first timed run
+	if ((o.mode != NS_MODE_SEQ && (rc = par_preload())) || (rc = seq_preload())) return rc;   // load the kernels now, not inside the first timed run
 	// module init: group 0 of the script (first sim_establish_flow calls, scheduled USER events)
 	if (d->mode == NS_MODE_SEQ) {
-		k_init_groups<<<1, 32, 0, d->stream>>>(d->d_sim, 1);
+		if ((rc = seq_launch_init_groups(d->d_sim, 1, d->stream))) return rc;
 		d->launches++;
 	} else {
 		rc = par_init_group0(d->h.S, d->d_sim, d->h.par, d->sm_count, d->stream, &d->launches);
@@ -450,9 +418,9 @@ extern "C" int ns_dev_run(ns_dev *d, uint64_t max_events, float *device_ms){
 	{ int zero = 0; CK(cudaMemcpyAsync(&d->h.S.st->host_stop, &zero, 4, cudaMemcpyHostToDevice, d->stream)); }
 	CK(cudaEventRecord(d->e0, d->stream));
 	if (d->mode == NS_MODE_SEQ) {
-		k_run_seq<<<1, 32, 0, d->stream>>>(d->d_sim, d->d_scr, 1);
+		int rc = seq_launch_run(d->d_sim, d->d_scr, 1, d->stream);
+		if (rc) return rc;
 		d->launches++;
-		CK(cudaGetLastError());
 	} else {
 		int rc = par_run(d->h.S, d->d_sim, d->d_scr, d->h.par, d->sm_count, d->stream, &d->launches);
 		if (rc) return rc;
@@ -620,10 +588,10 @@ extern "C" int ns_dev_run_host(ns_dev *d, ns_host_event *ev){
 	int zero = 0; uint64_t nomax = 0;
 	CK(cudaMemcpyAsync(&d->h.S.st->host_stop, &zero, 4, cudaMemcpyHostToDevice, d->stream));
 	CK(cudaMemcpyAsync(&d->h.S.st->max_events, &nomax, 8, cudaMemcpyHostToDevice, d->stream));
-	k_run_seq<<<1, 32, 0, d->stream>>>(d->d_sim, d->d_scr, 1);       // callbacks serialise the run anyway
+	int rc = seq_launch_run(d->d_sim, d->d_scr, 1, d->stream);       // callbacks serialise the run anyway
+	if (rc) return rc;
 	d->launches++;
-	CK(cudaGetLastError());
-	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	SimState st; rc = read_state(d, &st); if (rc) return rc;
 	ev->type = st.le_type; ev->flow_ord = st.le_ord; ev->dir = st.le_dir; ev->token = st.le_token;
 	ev->time = st.le_time; ev->speed = st.le_speed; ev->stopped = st.host_stop; ev->status = st.status;
 	ev->now = st.now; ev->exited = st.exit_flag;
@@ -634,9 +602,8 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 	if (n == 0) return 0;
 	CK(cudaSetDevice(d->device));
 	CK(cudaMemcpyAsync(d->h.S.host_ops, ops, (size_t)n*sizeof *ops, cudaMemcpyHostToDevice, d->stream));
-	k_exec_ops<<<1, 32, 0, d->stream>>>(d->d_sim, n);
+	{ int rc = seq_launch_exec_ops(d->d_sim, n, d->stream); if (rc) return rc; }
 	d->launches++;
-	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(ops, d->h.S.host_ops, (size_t)n*sizeof *ops, cudaMemcpyDeviceToHost, d->stream));
 	CK(cudaStreamSynchronize(d->stream));
 	return ns_dev_status(d);
@@ -741,9 +708,8 @@ static int ens_init(ns_ens *e, const void *const *scenarios, const size_t *lens,
 	CK(cudaMemcpy(e->d_sims, hs.data(), sizeof(Sim)*n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(e->d_scr, hscr.data(), sizeof(SeqScratch)*n, cudaMemcpyHostToDevice));
 	CK(cudaDeviceSynchronize());
-	k_init_groups<<<n, 32, 0, e->stream>>>(e->d_sims, n);
+	{ int rc = seq_launch_init_groups(e->d_sims, n, e->stream); if (rc) return rc; }
 	e->launches++;
-	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
 }
@@ -753,9 +719,8 @@ extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms)
 	for (int i = 0; i < e->n; i++)
 		CK(cudaMemcpyAsync(&e->sims[i].S.st->max_events, &max_events_each, 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaEventRecord(e->e0, e->stream));
-	k_run_seq<<<e->n, 32, 0, e->stream>>>(e->d_sims, e->d_scr, e->n);
+	{ int rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc; }
 	e->launches++;
-	CK(cudaGetLastError());
 	CK(cudaEventRecord(e->e1, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	if (device_ms) CK(cudaEventElapsedTime(device_ms, e->e0, e->e1));

@@ -11,21 +11,7 @@
 #pragma once
 #include "ns_sim.cuh"
 
-// Staging area of the grid-parallel path: an event handled out of order cannot know its final
-// sequence numbers / record offset, so its event_adds, records and trace row are parked here under
-// LOCAL indices and committed in batch order by a prefix scan (ns_par.cuh).
-#define NS_STAGE_INLINE 4
-#define NS_STAGE_REC 56
-#define NS_SEQ_PROV (1ull << 63)
-#define NS_HOLE_PURE (-2147483647-1)
-struct ParStage {
-	double *st_time, *st_speed; int *st_fd;     // [NS_STAGE_INLINE*seg_cap] inline, then overflow
-	u64 inline_n, ovf_cap; u64 *ovf_top;
-	uint8_t *st_rec; ns_trace_row32 *st_tr;
-	unsigned *ev_nins; long long *ev_ovf; uint8_t *ev_nrec, *ev_ntr;
-	unsigned *ev_idpos;           // parallel creates: event_adds of the op before its flow-id draw (flow.c:327)
-};
-enum { LC_EVENTS = 0, LC_SPEED_CHANGE, LC_SOLVES, LC_FULL_SPREADS, LC_FLOW_VISITS, LC_RETIMES, LC_N };
+namespace {   // internal linkage: every engine translation unit carries its own copy of the device code
 
 struct Ctx {
 	const Sim *S; SimState *st; int lane;
@@ -1214,3 +1200,5 @@ __device__ void ge_full_event(Ctx &c, const Sim &S, GFlow &g, double &usage, dou
 	write_record(c, R_SPD|dir, oid, -1, 0, speed);
 	trace_row(c, EV_SPEED_CHANGE|(dir << 8), oord, speed, osp);
 }
+
+}   // namespace

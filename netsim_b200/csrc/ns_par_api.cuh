@@ -1,0 +1,91 @@
+// ns_par_api.cuh — what the host layer (ns_engine.cu) sees of the two device engines: the scratch
+// structs it allocates and the launchers.  The kernels live in their own translation units
+// (ns_par.cu: k_run_par; ns_init.cu: k_init_par; ns_seq.cu: k_run_seq, k_init_groups, k_exec_ops) so
+// that they compile in parallel and a change to one engine does not rebuild the others.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+#include <algorithm>
+#include "ns_sim.cuh"
+
+#define PAR_THREADS 256
+#ifndef PAR_MIN_BLOCKS
+#define PAR_MIN_BLOCKS 1       // CTAs per SM the persistent kernel is compiled for (register budget)
+#endif
+#define PAR_WARPS (PAR_THREADS/32)
+#define PAR_MIN_BATCH 48          // smaller batches are cheaper on the single-warp path
+#define SPARSE_STREAK 6            // that many small batches in a row: the grid barriers cost more than the events
+#define SPARSE_MAX_TILES 4096     // ... provided one warp can scan the tile minima of both event stores
+
+struct ParScratch {
+	int enabled;
+	int seg_cap;                  // events per parallel segment
+	ParStage stage;               // staging arrays (device pointers)
+	ParStage *d_stage;
+	// per-timestamp
+	int *tile_cnt, *tile_off;     // per ring-window tile: matches, exclusive offset
+	// grouping
+	int *grp_cnt, *grp_off, *grp_fill, *active, *grp_items, *b_grp;
+	int *deferred, *defer_pos;     // groups handed from the per-thread pass to the per-warp pass
+	// parallel module init: CREATE ops of group 0 scheduled into conflict-free waves (host, par_plan_init)
+	int n_init, n_waves; int *wave_off, *wave_ops; u64 *cta_draws;
+	// scan
+	u64 *cta_ins; unsigned *cta_rec, *cta_tr;
+	// control block (device)
+	struct Ctl {
+		u64 tmin_bits, first_live;
+		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
+		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
+		int small_streak;                          // consecutive small batches (sparse phase detection)
+		u64 dbg_key;
+		u64 tot_ins; unsigned tot_rec, tot_tr;
+		u64 lc[LC_N];
+	} *ctl;
+};
+
+template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool enable, int n_init, A alloc){
+	memset(&p, 0, sizeof p);
+	p.enabled = enable;
+	if (!enable) return 0;
+	int rc;
+	p.n_init = n_init;
+	p.seg_cap = std::max((int)std::min<u64>((u64)S.batch_cap, 1u << 20), n_init);
+	ParStage &st = p.stage;
+	st.inline_n = (u64)NS_STAGE_INLINE*p.seg_cap;
+	st.ovf_cap = std::max<u64>(1u << 22, 64ull*S.cap_flows);
+	u64 n = st.inline_n+st.ovf_cap;
+#define PA(ptr, cnt) if ((rc = alloc((void **)&(ptr), (size_t)(cnt)*sizeof(*(ptr))))) return rc
+	PA(st.st_time, n); PA(st.st_speed, n); PA(st.st_fd, n); PA(st.ovf_top, 1);
+	PA(st.st_rec, (u64)NS_STAGE_REC*p.seg_cap); PA(st.st_tr, p.seg_cap);
+	PA(st.ev_nins, p.seg_cap); PA(st.ev_ovf, p.seg_cap); PA(st.ev_nrec, p.seg_cap); PA(st.ev_ntr, p.seg_cap); PA(st.ev_idpos, p.seg_cap);
+	PA(p.d_stage, 1);
+	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
+	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
+	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
+	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1);
+	PA(p.cta_ins, 4096); PA(p.cta_rec, 4096); PA(p.cta_tr, 4096); PA(p.cta_draws, 4096);
+	if (n_init) { PA(p.wave_off, n_init+2); PA(p.wave_ops, n_init); }
+	PA(p.ctl, 1);
+#undef PA
+	cudaError_t e;
+	if ((e = cudaMemcpy(p.d_stage, &p.stage, sizeof p.stage, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+	if ((e = cudaMemset(p.grp_cnt, 0, (size_t)(2*S.n_nodes+1)*4)) != cudaSuccess) return (int)e;
+	if ((e = cudaMemset(p.ctl, 0, sizeof *p.ctl)) != cudaSuccess) return (int)e;
+	if ((e = cudaMemset(st.ovf_top, 0, 8)) != cudaSuccess) return (int)e;
+	return 0;
+}
+
+
+// ---- launchers (each defined next to its kernel)
+// ns_seq.cu
+int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream);
+int seq_launch_init_groups(const Sim *d_sims, int n, cudaStream_t stream);
+int seq_launch_exec_ops(const Sim *d_sim, int n_ops, cudaStream_t stream);
+int seq_preload(void);
+// ns_init.cu
+int par_plan_init(ParScratch &p, const ns_sc_op *ops, int n0, int n_nodes);
+int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
+// ns_par.cu
+int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
+int par_preload(void);
+int par_grid(const void *kernel, int sm_count, int *grid);

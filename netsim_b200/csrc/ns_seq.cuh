@@ -9,6 +9,8 @@
 #pragma once
 #include "ns_model.cuh"
 
+namespace {   // internal linkage: every engine translation unit carries its own copy of the device code
+
 __device__ __forceinline__ double warp_min_d(double v){
 	#pragma unroll
 	for (int d = 16; d; d >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, d));
@@ -20,8 +22,6 @@ __device__ __forceinline__ u64 warp_min_u64(u64 v){
 	return v;
 }
 
-// scratch layout inside b_seq/b_ref: [0, batch_cap) ring part, L part in lb arrays
-struct SeqScratch { u64 *lb_seq; int *lb_ref; u64 *lb_tmp_seq; int *lb_tmp_ref; };
 
 // Step 1: global minimum event time + ring head advance.
 __device__ double seq_find_tmin(Ctx &c){
@@ -293,3 +293,5 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
 	ctx_flush(c);
 }
+
+}   // namespace

@@ -91,6 +91,25 @@ struct Sim {
 	uint8_t *rec; ns_trace_row32 *tr;
 };
 
+// Staging area of the grid-parallel path: an event handled out of order cannot know its final
+// sequence numbers / record offset, so its event_adds, records and trace row are parked here under
+// LOCAL indices and committed in batch order by a prefix scan (ns_par.cuh).
+#define NS_STAGE_INLINE 4
+#define NS_STAGE_REC 56
+#define NS_SEQ_PROV (1ull << 63)
+#define NS_HOLE_PURE (-2147483647-1)
+struct ParStage {
+	double *st_time, *st_speed; int *st_fd;     // [NS_STAGE_INLINE*seg_cap] inline, then overflow
+	u64 inline_n, ovf_cap; u64 *ovf_top;
+	uint8_t *st_rec; ns_trace_row32 *st_tr;
+	unsigned *ev_nins; long long *ev_ovf; uint8_t *ev_nrec, *ev_ntr;
+	unsigned *ev_idpos;           // parallel creates: event_adds of the op before its flow-id draw (flow.c:327)
+};
+enum { LC_EVENTS = 0, LC_SPEED_CHANGE, LC_SOLVES, LC_FULL_SPREADS, LC_FLOW_VISITS, LC_RETIMES, LC_N };
+
+// scratch layout inside b_seq/b_ref: [0, batch_cap) ring part, L part in lb arrays
+struct SeqScratch { u64 *lb_seq; int *lb_ref; u64 *lb_tmp_seq; int *lb_tmp_ref; };
+
 // ---------------------------------------------------------------- glibc random(), TYPE_3
 // r[k] = r[k-31] + r[k-3] (mod 2^32), output r[k] >> 1.  Shared by host init (sim_create_node ids)
 // and the device (flow ids, flow.c:327).
