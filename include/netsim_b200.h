@@ -49,6 +49,7 @@ enum ns_err {
 	NS_E_NO_DEVICE = -9,
 	NS_E_ARG = -10,
 	NS_E_BATCH_FULL = -11,
+	NS_E_INTERNAL = -12,     /* an engine invariant failed (a bug, not an input error) */
 };
 
 enum ns_counter {

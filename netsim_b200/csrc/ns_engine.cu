@@ -213,6 +213,12 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	S.adj_arena_cap = 16*F+8*N+64;
 	S.batch_cap = (int)std::min<u64>(S.ring_cap/2, 1ull << 30);
 	S.want_rec = o.want_records; S.want_tr = o.want_trace;
+	{	// engine paths that can be switched off for A/B runs: ns_dev_opts.reserved[0] or NS_FEATURES_OFF (bit mask)
+		unsigned off = (unsigned)o.reserved[0];
+		const char *env = getenv("NS_FEATURES_OFF");
+		if (env) off |= (unsigned)strtoul(env, nullptr, 0);
+		S.features = (int)(NS_FEAT_ALL & ~off);
+	}
 	S.rec_cap = o.want_records ? (o.record_cap ? o.record_cap : std::max<u64>(64u << 20, 64ull*N+4096ull*F)) : 0;
 	S.tr_cap = o.want_trace ? (o.trace_cap ? o.trace_cap : (1u << 20)) : 0;
 
@@ -788,6 +794,7 @@ extern "C" const char *ns_strerror(int err){
 	case NS_E_NO_DEVICE: return "no usable CUDA device";
 	case NS_E_ARG: return "bad argument";
 	case NS_E_BATCH_FULL: return "equal-timestamp batch exceeds scratch capacity";
+	case NS_E_INTERNAL: return "engine invariant failed";
 	default: return err > 0 ? "CUDA error" : "unknown error";
 	}
 }

@@ -192,7 +192,7 @@ int par_plan_init(ParScratch &p, const ns_sc_op *ops, int n0, int n_nodes){
 
 int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){
 	if (p.n_init > 0 && p.n_waves > 0) {
-		int grid = 0, rc = par_grid((const void *)k_init_par, sm_count, &grid);
+		int grid = 0, rc = par_grid((const void *)k_init_par, sm_count, &grid, 0);
 		if (rc) return rc;
 		void *args[] = { (void *)&d_sim, (void *)&p };
 		cudaError_t e = cudaLaunchCooperativeKernel((void *)k_init_par, dim3(grid), dim3(PAR_THREADS), args, 0, stream);

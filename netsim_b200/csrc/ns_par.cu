@@ -29,7 +29,7 @@ __device__ __noinline__ void par_finish_piece(const Sim &S, SimState *st, ParScr
 	st->cnt[NS_CNT_SEQ] = st->tail;
 	for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
 	ctl->pos = ctl->seg_hi;
-	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
+	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0;
 	ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 	*P.stage.ovf_top = 0;
 }
@@ -90,6 +90,9 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 	const u64 gtid = (u64)blockIdx.x*PAR_THREADS+tid, gth = (u64)gridDim.x*PAR_THREADS;
 	const u64 tmask = (u64)S.n_ring_tiles-1, smask = S.ring_cap-1;
 	const bool leader = blockIdx.x == 0 && tid == 0;
+	extern __shared__ __align__(16) unsigned char dyn_smem[];
+	HubSmem &Hs = *reinterpret_cast<HubSmem *>(dyn_smem);
+	const bool hub_on = (S.features & NS_FEAT_HUBCTA) != 0;
 #ifdef NS_PROFILE
 	u64 t_ph = gtimer();
 	const u64 t_kernel0 = t_ph;
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			// sparse phase: many small batches in a row and event stores one warp can scan -> hand over to k_run_seq
 			ctl->small_streak = nb+nl < PAR_MIN_BATCH ? ctl->small_streak+1 : 0;
 			if (ctl->small_streak >= SPARSE_STREAK && n_wt+(u64)S.n_l_tiles <= SPARSE_MAX_TILES) { st->want_sparse = 1; ctl->small_streak = 0; }
-			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0;
+			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0;
 			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 			*P.stage.ovf_top = 0;
 		}
@@ -283,13 +286,34 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 							par_handle_event(c, P, seg_lo, e, m);
 						}
 					}
-					if (j < cnt) { P.defer_pos[g] = j; P.deferred[atomicAdd(&ctl->n_deferred, 1)] = g; }
+					if (j < cnt) {
+						P.defer_pos[g] = j;
+						// a large sender group goes to a whole CTA (hub_chain_cta), everything else to one warp
+						if (hub_on && (g & 1) == SND && S.adj_live[g] >= HUB_MIN_DEG && S.adj_len[g] <= HUB_CAP) P.deferred[P.seg_cap-1-atomicAdd(&ctl->n_hub, 1)] = g;
+						else P.deferred[atomicAdd(&ctl->n_deferred, 1)] = g;
+					}
 					else P.grp_cnt[g] = 0;                            // ready for the next segment
 				}
 				for (int q = 0; q < LC_N; q++) if (c.lc[q]) atomicAdd((unsigned long long *)&ctl->lc[q], c.lc[q]);
 			}
 			grid.sync();
 			PHASE_MARK(PH_SOLVE1);
+			// ---- E3: one CTA per large sender group, its flows resident in shared memory ------------------
+			// (before E2 in program order, concurrent with it in time: CTAs without a hub go straight on)
+			if (ctl->n_hub) {
+				const int n_hub = ctl->n_hub;
+				u64 hlc[LC_N];
+				for (int q = 0; q < LC_N; q++) hlc[q] = 0;
+				while (true) {
+					__syncthreads();
+					if (tid == 0) Hs.work = atomicAdd(&ctl->hub_work, 1);
+					__syncthreads();
+					const int k = Hs.work;
+					if (k >= n_hub) break;
+					hub_chain_cta(S, st, P, Hs, P.deferred[P.seg_cap-1-k], seg_lo, m, hlc);
+				}
+				if (tid == 0) for (int q = 0; q < LC_N; q++) if (hlc[q]) atomicAdd((unsigned long long *)&ctl->lc[q], hlc[q]);
+			}
 			// ---- E2: one WARP per remaining group: full spreads strided over the lanes ----------------
 			{
 				const int n_def = ctl->n_deferred;
@@ -313,7 +337,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 #ifdef NS_PROFILE
 					int j0 = j;
 #endif
-					if (cnt-j >= GE_MIN_CHAIN && S.adj_len[g] <= 32) ge_chain(c, P, g, seg_lo, off, j, cnt, m);
+					if (cnt-j >= GE_MIN_CHAIN && S.adj_len[g] <= 32) { if (S.features & NS_FEAT_CHAIN2) ge_chain2(c, P, g, seg_lo, off, j, cnt, m); else ge_chain(c, P, g, seg_lo, off, j, cnt, m); }
 					else for (; j < cnt; j++) par_handle_event(c, P, seg_lo, P.grp_items[off+j], m);
 					if (lane == 0) {
 						P.grp_cnt[g] = 0;                             // ready for the next segment
@@ -425,23 +449,27 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 }
 
 // ---------------------------------------------------------------- host launchers
-int par_grid(const void *kernel, int sm_count, int *grid){
+int par_grid(const void *kernel, int sm_count, int *grid, size_t dyn_smem){
 	int per_sm = 0;
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PAR_THREADS, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PAR_THREADS, dyn_smem);
 	if (e != cudaSuccess) return (int)e;
 	if (per_sm < 1) return NS_E_ARG;
 	*grid = std::min(sm_count*per_sm, 4096);
 	return 0;
 }
 int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){
-	int grid = 0, rc = par_grid((const void *)k_run_par, sm_count, &grid);
+	{	// per device: the hub path keeps a node's flows in dynamic shared memory
+		cudaError_t e0 = cudaFuncSetAttribute(k_run_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HubSmem));
+		if (e0 != cudaSuccess) return (int)e0;
+	}
+	int grid = 0, rc = par_grid((const void *)k_run_par, sm_count, &grid, sizeof(HubSmem));
 	if (rc) return rc;
 	// The grid engine runs until it is done or asks for the single-warp engine (a sparse phase: many
 	// timestamps with a handful of events each, where six grid barriers per timestamp cost more than
 	// the events); that one hands back at the first timestamp that spans many ring tiles.
 	for (int round = 0; round < 1 << 20; round++) {
 		void *args[] = { (void *)&d_sim, (void *)&d_scr, (void *)&p };
-		cudaError_t e = cudaLaunchCooperativeKernel((void *)k_run_par, dim3(grid), dim3(PAR_THREADS), args, 0, stream);
+		cudaError_t e = cudaLaunchCooperativeKernel((void *)k_run_par, dim3(grid), dim3(PAR_THREADS), args, sizeof(HubSmem), stream);
 		if (e != cudaSuccess) return (int)e;
 		(*launches)++;
 		int flags[3];                                                     // sparse_mode, want_sparse, want_dense

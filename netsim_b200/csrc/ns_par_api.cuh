@@ -35,6 +35,7 @@ struct ParScratch {
 	struct Ctl {
 		u64 tmin_bits, first_live;
 		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
+		int n_hub, hub_work;                       // groups handed to whole CTAs (hub_chain_cta); stored from the END of `deferred`
 		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
 		int small_streak;                          // consecutive small batches (sparse phase detection)
 		u64 dbg_key;
@@ -88,4 +89,4 @@ int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count,
 // ns_par.cu
 int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
 int par_preload(void);
-int par_grid(const void *kernel, int sm_count, int *grid);
+int par_grid(const void *kernel, int sm_count, int *grid, size_t dyn_smem);

@@ -167,6 +167,509 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 	__syncwarp();
 }
 
+// ---------------------------------------------------------------- chains, second form
+// The same chain split the way its data dependences run.  Inside one (node,dir) group at one `now`
+// the only loop-carried state of the O(1) solves (flow.c:64-124) is the speed of each flow and the
+// node's usage; everything an event EMITS — its records (record.c:53-116), its event_adds, the
+// completion re-time of range.c:16-79 — depends on that state only through the event's own
+// (speed after, usage after, branch taken).  So, 32 events at a time:
+//   pass A  walks the events in order carrying (gf.sp per lane, usage) and leaves each event's
+//           {speed after, usage after, branch flags} in the lane of the same index;
+//   advance the byte progress of every touched flow once, with the speed it had before its first event of
+//           the run (flow.c:355-357 -> range.h:91-125 is a no-op for later events at the same `now`);
+//   pass B  gives each lane ONE event: owner constants come by indexed shuffle, records are built as words,
+//           event_adds staged, the L-table entry written by the last event of each flow.
+// A full spread in the middle ends the run: pass B for what came before, ge_full_event, next run.
+#define GE_EMIT 1u        // flow.c:64-78: the flow is at its share, tell the other end
+#define GE_DONE_BW 2u     // ... and bwspread returned right there (flow.c:66-74)
+#define GE_CHANGED 4u     // speed and usage changed: R_USAGE record (flow.c:85-124)
+#define GE_DELTA_POS 8u   // flow.c:371: delta > 0
+
+// one 19-byte record with a 6-byte fixed-point value (record.c:53-116) as little-endian words; h0/h1 carry
+// the time fields, which are the same for every record of a chain
+__device__ __forceinline__ uint32_t bswap32(uint32_t x){ return __byte_perm(x, 0, 0x0123); }
+__device__ __forceinline__ void rec19_time(double now, u64 &h0, u64 &h1){
+	uint32_t t = (uint32_t)(int)now;                                  // record.c:66
+	uint16_t ut = (uint16_t)(int)((now-(double)((int)now))*1000);     // record.c:69
+	uint32_t bt = bswap32(t);
+	h0 = (u64)(bt & 0xffffu) << 48;                                   // bytes 6,7
+	h1 = (u64)(bt >> 16) | ((u64)(((ut & 0xffu) << 8) | (ut >> 8)) << 16) | (0xffull << 32);   // bytes 8..12 (bytes = -1)
+}
+__device__ __forceinline__ void rec19_words(u64 h0, u64 h1, uint8_t minor, uint32_t id, double dval, u64 &w0, u64 &w1, u64 &w2){
+	double tmp = dval;                                                // record.c:98-106
+	uint32_t ip = (uint32_t)(int)tmp;
+	tmp = tmp-(double)((int)tmp);
+	uint16_t fp = (uint16_t)(int)(tmp*1000);
+	uint32_t bi = bswap32(ip);
+	w0 = ((u64)minor << 8) | ((u64)bswap32(id) << 16) | h0;
+	w1 = h1 | ((u64)(bi & 0xffffffu) << 40);
+	w2 = (u64)(bi >> 24) | ((u64)(((fp & 0xffu) << 8) | (fp >> 8)) << 8);
+}
+
+__device__ void ge_chain2(Ctx &c, const ParScratch &P, int g, int seg_lo, int off, int j, int cnt, double m){
+	const Sim &S = *c.S;
+	SimState *st = c.st;
+	const int lane = c.lane, n = g >> 1, dir = g & 1;
+	const u64 smask = S.ring_cap-1;
+	const int a_off = S.adj_off[g], a_len = S.adj_len[g];
+	const double total = S.n_total[dir][n], mx = S.n_max[dir][n];
+	double usage = S.n_usage[dir][n];
+	const unsigned node_id = S.n_id[n];
+	const double now = m;
+	const bool sat = !(total < mx+NS_EPS);                            // flow.c:94: an unsaturated node never spreads
+	GFlow gf;
+	ge_load(S, gf, a_off, a_len, lane, dir, total, mx);
+	GeStage stg;
+	ge_stage_load(stg, S, *c.ps);
+	u64 h0, h1;
+	rec19_time(now, h0, h1);
+	unsigned n_simple = 0;
+	for (int j0 = j; j0 < cnt; j0 += 32) {
+		const int nev = cnt-j0 < 32 ? cnt-j0 : 32;
+		// ---- fetch: lane k holds event k of the block and the lane that owns its flow
+		int my_e = -1, my_fd = 0, own = lane; double my_speed = 0; u64 my_slot = 0;
+		bool bad = false;
+		if (lane < nev) {
+			my_e = P.grp_items[off+j0+lane];
+			my_slot = S.b_seq[seg_lo+my_e] & smask;
+			my_fd = S.q_fd[my_slot]; my_speed = S.q_speed[my_slot];
+			own = S.f_pos[dir][my_fd >> 1];                           // list position == lane (ge_load)
+			if ((unsigned)own >= 32u) { bad = true; own = lane; }
+		}
+		{
+			const int own_nf = __shfl_sync(FULLMASK, gf.nf, own);
+			if (lane < nev && own_nf != (my_fd >> 1)) bad = true;
+		}
+		if (__any_sync(FULLMASK, bad)) {
+			// a flow the lanes do not hold (cannot happen for a consistent group): the table-driven handler for
+			// this block; the tables are current (write-back below), reload afterwards
+			for (int k = 0; k < nev; k++) par_handle_event(c, P, seg_lo, __shfl_sync(FULLMASK, my_e, k), m);
+			ge_load(S, gf, a_off, a_len, lane, dir, total, mx);
+			usage = S.n_usage[dir][n];
+			continue;
+		}
+		unsigned dirty = 0;                                           // lanes whose gf.sp moved in this block
+		int k0 = 0;
+		while (k0 < nev) {
+			// ---- pass A: the recurrence, warp-uniform
+			const double sp0 = gf.sp;
+			double ev_fs = 0, ev_use = 0; unsigned ev_fl = 0;
+			bool hit_full = false;
+			int k = k0;
+			for (; k < nev; k++) {
+				const int owner = __shfl_sync(FULLMASK, own, k);
+				const double speed = __shfl_sync(FULLMASK, my_speed, k);
+				const double fs = __shfl_sync(FULLMASK, gf.sp, owner), share = __shfl_sync(FULLMASK, gf.share, owner);
+				double amount = speed-fs;                                 // flow.c:359
+				unsigned fl = amount > 0 ? GE_DELTA_POS : 0u;
+				if (amount > NS_EPS && fs+amount > share) {               // flow.c:64-78
+					fl |= GE_EMIT;
+					if (fs > share) fl |= GE_DONE_BW; else amount = share-fs;
+				}
+				double nfs = fs;
+				if (!(fl & GE_DONE_BW) && !(amount > -NS_EPS && amount < NS_EPS)) {   // flow.c:80-83
+					if (sat && !(amount < NS_EPS && amount > -64) && !(amount > -NS_EPS && usage+amount < mx+NS_EPS)) { hit_full = true; break; }
+					nfs = fs+amount;                                      // flow.c:85
+					usage += amount;                                      // flow.c:86-124, the O(1) exits
+					fl |= GE_CHANGED;
+					if (lane == owner) gf.sp = nfs;
+					dirty |= 1u << owner;
+				}
+				if (lane == k) { ev_fs = nfs; ev_use = usage; ev_fl = fl; }
+			}
+			const int k1 = k;
+			const bool act = lane >= k0 && lane < k1;
+			if (k1 > k0) {
+				n_simple += (unsigned)(k1-k0);
+				// ---- byte progress of the touched flows, once, with the speed before the run (range.h:91-125)
+				if (dir == RCV) {
+					const unsigned touched = __reduce_or_sync(FULLMASK, act ? (1u << own) : 0u);
+					if ((touched >> lane) & 1u) {
+						if (now != gf.s_last) { gf.s_last = now; S.r_last[gf.sr] = now; }
+						if (now != gf.d_last) {
+							double delta = sp0*(now-gf.d_last), tt;
+							delta = delta-gf.d_lenc;
+							tt = delta+gf.d_len;
+							gf.d_lenc = (tt-gf.d_len)-delta;
+							gf.d_len = tt;
+							gf.d_last = now;
+							S.r_lenc[gf.dr] = gf.d_lenc; S.r_len[gf.dr] = gf.d_len; S.r_last[gf.dr] = now;
+						}
+					}
+				}
+				// ---- pass B: one event per lane; the owner's constants by indexed shuffle
+				const unsigned o_id = __shfl_sync(FULLMASK, gf.id, own);
+				const int o_ord = __shfl_sync(FULLMASK, gf.ord, own);
+				const double o_delay = __shfl_sync(FULLMASK, gf.delay, own), o_share = __shfl_sync(FULLMASK, gf.share, own);
+				double o_dlen = 0, o_slen = 0; long long o_dstart = 0, o_sstart = 0; int o_npos = 0;
+				if (dir == RCV) {
+					o_dlen = __shfl_sync(FULLMASK, gf.d_len, own); o_slen = __shfl_sync(FULLMASK, gf.s_len, own);
+					o_dstart = __shfl_sync(FULLMASK, gf.d_start, own); o_sstart = __shfl_sync(FULLMASK, gf.s_start, own);
+					o_npos = __shfl_sync(FULLMASK, gf.npos, own);
+				}
+				// the last event of each flow in the run owns the flow's L-table entries
+				const unsigned peers = __match_any_sync(FULLMASK, act ? own : 32+lane);
+				const bool last = act && lane == 31-__clz(peers);
+				if (act) {
+					const int f = my_fd >> 1;
+					const unsigned e = (unsigned)my_e;
+					const u64 sbase = (u64)e*NS_STAGE_INLINE;
+					unsigned lseq = 0;
+					const double et = now+o_delay;                        // queue_speed_event, flow.c:22
+					if (!(et >= now)) atomicCAS(&st->status, 0, isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME);
+					if (ev_fl & GE_EMIT) {
+						stg.st_time[sbase+lseq] = et; stg.st_speed[sbase+lseq] = (ev_fl & GE_DONE_BW) ? ev_fs : o_share;
+						stg.st_fd[sbase+lseq] = f*2+(!dir); lseq++;
+					}
+					if (dir == RCV) {                                     // flow.c:367-370 -> range.c:16-79
+						Retime p;
+						p.add_drain = p.add_done = 0; p.drain_t = p.done_t = NS_INF;
+						if (!(ev_fs < NS_EPS)) {                          // range.c:26-27
+							int dtype = -1;
+							int err = retime_math(now, ev_fs, false, 0.0, NS_INF, o_slen, o_dlen, o_dstart, o_sstart, o_npos, p, dtype);
+							if (dtype >= 0) S.f_drain_type[f] = (uint8_t)dtype;
+							if (err) atomicCAS(&st->status, 0, err);
+						}
+						if (p.add_done) {
+							if (p.add_drain) { stg.st_fd[sbase+lseq] = NS_HOLE_PURE; lseq++; }
+							if (last) {
+								S.l_time[2*f] = p.done_t; S.l_seq[2*f] = NS_SEQ_PROV | ((u64)e << 24) | lseq;
+								S.l_time[2*f+1] = NS_INF;
+								tmin_lower(&S.l_tmin[(2*f) >> NS_TILE_SHIFT], p.done_t);
+							}
+							stg.st_fd[sbase+lseq] = -(2*f+1); lseq++;
+						} else if (p.add_drain) {
+							if (last) {
+								S.l_time[2*f+1] = p.drain_t; S.l_seq[2*f+1] = NS_SEQ_PROV | ((u64)e << 24) | lseq;
+								S.l_time[2*f] = NS_INF;
+								tmin_lower(&S.l_tmin[(2*f+1) >> NS_TILE_SHIFT], p.drain_t);
+							}
+							stg.st_fd[sbase+lseq] = -(2*f+1+1); lseq++;
+						} else if (last) { S.l_time[2*f] = NS_INF; S.l_time[2*f+1] = NS_INF; }
+					} else if (ev_fl & GE_DELTA_POS) {                    // flow.c:371-374
+						stg.st_time[sbase+lseq] = et; stg.st_speed[sbase+lseq] = ev_fs; stg.st_fd[sbase+lseq] = f*2+RCV; lseq++;
+					}
+					unsigned rec_n = 0;
+					if (stg.want_rec) {
+						u64 *rw = (u64 *)(stg.st_rec+(u64)e*NS_STAGE_REC);
+						u64 a0, a1, a2;
+						rec19_words(h0, h1, R_SPD|dir, o_id, my_speed, a0, a1, a2);      // flow.c:383
+						if (ev_fl & GE_CHANGED) {
+							u64 u0, u1, u2;
+							rec19_words(h0, h1, R_USAGE|dir, node_id, ev_use, u0, u1, u2);   // record_wrapper.h:6-9
+							rw[0] = u0; rw[1] = u1; rw[2] = u2 | (a0 << 24);
+							rw[3] = (a0 >> 40) | (a1 << 24); rw[4] = (a1 >> 40) | (a2 << 24);
+							rec_n = 38;
+						} else { rw[0] = a0; rw[1] = a1; rw[2] = a2; rec_n = 19; }
+					}
+					unsigned ntr = 0;
+					if (stg.want_tr) {
+						ns_trace_row32 r; r.type = EV_SPEED_CHANGE|(dir << 8); r.ord = o_ord; r.time = now; r.v0 = my_speed; r.v1 = ev_fs;
+						stg.st_tr[e] = r; ntr = 1;
+					}
+					stg.ev_nins[e] = lseq; stg.ev_ovf[e] = -1; stg.ev_nrec[e] = (uint8_t)rec_n; stg.ev_ntr[e] = (uint8_t)ntr;
+					S.q_time[my_slot] = NS_INF;                           // event_pop
+				}
+			}
+			if (!hit_full) break;
+			// ---- event k1 reaches the full spread (flow.c:126-203): warp-cooperative, on the registers
+			{
+				const int e = __shfl_sync(FULLMASK, my_e, k1), owner = __shfl_sync(FULLMASK, own, k1);
+				const double speed = __shfl_sync(FULLMASK, my_speed, k1);
+				const u64 slot = __shfl_sync(FULLMASK, my_slot, k1);
+				c.ev = (unsigned)e; c.lseq = 0; c.rec_n = 0; c.tr_n = 0; c.ovf_base = -1;
+				ge_full_event(c, S, gf, usage, total, mx, node_id, n, dir, speed, owner);
+				if (lane == 0) {
+					const ParStage &ps = *c.ps;
+					ps.ev_nins[e] = c.lseq; ps.ev_ovf[e] = c.ovf_base;
+					ps.ev_nrec[e] = (uint8_t)c.rec_n; ps.ev_ntr[e] = (uint8_t)c.tr_n;
+					S.q_time[slot] = NS_INF;                              // event_pop
+				}
+			}
+			k0 = k1+1;
+		}
+		// ---- write-back: the speeds that moved, the usage
+		if ((dirty >> lane) & 1u) S.f_speed[dir][gf.nf] = gf.sp;
+		if (lane == 0) S.n_usage[dir][n] = usage;
+		__syncwarp();
+	}
+	c.lc[LC_EVENTS] += n_simple; c.lc[LC_SPEED_CHANGE] += n_simple; c.lc[LC_SOLVES] += n_simple;
+	if (dir == RCV) c.lc[LC_RETIMES] += n_simple;
+	__syncwarp();
+}
+
+// ---------------------------------------------------------------- hub chains: one CTA, shared memory
+// A saturated sender with hundreds or thousands of flows (a p2p server / seeder) answers nearly every event
+// with a full spread (flow.c:126-203), and a batch holds a chain of them for the same node.  One CTA takes
+// the whole chain: the node's flows {speed, share, remote share, delay} are loaded into shared memory once
+// (list position p, newest = highest, flow.c:311-312), every spread runs its two passes over them with all
+// threads, and the reference's two in-order fp64 sums (e, new_use; flow.c:128-145,199) are taken by one thread
+// over the order-preserving compaction of the NON-ZERO terms (x + 0.0 == x, and the sums never reach -0.0, so
+// dropping exact zeros leaves every partial sum unchanged).  SND groups only: RCV victims re-time (flow.c:193).
+#define HUB_CAP 3584
+#define HUB_MIN_DEG 160
+#define HUB_ROWS (HUB_CAP/PAR_THREADS)
+#define HUB_SORT_MAX 4096
+struct HubSmem {
+	double sp[HUB_CAP], shr[HUB_CAP], rsh[HUB_CAP], dly[HUB_CAP], term[HUB_CAP];
+	int nf[HUB_CAP];
+	int cnt_a[HUB_ROWS*PAR_WARPS], cnt_b[HUB_ROWS*PAR_WARPS];     // per (row, warp): selected entries -> exclusive offsets
+	int ev_e[PAR_THREADS], ev_pf[PAR_THREADS]; double ev_speed[PAR_THREADS]; u64 ev_slot[PAR_THREADS];
+	double bcast_d; long long bcast_ll; int tot_a, tot_b, work;
+};
+// exclusive scan of the (row, warp) counts in row-major order by warp 0; returns nothing, leaves the total in *tot
+__device__ __forceinline__ void hub_scan(int *cnt, int n, int *tot, int lane){
+	const int per = (HUB_ROWS*PAR_WARPS+31)/32;
+	int v[per], s = 0;
+	#pragma unroll
+	for (int q = 0; q < per; q++) { int i = lane*per+q; v[q] = i < n ? cnt[i] : 0; s += v[q]; }
+	int incl = s;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+	int run = incl-s;
+	#pragma unroll
+	for (int q = 0; q < per; q++) { int i = lane*per+q; if (i < n) cnt[i] = run; run += v[q]; }
+	if (lane == 31) *tot = incl;
+}
+__device__ __forceinline__ double hub_serial_sum(const double *t, int n){
+	double a = 0;
+	int i = 0;
+	for (; i+8 <= n; i += 8) {
+		double x0 = t[i], x1 = t[i+1], x2 = t[i+2], x3 = t[i+3], x4 = t[i+4], x5 = t[i+5], x6 = t[i+6], x7 = t[i+7];
+		a += x0; a += x1; a += x2; a += x3; a += x4; a += x5; a += x6; a += x7;
+	}
+	for (; i < n; i++) a += t[i];
+	return a;
+}
+__device__ void hub_chain_cta(const Sim &S, SimState *st, const ParScratch &P, HubSmem &H, int g, int seg_lo, double m, u64 *lc){
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n = g >> 1;                                             // dir == SND
+	const ParStage &ps = P.stage;
+	const int off = P.grp_off[g], cnt = P.grp_cnt[g];
+	int j = P.defer_pos[g];
+	const int a_off = S.adj_off[g], len = S.adj_len[g], live = S.adj_live[g];
+	const double total = S.n_total[SND][n], mx = S.n_max[SND][n];
+	double usage = S.n_usage[SND][n];
+	const unsigned node_id = S.n_id[n];
+	const u64 smask = S.ring_cap-1;
+	const bool sat = !(total < mx+NS_EPS);
+	const int rows = (len+PAR_THREADS-1)/PAR_THREADS;
+	u64 h0, h1;
+	rec19_time(m, h0, h1);
+	__syncthreads();
+	// ---- the chain in batch order
+	if (j < 0) {
+		int *items = P.grp_items+off;
+		if (cnt <= HUB_SORT_MAX) {
+			int *a = (int *)H.term;
+			int np = 1; while (np < cnt) np <<= 1;
+			for (int i = tid; i < np; i += PAR_THREADS) a[i] = i < cnt ? items[i] : 0x7fffffff;
+			__syncthreads();
+			for (int k = 2; k <= np; k <<= 1)
+				for (int jj = k >> 1; jj > 0; jj >>= 1) {
+					for (int i = tid; i < np; i += PAR_THREADS) {
+						int ixj = i ^ jj;
+						if (ixj > i) { int x = a[i], y = a[ixj]; bool asc = (i & k) == 0; if ((x > y) == asc) { a[i] = y; a[ixj] = x; } }
+					}
+					__syncthreads();
+				}
+			for (int i = tid; i < cnt; i += PAR_THREADS) items[i] = a[i];
+		} else if (warp == 0) warp_sort_global(items, cnt, lane);
+		j = 0;
+		__syncthreads();
+	}
+	// ---- the node's flows, once
+	for (int p = tid; p < len; p += PAR_THREADS) {
+		int nf = S.adj_arena[a_off+p];
+		H.nf[p] = nf;
+		if (nf >= 0) {
+			double ub = S.f_ub[nf];
+			H.sp[p] = S.f_speed[SND][nf];
+			H.shr[p] = total > mx ? ub*mx/total : ub;                     // flow.c:61; == ub*mx/total inside a spread (total > max there)
+			H.rsh[p] = get_share(S, nf, RCV);                             // flow.c:140,165
+			H.dly[p] = S.f_delay[nf];
+		}
+	}
+	for (int j0 = j; j0 < cnt; j0 += PAR_THREADS) {
+		const int nev = cnt-j0 < PAR_THREADS ? cnt-j0 : PAR_THREADS;
+		__syncthreads();
+		if (tid < nev) {
+			int e = P.grp_items[off+j0+tid];
+			u64 slot = S.b_seq[seg_lo+e] & smask;
+			int f = S.q_fd[slot] >> 1;
+			int pf = S.f_pos[SND][f];
+			if ((unsigned)pf >= (unsigned)len || H.nf[pf] != f) pf = -1;
+			H.ev_e[tid] = e; H.ev_pf[tid] = pf; H.ev_speed[tid] = S.q_speed[slot]; H.ev_slot[tid] = slot;
+		}
+		__syncthreads();
+		for (int i = 0; i < nev; i++) {
+			const int e = H.ev_e[i], pf = H.ev_pf[i];
+			const double speed = H.ev_speed[i];
+			if (pf < 0) { if (tid == 0) atomicCAS(&st->status, 0, NS_E_INTERNAL); continue; }
+			const int f = H.nf[pf];
+			double fs = H.sp[pf];
+			const double share = H.shr[pf];
+			const double et = m+H.dly[pf];                                // queue_speed_event, flow.c:22
+			__syncthreads();                                              // everyone has read sp[pf] before thread 0 rewrites it
+			const double delta0 = speed-fs;                               // flow.c:359
+			double amount = delta0;
+			const u64 sbase = (u64)e*NS_STAGE_INLINE;
+			unsigned lseq = 0;
+			bool done_bw = false, changed = false, full = false;
+			if (amount > NS_EPS && fs+amount > share) {                   // flow.c:64-78
+				double es = share;
+				if (fs > share) { es = fs; done_bw = true; } else amount = share-fs;
+				if (tid == 0) { ps.st_time[sbase] = et; ps.st_speed[sbase] = es; ps.st_fd[sbase] = f*2+RCV; }
+				lseq = 1;
+			}
+			if (!done_bw && !(amount > -NS_EPS && amount < NS_EPS)) {     // flow.c:80-85
+				fs += amount;
+				changed = true;
+				full = sat && !(amount < NS_EPS && amount > -64) && !(amount > -NS_EPS && usage+amount < mx+NS_EPS);
+				if (!full) usage += amount;                               // flow.c:86-124
+			}
+			long long ovf_base = -1;
+			if (full) {                                                   // flow.c:126-203
+				if (tid == 0) {
+					H.sp[pf] = fs; S.f_speed[SND][f] = fs;
+					u64 need = (u64)live+8;
+					long long b = (long long)atomicAdd((unsigned long long *)ps.ovf_top, (unsigned long long)need);
+					if ((u64)b+need > ps.ovf_cap) { atomicCAS(&st->status, 0, NS_E_TABLE_FULL); b = 0; }
+					H.bcast_ll = b;
+				}
+				double spread_amount = amount;                            // flow.c:112-122
+				if (amount > -NS_EPS) spread_amount = amount-mx+usage;
+				const bool dec = amount < NS_EPS, inc = !dec && amount > NS_EPS;
+				__syncthreads();
+				ovf_base = H.bcast_ll;
+				// pass 1 (flow.c:128-145): terms in list order, non-zero ones compacted in order
+				double term[HUB_ROWS]; unsigned bal[HUB_ROWS];
+				#pragma unroll
+				for (int r = 0; r < HUB_ROWS; r++) {
+					double t = 0.0;
+					if (r < rows) {
+						int p = len-1-r*PAR_THREADS-tid;
+						if (p >= 0 && p != pf && H.nf[p] >= 0) {
+							double sp = H.sp[p];
+							if (dec) { double ls = H.rsh[p]; if (sp < ls) t = ls-sp; }
+							else if (inc) { double ls = H.shr[p]; if (sp > ls) t = sp-ls; }
+						}
+						unsigned b = __ballot_sync(FULLMASK, t != 0.0);
+						bal[r] = b;
+						if (lane == 0) H.cnt_a[r*PAR_WARPS+warp] = __popc(b);
+					}
+					term[r] = t;
+				}
+				__syncthreads();
+				if (warp == 0) hub_scan(H.cnt_a, rows*PAR_WARPS, &H.tot_a, lane);
+				__syncthreads();
+				#pragma unroll
+				for (int r = 0; r < HUB_ROWS; r++)
+					if (r < rows && term[r] != 0.0) H.term[H.cnt_a[r*PAR_WARPS+warp]+__popc(bal[r] & ((1u << lane)-1))] = term[r];
+				__syncthreads();
+				if (tid == 0) H.bcast_d = hub_serial_sum(H.term, H.tot_a);
+				__syncthreads();
+				const double esum = H.bcast_d;
+				if (dec && -amount > esum) amount = -esum;                // flow.c:149-154
+				const bool dec2 = amount < NS_EPS, inc2 = !dec2 && amount > NS_EPS;
+				// pass 2 (flow.c:156-200): new speeds, one event per adjusted flow in list order, values for new_use
+				double val[HUB_ROWS];
+				#pragma unroll
+				for (int r = 0; r < HUB_ROWS; r++) {
+					double v = 0.0; int ok = 0;
+					if (r < rows) {
+						int p = len-1-r*PAR_THREADS-tid;
+						if (p == pf) v = fs;
+						else if (p >= 0 && H.nf[p] >= 0) {
+							const int nf = H.nf[p];
+							double sp = H.sp[p];
+							v = sp;
+							int adj = 0;
+							if (dec2) {
+								double ls = H.rsh[p];
+								if (sp < ls) { double delta = ls-sp; double nsp = sp-amount*delta/esum; H.sp[p] = nsp; S.f_speed[SND][nf] = nsp; v = nsp; adj = 1; }   // :171-178
+							} else if (inc2) {
+								double ls = H.shr[p];
+								if (sp > ls) { double delta = sp-ls; double nsp = sp-spread_amount*delta/esum; H.sp[p] = nsp; S.f_speed[SND][nf] = nsp; v = nsp; adj = 1; }   // :187-189
+							}
+							if (adj) {
+								double t = m+H.dly[p];
+								ok = 1;
+								if (t < m) { if (t < m-NS_EPS) ok = 0; }
+								if (isnan(t)) ok = 0;
+								if (!ok) atomicCAS(&st->status, 0, isnan(t) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME);
+							}
+						}
+						unsigned b = __ballot_sync(FULLMASK, ok), bv = __ballot_sync(FULLMASK, v != 0.0);
+						bal[r] = b;
+						if (lane == 0) { H.cnt_a[r*PAR_WARPS+warp] = __popc(b); H.cnt_b[r*PAR_WARPS+warp] = __popc(bv); }
+					}
+					val[r] = v;                                               // an adjusted flow emits its new speed, which is its value
+				}
+				__syncthreads();
+				if (warp == 0) hub_scan(H.cnt_a, rows*PAR_WARPS, &H.tot_a, lane);
+				if (warp == 1) hub_scan(H.cnt_b, rows*PAR_WARPS, &H.tot_b, lane);
+				__syncthreads();
+				#pragma unroll
+				for (int r = 0; r < HUB_ROWS; r++) {
+					if (r >= rows) continue;
+					const unsigned lt = (1u << lane)-1;
+					const unsigned bv = __ballot_sync(FULLMASK, val[r] != 0.0);
+					if ((bal[r] >> lane) & 1u) {
+						int p = len-1-r*PAR_THREADS-tid;
+						u64 q = (u64)lseq+(u64)(H.cnt_a[r*PAR_WARPS+warp]+__popc(bal[r] & lt));
+						u64 si = q < NS_STAGE_INLINE ? sbase+q : ps.inline_n+(u64)ovf_base+(q-NS_STAGE_INLINE);
+						double t = m+H.dly[p];
+						if (t < m) t = m;
+						ps.st_time[si] = t; ps.st_speed[si] = val[r]; ps.st_fd[si] = H.nf[p]*2+RCV;
+					}
+					if (val[r] != 0.0) H.term[H.cnt_b[r*PAR_WARPS+warp]+__popc(bv & lt)] = val[r];
+				}
+				__syncthreads();
+				lseq += (unsigned)H.tot_a;
+				if (tid == 0) H.bcast_d = hub_serial_sum(H.term, H.tot_b);   // flow.c:199
+				__syncthreads();
+				usage = H.bcast_d;                                        // flow.c:201
+			}
+			if (tid == 0) {
+				if (!(et >= m)) atomicCAS(&st->status, 0, isnan(et) ? NS_E_NAN_TIME : NS_E_BACK_IN_TIME);
+				if (changed && !full) { H.sp[pf] = fs; S.f_speed[SND][f] = fs; }
+				if (changed) S.n_usage[SND][n] = usage;
+				if (delta0 > 0) {                                         // flow.c:371-374
+					u64 q = lseq;
+					u64 si = q < NS_STAGE_INLINE ? sbase+q : ps.inline_n+(u64)ovf_base+(q-NS_STAGE_INLINE);
+					ps.st_time[si] = et; ps.st_speed[si] = fs; ps.st_fd[si] = f*2+RCV;
+				}
+				unsigned rec_n = 0;
+				if (S.want_rec) {
+					u64 *rw = (u64 *)(ps.st_rec+(u64)e*NS_STAGE_REC);
+					u64 a0, a1, a2;
+					rec19_words(h0, h1, R_SPD|SND, S.f_id[f], speed, a0, a1, a2);        // flow.c:383
+					if (changed) {
+						u64 u0, u1, u2;
+						rec19_words(h0, h1, R_USAGE|SND, node_id, usage, u0, u1, u2);     // record_wrapper.h:6-9
+						rw[0] = u0; rw[1] = u1; rw[2] = u2 | (a0 << 24);
+						rw[3] = (a0 >> 40) | (a1 << 24); rw[4] = (a1 >> 40) | (a2 << 24);
+						rec_n = 38;
+					} else { rw[0] = a0; rw[1] = a1; rw[2] = a2; rec_n = 19; }
+				}
+				unsigned ntr = 0;
+				if (S.want_tr) {
+					ns_trace_row32 r; r.type = EV_SPEED_CHANGE|(SND << 8); r.ord = S.f_ord[f]; r.time = m; r.v0 = speed; r.v1 = fs;
+					ps.st_tr[e] = r; ntr = 1;
+				}
+				ps.ev_nins[e] = lseq+(delta0 > 0 ? 1u : 0u); ps.ev_ovf[e] = ovf_base; ps.ev_nrec[e] = (uint8_t)rec_n; ps.ev_ntr[e] = (uint8_t)ntr;
+				S.q_time[H.ev_slot[i]] = NS_INF;                          // event_pop
+				lc[LC_EVENTS] += 1; lc[LC_SPEED_CHANGE] += 1; lc[LC_SOLVES] += 1;
+				if (full) { lc[LC_FULL_SPREADS] += 1; lc[LC_FLOW_VISITS] += 2ull*(u64)live; }
+			}
+			__syncthreads();
+		}
+	}
+	if (tid == 0) { S.n_usage[SND][n] = usage; P.grp_cnt[g] = 0; }
+	__syncthreads();
+}
+
 // copy the staged outputs of segment-local event e to their final places
 __device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep){
 	unsigned nins = ps.ev_nins[e];

@@ -25,6 +25,9 @@
 #define NS_EPS 1e-4                       /* sim.c:11 */
 #define NS_INF (__longlong_as_double(0x7ff0000000000000LL))
 #define FULLMASK 0xffffffffu
+#define NS_FEAT_CHAIN2 1u   /* small-node event chains: scalar recurrence pass + lane-parallel emission pass */
+#define NS_FEAT_HUBCTA 2u   /* full spreads of large SND groups by a whole CTA from shared memory */
+#define NS_FEAT_ALL 0xffffu
 
 enum { SND = 0, RCV = 1 };
 enum { EV_FLOW_DRAIN = 0, EV_FLOW_DONE = 1, EV_FLOW_SPEED_THROTTLE = 2, EV_PACKET_DONE = 3, EV_SPEED_CHANGE = 4, EV_USER = 5 };
@@ -64,6 +67,7 @@ struct Sim {
 	int adj_arena_cap, batch_cap;
 	u64 rec_cap, tr_cap;
 	int want_rec, want_tr;
+	int features;                 // NS_FEAT_* bits (ns_dev_opts.reserved[0] / NS_FEATURES): engine paths that can be switched off for A/B runs
 	SimState *st;
 	// nodes
 	double *n_max[2], *n_usage[2], *n_total[2]; uint32_t *n_id; int *n_res_head;

@@ -25,7 +25,13 @@ def golden_cases():
     d = os.path.join(ROOT, "tests", "golden")
     out = []
     for fn in sorted(os.listdir(d)):
-        if fn.endswith(".npz"):
+        if fn.endswith(".npz") and not fn.startswith("pick"):
             z = np.load(os.path.join(d, fn))
             out.append((fn[:-4], z))
     return out
+
+
+def pick_golden():
+    """tables through the reference's own qselect_eval / fetch metrics (tests/golden/make_golden.py pick_goldens)"""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "pick.npz"))

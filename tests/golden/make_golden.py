@@ -59,6 +59,49 @@ def stderr_goldens():
             open(os.path.join(OUT, t + ".stderr.txt"), "wb").write(p.stderr)
 
 
+def pick_goldens():
+    """Candidate tables through the reference's own qselect_eval (client_behaviour.h:63-65 over qselect.h:5-27)
+    and fetch metrics (p2p_common.h:171-198), via oracle/ref_pick.c -> oracle/_ref/libref_pick.so."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(refrun.REF, "libref_pick.so"))
+    L.ref_pick_opt1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ref_metric.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    rng = np.random.default_rng(2024)
+    offs, vals, nodes, ks = [0], [], [], []
+    for q in range(600):
+        c = int(rng.integers(0, 90)) if q % 50 else int(rng.integers(1100, 2600))   # some beyond the kernel's smem table
+        # many ties ... the widest range on which the reference is DEFINED: its cmp is `a->val - b->val` in int
+        # (client_behaviour.h:63), so |val| < 2^30 keeps every difference representable (beyond that the
+        # reference is signed-overflow UB and gcc -O2 no longer wraps; real metrics are within +-4000)
+        span = int(rng.choice([3, 30, 1000, 2 ** 30 - 1]))
+        offs.append(offs[-1] + c)
+        vals.extend(rng.integers(-span, span, c, dtype=np.int64).tolist())
+        nodes.extend(rng.permutation(max(c, 1) * 3)[:c].tolist())
+        ks.append(int(rng.integers(1, max(2, c + 3))))
+    off, val, node, k = (np.array(x, dtype=np.int32) for x in (offs, vals, nodes, ks))
+    ov, on, oc = val.copy(), node.copy(), np.zeros(len(ks), dtype=np.int32)
+    for q in range(len(ks)):
+        lo, hi = int(off[q]), int(off[q + 1])
+        v, nd = val[lo:hi].copy(), node[lo:hi].copy()
+        oc[q] = L.ref_pick_opt1(v.ctypes.data, nd.ctypes.data, hi - lo, int(k[q]))
+        ov[lo:hi], on[lo:hi] = v, nd
+    # metrics: (metric, tz_node, tz_client, total_up, max_up) -> value
+    mq = np.zeros(4000, dtype=[("metric", "<i4"), ("tz_node", "<i4"), ("tz_client", "<i4"), ("total_up", "<f8"), ("max_up", "<f8"), ("out", "<i4")])
+    mq["metric"] = rng.integers(0, 2, len(mq))
+    mq["tz_node"] = rng.integers(0, 24, len(mq))
+    mq["tz_client"] = rng.integers(0, 24, len(mq))
+    mq["total_up"] = np.round(rng.random(len(mq)) * 400000, 1) * (rng.random(len(mq)) < 0.9)
+    mq["max_up"] = rng.choice([8000.0, 40000.0, 160000.0, 1000.0], len(mq))
+    for i in range(len(mq)):
+        mq["out"][i] = L.ref_metric(int(mq["metric"][i]), int(mq["tz_node"][i]), int(mq["tz_client"][i]), float(mq["total_up"][i]), float(mq["max_up"][i]))
+    np.savez_compressed(os.path.join(OUT, "pick.npz"), off=off, val=val, node=node, k=k, out_val=ov, out_node=on, out_cnt=oc, metric=mq)
+    print("pick", len(ks), "tables,", len(val), "candidates,", len(mq), "metric points")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pick":
+        pick_goldens()
+        sys.exit(0)
     main()
     stderr_goldens()
+    pick_goldens()

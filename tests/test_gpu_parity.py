@@ -3,7 +3,7 @@ committed golden vectors from the compiled reference, and (when it travelled) th
 import numpy as np
 import pytest
 
-from conftest import golden_cases
+from conftest import golden_cases, pick_golden
 from netsim_b200 import engine as E
 from netsim_b200 import scenario as S
 from oracle import pyoracle, refrun
@@ -121,6 +121,14 @@ def test_ensemble_digests_match_single_runs(built):
             assert dig[i]["record_bytes"] == len(o.records())
             assert dig[i]["record_hash"] == E.stream_hash(o.records())
     ens.close()
+
+
+def test_pick_batch_matches_reference_golden(built):
+    """k_pick against the tables the reference's own qselect_eval left (tests/golden/pick.npz): same order"""
+    z = pick_golden()
+    ov, on, oc, ms = E.pick_batch(1, z["off"], z["val"], z["node"], z["k"])
+    assert (oc == z["out_cnt"]).all()
+    assert (ov == z["out_val"]).all() and (on == z["out_node"]).all()
 
 
 def test_pick_batch_matches_qselect(built):

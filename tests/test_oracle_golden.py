@@ -4,7 +4,7 @@ runs against the reference itself.  Bit-exact: record bytes and fp64 trace rows.
 import numpy as np
 import pytest
 
-from conftest import golden_cases
+from conftest import golden_cases, pick_golden
 from netsim_b200 import scenario as S
 from oracle import pyoracle, refrun
 
@@ -90,3 +90,40 @@ def test_qselect_restatement_against_definition(built):
         assert sorted(v[:k]) == sorted(val)[:k]
         assert sorted(nd) == list(range(n))
         assert all(val[nd[i]] == v[i] for i in range(n))
+
+
+def test_picker_oracle_pinned_to_reference_golden(built):
+    """oracle/ns_oracle.c's picker functions against what the reference's own qselect_eval (modules/qselect.h:5-27
+    as instantiated at client_behaviour.h:63-65) and fetch metrics (p2p_common.h:171-198) produced
+    (tests/golden/pick.npz, generated through oracle/ref_pick.c): same kept count, same ORDER."""
+    z = pick_golden()
+    L = pyoracle.lib()
+    off, val, node, k = z["off"], z["val"], z["node"], z["k"]
+    for q in range(len(k)):
+        lo, hi = int(off[q]), int(off[q + 1])
+        v, nd = val[lo:hi].copy(), node[lo:hi].copy()
+        cnt = L.ns_oracle_pick_opt1(v.ctypes.data, nd.ctypes.data, hi - lo, int(k[q]))
+        assert cnt == int(z["out_cnt"][q])
+        assert (v == z["out_val"][lo:hi]).all() and (nd == z["out_node"][lo:hi]).all()
+    import ctypes as C
+    L.ns_oracle_metric.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    for r in z["metric"]:
+        assert L.ns_oracle_metric(int(r["metric"]), int(r["tz_node"]), int(r["tz_client"]), float(r["total_up"]), float(r["max_up"])) == int(r["out"])
+
+
+@pytest.mark.skipif(not refrun.available(), reason="compiled reference (oracle/_ref) not present")
+def test_picker_oracle_vs_live_reference(built):
+    """fresh random tables through oracle/_ref/libref_pick.so (the reference's code) and the restatement"""
+    import ctypes as C
+    import os
+    R = C.CDLL(os.path.join(refrun.REF, "libref_pick.so"))
+    L = pyoracle.lib()
+    rng = np.random.default_rng(77)
+    for _ in range(400):
+        c = int(rng.integers(1, 200))
+        k = int(rng.integers(1, c + 4))
+        val = rng.integers(-40, 40, c).astype(np.int32)
+        node = rng.permutation(c).astype(np.int32)
+        v1, n1, v2, n2 = val.copy(), node.copy(), val.copy(), node.copy()
+        assert R.ref_pick_opt1(v1.ctypes.data, n1.ctypes.data, c, k) == L.ns_oracle_pick_opt1(v2.ctypes.data, n2.ctypes.data, c, k)
+        assert (v1 == v2).all() and (n1 == n2).all()
