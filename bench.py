@@ -6,12 +6,14 @@
 Workload (BASELINE.json configs[2]): a p2p swarm of 100 032 peers + 320 hubs with ~1M concurrent
 flows, one simulation per GPU (generator netsim_b200/scenario.py:swarm_fast).
 A "step" is one window of `--events-per-step` simulated events handled by ONE launch of the
-persistent engine kernel (ns_dev_run through the C ABI).  With N>1 every rank simulates its own
+persistent engine kernel (ns_dev_run through the C ABI).  Both arms time the SAME absolute event range of
+the same script: events [W*E, (W+K)*E) after W warm-up windows of E events each.  With N>1 every rank simulates its own
 seeded replica of the swarm (weak scaling, no data-path collective: a single simulation is globally
 coupled); the per-replica digests are gathered with one NCCL all_gather.
 
 --impl reference times the UNMODIFIED reference core (oracle/_ref, compiled from /root/reference
-by oracle/Makefile) on the same script on one host core (the reference is single-threaded).
+by oracle/Makefile) on the same script and the same event range, one process per replica on
+min(N, host cores) cores (one simulation is single-threaded by design).
 """
 from __future__ import annotations
 
@@ -149,17 +151,57 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def config_for(args):
+    flows_k = args.peers * 10 // 1000
+    return {"workload": f"BASELINE.json configs[2]: p2p swarm script, {args.peers} peers + {args.hubs} hubs, ~{flows_k}k flows established at init, "
+                        f"records on; step = window of {args.events_per_step} events; timed range = events "
+                        f"[{args.warmup * args.events_per_step}, {(args.warmup + args.steps) * args.events_per_step}) of the script, the same for both arms. "
+                        f"hub_frac {args.hub_frac} of the sources are Zipf hubs (SURVEY §8d says 0.1: at 0.1 the top hub carries ~16k flows and the REFERENCE's "
+                        f"module init alone queues 1.8e8 events — each flow_create on a saturated hub re-notifies every earlier flow, flow.c:157-200 — "
+                        f"which does not fit the reference arm's few minutes; 0.02 keeps both arms runnable on the same script)",
+            "peers": args.peers, "hubs": args.hubs, "hub_frac": args.hub_frac, "events_per_step": args.events_per_step,
+            "working_set": "node/flow/range tables + pending-event ring (several GB) exceed the 126 MB L2; no explicit L2 flush"}
+
+
+def reference_arm(args, n_proc):
+    """n_proc independent reference processes side by side (one seeded replica each, like our ranks), every one
+    on its own core; value = all timed events / the slowest process's timed seconds"""
+    from concurrent.futures import ThreadPoolExecutor
+    scs = [workload(args, r).to_bytes() for r in range(n_proc)]
+    with ThreadPoolExecutor(max_workers=n_proc) as ex:
+        rs = list(ex.map(lambda sb: run_reference(args, sb, args.steps, args.warmup, args.events_per_step), scs))
+    if any(r is None for r in rs):
+        return None
+    bad = [r["error"] for r in rs if "error" in r]
+    if bad:
+        return {"error": bad[0]}
+    sec = max(r["seconds"] for r in rs)
+    ev = sum(r["events"] for r in rs)
+    return {"events": ev, "seconds": sec, "events_per_s": ev / sec, "steps": rs[0]["steps"], "init_seconds": max(r["init_seconds"] for r in rs),
+            "processes": n_proc}
+
+
+def expected_digest(args, rank, total_events):
+    """tests/golden/bench_expected.json: the CPU oracle's digest of this script after total_events events
+    (tools/make_bench_expected.py, computed where /root/reference pins the oracle)"""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_expected.json")))
+    except Exception:
+        return None
+    return tab.get(f"peers={args.peers},hubs={args.hubs},hub_frac={args.hub_frac},rank={rank},events={total_events}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="swarm100k", choices=list(WORKLOADS))
     ap.add_argument("--peers", type=int, default=100032)
     ap.add_argument("--hubs", type=int, default=320)
     ap.add_argument("--hub-frac", type=float, default=0.02)
-    ap.add_argument("--events-per-step", type=int, default=2000000)
-    ap.add_argument("--ref-events-per-step", type=int, default=150000)
+    ap.add_argument("--events-per-step", type=int, default=1000000)
     ap.add_argument("--ref-timeout", type=float, default=1500.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -167,29 +209,29 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": f"p2p swarm script: {args.peers} peers + {args.hubs} hubs, ~{args.peers * 10 // 1000}k flows established at init, "
-                          f"records on; step = window of events",
-              "peers": args.peers, "hubs": args.hubs, "hub_frac": args.hub_frac,
-              "working_set": "node/flow/range tables + pending-event ring (several GB) exceed the 126 MB L2; no explicit L2 flush"}
+    if args.workload != "swarm100k":
+        return WORKLOADS[args.workload](args, rank, local_rank, world)
+    config = config_for(args)
+    eps = args.events_per_step
+    total_steps = args.steps + args.warmup
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sc = workload(args, 0)
-        eps = args.ref_events_per_step
-        r = run_reference(args, sc.to_bytes(), args.steps, args.warmup, eps)
+        n_proc = max(1, min(args.gpus, os.cpu_count() or 1))
+        r = reference_arm(args, n_proc)
         if r is None or "error" in r:
             emit({"impl": "reference", "unavailable": (r or {}).get("error", "oracle/_ref not built")})
             return 0
         val = r["events_per_s"]
-        config["events_per_step"] = eps
         line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
                 "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
-                                 "sample": f"{r['steps']} windows of {eps} events after {args.warmup} warm-up windows of the same script; "
-                                           f"unmodified reference core, single-threaded by design; init {r['init_seconds']:.1f}s untimed"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_proc, "kind": "reference",
+                                 "sample": f"{n_proc} process(es) of the unmodified reference core (single-threaded by design), one seeded replica each "
+                                           f"like our ranks; each: {r['steps']} windows of {eps} events after {args.warmup} warm-up windows of the same "
+                                           f"script = the same absolute event range as our arm; init {r['init_seconds']:.1f}s untimed"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -206,13 +248,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc = workload(args, rank)
     sc_bytes = sc.to_bytes()
-    total_steps = args.steps + args.warmup
-    # the swarm's pending-event population grows by ~1.4 events per handled event in this phase of the
-    # simulation: keep the whole run inside the event ring (2^28 entries) whatever K and W are
-    eps = min(args.events_per_step, max(10000, 100_000_000 // max(1, total_steps)))
+    ring_cap = 1 << 28
+    # the pending-event population of this script grows by ~2.6 events per handled event in this phase: refuse a
+    # run that cannot stay inside the event ring instead of silently shrinking the windows
+    if total_steps * eps * 4 > ring_cap:
+        raise SystemExit(f"bench.py: {total_steps} windows of {eps} events do not fit the {ring_cap}-entry event ring; lower --steps or --events-per-step")
     t0 = time.time()
     rec_cap = int((total_steps * eps + 4 * sc.n_creates()) * 48 + (64 << 20))
-    eng = E.Engine(sc_bytes, device=local_rank, mode=E.MODE_AUTO, records=True, record_cap=rec_cap, ring_cap=1 << 28)
+    eng = E.Engine(sc_bytes, device=local_rank, mode=E.MODE_AUTO, records=True, record_cap=rec_cap, ring_cap=ring_cap)
     create_s = time.time() - t0
     c_init = eng.counters()
     import ctypes as C
@@ -243,7 +286,7 @@ def main():
         return dev_ms, time.perf_counter() - t_a, got
 
     sampler = ClockSampler(local_rank)
-    sampler.start()                      # the windows are tens of ms: sample from the warm-up on
+    sampler.start()                      # the windows are milliseconds long: sample from the warm-up on
     for i in range(args.warmup):
         step(i)
     c0 = eng.counters()
@@ -268,6 +311,16 @@ def main():
     dig = eng.digest()
     d = {k: c1[k] - c0[k] for k in c1}
     events = d["events"]
+    # parity inside the bench (outside the timed region): the digest of everything simulated so far against the CPU
+    # oracle's (committed for the default arguments; tools/make_bench_expected.py)
+    exp = expected_digest(args, rank, total_steps * eps)
+    parity = {"checked": exp is not None}
+    if exp is not None:
+        parity.update({"ok": bool(exp["record_hash"] == dig["record_hash"] and exp["record_bytes"] == dig["record_bytes"] and
+                                  exp["events"] == c1["events"] and exp["solves"] == c1["solves"] and exp["seq"] == c1["seq"]),
+                       "expected_record_hash": exp["record_hash"], "against": "CPU oracle (oracle/ns_oracle.c, pinned to the compiled reference)"})
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: PARITY FAILURE on rank {rank}: digest {dig} counters {c1} expected {exp}")
 
     # max over ranks of the timed quantities, sum of the work
     vals = torch.tensor([dev_ms_sum, wall_sum, t_region, float(events), float(d["solves"])], dtype=torch.float64, device="cuda")
@@ -306,10 +359,10 @@ def main():
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
-    config.update({"events_per_step": eps, "flows": c_init["creates"], "create_init_s": round(create_s, 2),
+    config.update({"flows": c_init["creates"], "create_init_s": round(create_s, 2),
                    "pending_events_at_end": c1["seq"] - c1["events"], "batches_timed": d["batches"], "max_batch": c1["max_batch"],
                    "parallel_fraction": d["par_events"] / max(1, events), "solves_per_s": solves_all / (dev_ms_max / 1e3),
-                   "full_spreads": d["full_spreads"], "flow_visits": d["flow_visits"], "record_hash": dig["record_hash"],
+                   "full_spreads": d["full_spreads"], "flow_visits": d["flow_visits"], "record_hash": dig["record_hash"], "parity": parity,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -323,17 +376,20 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_run_par (persistent, one launch per window)", "algorithmic_bytes_per_launch": alg_bytes / args.steps}}
     if not args.no_cpu_baseline and world == 1:
-        r = run_reference(args, sc_bytes, 2, 1, args.ref_events_per_step)
+        r = reference_arm(args, 1)       # the same windows as the reference arm (same absolute event range)
         if r and "error" not in r:
             line["cpu_baseline"] = {"value": r["events_per_s"], "unit": UNIT, "cores": 1, "kind": "reference",
-                                    "sample": f"unmodified reference core (oracle/_ref) on the same script: {r['steps']} windows of "
-                                              f"{args.ref_events_per_step} events after 1 warm-up window; init {r['init_seconds']:.1f}s untimed"}
+                                    "sample": f"unmodified reference core (oracle/_ref) on the same script, the same windows as --impl reference: "
+                                              f"{r['steps']} windows of {eps} events after {args.warmup} warm-up windows; init {r['init_seconds']:.1f}s untimed"}
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": (r or {}).get("error", "oracle/_ref missing")}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+WORKLOADS = {"swarm100k": None}
 
 
 if __name__ == "__main__":

@@ -50,6 +50,8 @@ enum ns_err {
 	NS_E_ARG = -10,
 	NS_E_BATCH_FULL = -11,
 	NS_E_INTERNAL = -12,     /* an engine invariant failed (a bug, not an input error) */
+	NS_E_RECORDS_LOST = -13, /* the record buffer overflowed INSIDE a batch and records were dropped (sticky, unlike the soft
+	                            NS_E_RECORDS_FULL): recreate with a larger record_cap */
 };
 
 enum ns_counter {
@@ -79,7 +81,11 @@ struct ns_dev_opts {
 	uint64_t record_cap;   /* bytes, 0 = auto */
 	uint64_t trace_cap;    /* rows, 0 = auto */
 	int cap_flows;         /* concurrent flows, 0 = auto (number of CREATE ops) */
-	int reserved[5];
+	int features_off;      /* bit mask of engine paths to switch OFF (A/B measurements), 0 = everything on */
+	int cap_ord;           /* flows ever created (creation ordinals), 0 = auto (2x the script's CREATE ops, >= 2x cap_flows) */
+	int cap_ranges;        /* ranges, 0 = auto */
+	int cap_users;         /* pending USER events, 0 = auto (2x the script's SCHED ops) */
+	int reserved[1];
 };
 
 struct ns_trace_row32 { uint32_t type, ord; double time, v0, v1; };

@@ -171,6 +171,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	ns_sc_header H;
 	memcpy(&H, scenario, sizeof H);
 	if (H.magic != NS_SC_MAGIC || H.version != NS_SC_VERSION || H.n_groups < 1 || H.n_nodes < 0) return NS_E_BAD_SCENARIO;
+	if (H.n_resources < 0 || H.n_copies < 0 || H.n_ops < 0 || H.n_ondone < 0) return NS_E_BAD_SCENARIO;
 	size_t need = sizeof H+(size_t)H.n_nodes*16+(size_t)H.n_resources*sizeof(ns_sc_resource)+(size_t)H.n_copies*sizeof(ns_sc_copy)+
 		(size_t)(H.n_groups+1)*4+(size_t)H.n_ops*sizeof(ns_sc_op)+(size_t)H.n_ondone*sizeof(ns_sc_ondone);
 	if (len < need) return NS_E_BAD_SCENARIO;
@@ -182,8 +183,14 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	const int32_t *goff = (const int32_t *)p; p += (size_t)(H.n_groups+1)*4;
 	const ns_sc_op *ops = (const ns_sc_op *)p; p += (size_t)H.n_ops*sizeof *ops;
 	const ns_sc_ondone *od = (const ns_sc_ondone *)p;
+	// group g = ops[goff[g] .. goff[g+1]): offsets must be monotone and inside the op table
+	if (goff[0] < 0 || goff[H.n_groups] > H.n_ops) return NS_E_BAD_SCENARIO;
+	for (int g = 0; g < H.n_groups; g++) if (goff[g] > goff[g+1]) return NS_E_BAD_SCENARIO;
+	// the on-done table is binary-searched on the device: sorted, unique
+	for (int i = 1; i < H.n_ondone; i++) if (od[i-1].flow_ord >= od[i].flow_ord) return NS_E_BAD_SCENARIO;
 	int n_create = 0, n_sched = 0;
 	for (int i = 0; i < H.n_ops; i++) {
+		if (ops[i].kind == NS_OP_CLOSE && ops[i].a < 0) return NS_E_BAD_SCENARIO;
 		if (ops[i].kind == NS_OP_CREATE) {
 			n_create++;
 			if (ops[i].a < 0 || ops[i].a >= H.n_nodes || ops[i].b < 0 || ops[i].b >= H.n_nodes || ops[i].c < 0 || ops[i].c >= H.n_resources) return NS_E_BAD_SCENARIO;
@@ -201,10 +208,13 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	S.n_nodes = N;
 	S.cap_flows = o.cap_flows > 0 ? o.cap_flows : std::max(16, n_create);
 	const int F = S.cap_flows;
-	S.cap_ranges = 2*n_create+H.n_resources+H.n_copies+16;
-	S.cap_res = H.n_resources+H.n_copies+n_create+16;
-	S.cap_users = 2*n_sched+16;
-	S.cap_ord = 2*n_create+16;
+	// a caller that creates flows beyond the script (the host core: the module IS the script) sizes the tables
+	// through cap_flows / cap_ord / cap_ranges / cap_users; the static op counts are only the default
+	const int base = std::max(n_create, F);
+	S.cap_ord = o.cap_ord > 0 ? o.cap_ord : 2*base+16;
+	S.cap_ranges = o.cap_ranges > 0 ? o.cap_ranges : 2*base+H.n_resources+H.n_copies+16;
+	S.cap_res = H.n_resources+H.n_copies+std::max(base, S.cap_ord)+16;
+	S.cap_users = o.cap_users > 0 ? o.cap_users : 2*n_sched+16;
 	S.n_groups = H.n_groups; S.n_ops = H.n_ops; S.n_ondone = H.n_ondone; S.n_rids = H.n_resources;
 	S.ring_cap = o.ring_cap ? next_pow2(std::max<u64>(o.ring_cap, NS_TILE)) : next_pow2(std::min<u64>(std::max<u64>(1u << 16, 128ull*F), 1ull << 28));
 	S.n_ring_tiles = (int)(S.ring_cap >> NS_TILE_SHIFT);
@@ -214,7 +224,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	S.batch_cap = (int)std::min<u64>(S.ring_cap/2, 1ull << 30);
 	S.want_rec = o.want_records; S.want_tr = o.want_trace;
 	{	// engine paths that can be switched off for A/B runs: ns_dev_opts.reserved[0] or NS_FEATURES_OFF (bit mask)
-		unsigned off = (unsigned)o.reserved[0];
+		unsigned off = (unsigned)o.features_off;
 		const char *env = getenv("NS_FEATURES_OFF");
 		if (env) off |= (unsigned)strtoul(env, nullptr, 0);
 		S.features = (int)(NS_FEAT_ALL & ~off);
@@ -255,6 +265,16 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		n_init = goff[1]-goff[0];
 		for (int i = goff[0]; i < goff[1]; i++) if (ops[i].kind != NS_OP_CREATE) { n_init = 0; break; }
 		if (goff[0] != 0) n_init = 0;
+		// the wave schedule assumes sim_establish_flow touches only its two end nodes; a RELAY create (its source is
+		// still being filled by an earlier flow of the init) also re-times that producer (sim.c:86-91, range.c:16-79
+		// reads the producer's speed and done time): such inits run on the sequential warp
+		if (n_init) {
+			std::unordered_set<u64> filling;
+			for (int i = goff[0]; i < goff[1] && n_init; i++) {
+				if (filling.count(((u64)(uint32_t)ops[i].a << 32) | (uint32_t)ops[i].c)) n_init = 0;
+				filling.insert(((u64)(uint32_t)ops[i].b << 32) | (uint32_t)ops[i].c);
+			}
+		}
 	}
 	if ((rc = par_alloc(h.par, S, parallel_scratch, n_init, [&](void **pp, size_t b){ return dev_alloc(h, pp, b); }))) return rc;
 	if (n_init && (rc = par_plan_init(h.par, ops, n_init, N))) return rc;
@@ -303,7 +323,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		add_full(cp[i].node, rid, rs[cp[i].res].len);
 	}
 	const int nres0 = (int)s_id.size(), nrng0 = (int)r_start.size();
-	if (rec.size() > S.rec_cap && o.want_records) return NS_E_RECORDS_FULL;
+	if (rec.size() > S.rec_cap && o.want_records) return NS_E_RECORDS_LOST;
 
 	// ---- fill and upload
 	for (int d = 0; d < 2; d++) { if ((rc = fill_f64(S.n_usage[d], N, 0))) return rc; if ((rc = fill_f64(S.n_total[d], N, 0))) return rc; }
@@ -606,6 +626,12 @@ extern "C" int ns_dev_run_host(ns_dev *d, ns_host_event *ev){
 extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 	if (!d || !ops || n < 0 || n > d->h.S.host_ops_cap) return NS_E_ARG;
 	if (n == 0) return 0;
+	for (int i = 0; i < n; i++) {                                        // the device indexes its tables with these
+		const ns_sc_op &op = ops[i];
+		if (op.kind == NS_OP_CREATE) { if (op.a < 0 || op.a >= d->h.S.n_nodes || op.b < 0 || op.b >= d->h.S.n_nodes || op.c < 0 || op.c >= d->h.S.n_rids) return NS_E_ARG; }
+		else if (op.kind == NS_OP_CLOSE) { if (op.a < 0) return NS_E_ARG; }
+		else if (op.kind != NS_OP_SCHED && op.kind != NS_OP_END) return NS_E_ARG;
+	}
 	CK(cudaSetDevice(d->device));
 	CK(cudaMemcpyAsync(d->h.S.host_ops, ops, (size_t)n*sizeof *ops, cudaMemcpyHostToDevice, d->stream));
 	{ int rc = seq_launch_exec_ops(d->d_sim, n, d->stream); if (rc) return rc; }
@@ -795,6 +821,7 @@ extern "C" const char *ns_strerror(int err){
 	case NS_E_ARG: return "bad argument";
 	case NS_E_BATCH_FULL: return "equal-timestamp batch exceeds scratch capacity";
 	case NS_E_INTERNAL: return "engine invariant failed";
+	case NS_E_RECORDS_LOST: return "record buffer overflowed inside a batch: records were dropped";
 	default: return err > 0 ? "CUDA error" : "unknown error";
 	}
 }

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_init_par(const 
 	const u64 tail0 = st->tail, rec0 = st->rec_len;
 	bool okc = true;
 	if (tail0+t_ins-st->head > S.ring_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RING_FULL); }
-	if (S.want_rec && rec0+t_rec > S.rec_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RECORDS_FULL); }
+	if (S.want_rec && rec0+t_rec > S.rec_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RECORDS_LOST); }
 	if (okc) {
 		// ---- flow ids: this chunk's slice of the random() stream, walked in op order -----------
 		if (tid == 0) {

@@ -89,7 +89,7 @@ __device__ __forceinline__ void write_record(Ctx &c, uint8_t minor, uint32_t id,
 		c.rec_n += n;
 		return;
 	}
-	if (c.rec_len+n > S.rec_cap) { set_status(c, NS_E_RECORDS_FULL); return; }
+	if (c.rec_len+n > S.rec_cap) { set_status(c, NS_E_RECORDS_LOST); return; }   // a record was DROPPED: hard error, unlike the soft stop before a batch
 	L0 {
 		uint8_t b[19];
 		rec_encode(b, c.now, minor, id, bytes, ival, dval);
@@ -310,7 +310,7 @@ __device__ __forceinline__ void range_calc_and_requeue_events(Ctx &c, int f){
 	int n = p.add_drain+p.add_done;
 	if (n) {
 		u64 seq = seq_reserve(c, n);
-		L0 { if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) retime_commit_1(c, f, p, seq); }
+		L0 { if (c.st->status == 0 || c.st->status == NS_E_RECORDS_LOST) retime_commit_1(c, f, p, seq); }
 	}
 	WSYNC();
 }
@@ -464,7 +464,7 @@ __device__ void bwspread(Ctx &c, int f, double amount, int dir, int close){
 			int tot = __shfl_sync(FULLMASK, incl, 31);
 			if (tot) {
 				u64 seq0 = seq_reserve(c, tot);
-				if (c.st->status == 0 || c.st->status == NS_E_RECORDS_FULL) {
+				if (c.st->status == 0 || c.st->status == NS_E_RECORDS_LOST) {
 					u64 seq = seq0+(u64)(incl-k);
 					if (okv[u]) { ring_put(c, seq, etv[u], emitv[u], nfv[u], !dir); seq++; }
 					if (adjv[u]) retime_commit_1(c, nfv[u], rpv[u], seq);
@@ -740,7 +740,7 @@ __device__ __noinline__ int sim_establish_flow(Ctx &c, uint32_t rid, long long s
 	if (range_get(S, dr, (int)start) >= 0) return -1;                 // :62-67
 	int rng = range_get(S, sr, (int)start);                           // :69
 	int f = flow_create(c, src, dst, ub, delay);                      // :70
-	if (f < 0 || (c.st->status && c.st->status != NS_E_RECORDS_FULL)) return f;
+	if (f < 0 || (c.st->status && c.st->status != NS_E_RECORDS_LOST)) return f;
 	int dg = resource_new_range(c, dr, start, 0, c.now);              // :74-76
 	if (dg < 0) return f;
 	L0 { S.f_drng[f] = dg; S.r_prod[dg] = f; S.f_srng[f] = rng; }     // :75-77

@@ -29,7 +29,7 @@ __device__ __noinline__ void par_finish_piece(const Sim &S, SimState *st, ParScr
 	st->cnt[NS_CNT_SEQ] = st->tail;
 	for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
 	ctl->pos = ctl->seg_hi;
-	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0;
+	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0; ctl->n_long = 0;
 	ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 	*P.stage.ovf_top = 0;
 }
@@ -45,7 +45,9 @@ __device__ __noinline__ void par_plan_piece(const Sim &S, SimState *st, ParScrat
 		u64 reserve = S.rec_cap > 8ull*NS_REC_RESERVE ? NS_REC_RESERVE : S.rec_cap/8;
 		u64 left = (u64)(nb-pos)+(u64)(nl-li);
 		u64 next = left < (u64)P.seg_cap ? left : (u64)P.seg_cap;
-		if (st->rec_len+next*NS_REC_PER_EVENT+reserve > S.rec_cap) { st->host_stop = 2; return; }
+		u64 ops = 0;                                                  // scripted creates / closes the long-lived events of the batch will run
+		for (int k = li; k < nl; k++) ops += (u64)l_entry_ops(S, sc.lb_ref[k]);
+		if (st->rec_len+next*NS_REC_PER_EVENT+ops*NS_REC_PER_OP+reserve > S.rec_cap) { st->host_stop = 2; return; }
 	}
 	const bool no_par = st->relay_seen || budget < PAR_MIN_BATCH;
 	const u64 ls = li < nl ? sc.lb_seq[li] : ~0ull;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 	const bool leader = blockIdx.x == 0 && tid == 0;
 	extern __shared__ __align__(16) unsigned char dyn_smem[];
 	HubSmem &Hs = *reinterpret_cast<HubSmem *>(dyn_smem);
+	RadSmem &Rs = *reinterpret_cast<RadSmem *>(dyn_smem);       // the partition phase and the hub phase never overlap
 	const bool hub_on = (S.features & NS_FEAT_HUBCTA) != 0;
 #ifdef NS_PROFILE
 	u64 t_ph = gtimer();
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			// sparse phase: many small batches in a row and event stores one warp can scan -> hand over to k_run_seq
 			ctl->small_streak = nb+nl < PAR_MIN_BATCH ? ctl->small_streak+1 : 0;
 			if (ctl->small_streak >= SPARSE_STREAK && n_wt+(u64)S.n_l_tiles <= SPARSE_MAX_TILES) { st->want_sparse = 1; ctl->small_streak = 0; }
-			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0;
+			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0; ctl->n_long = 0;
 			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 			*P.stage.ovf_top = 0;
 		}
@@ -227,37 +230,44 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			}
 			const int seg_lo = ctl->seg_lo, seg_hi = ctl->seg_hi;
 			const int ns = seg_hi-seg_lo;
-			// ---- D1: group of every event; cancelled events drop out ---------------------------
+			// ---- D1: key of every event = the (node,dir) group it rewrites; cancelled events get the sentinel ----
+			const int NG = 2*S.n_nodes;
 			for (u64 e = gtid; e < (u64)ns; e += gth) {
 				u64 s = S.b_seq[seg_lo+e];
 				u64 slot = s & smask;
 				int fd = S.q_fd[slot];
 				int f = fd >> 1, dir = fd & 1;
-				int g = -1;
-				if (S.f_gen[f] == S.q_gen[slot] && S.f_alive[f]) {
-					g = S.f_peer[dir][f]*2+dir;
-					if (atomicAdd(&P.grp_cnt[g], 1) == 0) P.active[atomicAdd(&ctl->n_active, 1)] = g;
-				} else {
+				int g = NG;
+				if (S.f_gen[f] == S.q_gen[slot] && S.f_alive[f]) g = S.f_peer[dir][f]*2+dir;
+				else {
 					S.q_time[slot] = NS_INF;                          // flow_close cancelled it (flow.c:260-270)
 					P.stage.ev_nins[e] = 0; P.stage.ev_nrec[e] = 0; P.stage.ev_ntr[e] = 0; P.stage.ev_ovf[e] = -1;
 				}
 				P.b_grp[e] = g;
 			}
 			grid.sync();
+			// ---- D2: STABLE partition of the segment by group (LSD radix, RAD_BITS per pass): afterwards the events
+			//      of a group are contiguous in grp_items AND in batch order, so no chain ever needs sorting
+			{
+				int kb = 1; while ((NG >> kb) != 0) kb++;
+				const int np = (kb+RAD_BITS-1)/RAD_BITS;
+				const int *sk = P.b_grp, *sv = nullptr;
+				for (int i = 0; i < np; i++) {
+					const bool fin = ((np-1-i) & 1) == 0;
+					int *dk = fin ? P.srt_key : P.srt_key2, *dv = fin ? P.grp_items : P.srt_val2;
+					radix_pass(grid, Rs, sk, sv, dk, dv, ns, i*RAD_BITS, P.rad_hist);
+					sk = dk; sv = dv;
+				}
+			}
+			// ---- D3: group boundaries ------------------------------------------------------------------
+			for (u64 i = gtid; i < (u64)ns; i += gth) {
+				const int k = P.srt_key[i];
+				if (k >= NG) continue;
+				if (i == 0 || P.srt_key[i-1] != k) { P.grp_off[k] = (int)i; P.active[atomicAdd(&ctl->n_active, 1)] = k; }
+				if (i+1 == (u64)ns || P.srt_key[i+1] != k) P.grp_fill[k] = (int)i+1;
+			}
+			grid.sync();
 			const int n_active = ctl->n_active;
-			// ---- D2: slice of grp_items per active group ---------------------------------------
-			for (u64 k = gtid; k < (u64)n_active; k += gth) {
-				int g = P.active[k];
-				P.grp_off[g] = atomicAdd(&ctl->cursor, P.grp_cnt[g]);
-				P.grp_fill[g] = 0;
-			}
-			grid.sync();
-			// ---- D3: fill -------------------------------------------------------------------------
-			for (u64 e = gtid; e < (u64)ns; e += gth) {
-				int g = P.b_grp[e];
-				if (g >= 0) P.grp_items[P.grp_off[g]+atomicAdd(&P.grp_fill[g], 1)] = (int)e;
-			}
-			grid.sync();
 			PHASE_MARK(PH_GROUP);
 			// ---- E1: one THREAD per group: O(1) solves (no full spread), events in sequence order ----
 			{
@@ -268,16 +278,11 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				for (int q = 0; q < LC_N; q++) c.lc[q] = 0;
 				for (u64 k = gtid; k < (u64)n_active; k += gth) {
 					int g = P.active[k];
-					int cnt = P.grp_cnt[g], off = P.grp_off[g];
+					const int off = P.grp_off[g], cnt = P.grp_fill[g]-off;
+					P.grp_cnt[g] = cnt;
 					int j = 0;
-					if (cnt > 32) j = -1;                             // long chains: sorted and run by a warp
-					else {
-						int *it = P.grp_items+off;
-						for (int a = 1; a < cnt; a++) {               // insertion sort by batch position
-							int x = it[a], b = a-1;
-							while (b >= 0 && it[b] > x) { it[b+1] = it[b]; b--; }
-							it[b+1] = x;
-						}
+					if (cnt <= 32) {                                  // long chains go straight to a warp / a CTA
+						const int *it = P.grp_items+off;
 						for (; j < cnt; j++) {
 							int e = it[j];
 							u64 slot = S.b_seq[seg_lo+e] & smask;
@@ -288,8 +293,10 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 					}
 					if (j < cnt) {
 						P.defer_pos[g] = j;
-						// a large sender group goes to a whole CTA (hub_chain_cta), everything else to one warp
+						// a large sender group goes to a whole CTA (hub_chain_cta), everything else to one warp — the long
+						// chains first, since the segment ends with its slowest group
 						if (hub_on && (g & 1) == SND && S.adj_live[g] >= HUB_MIN_DEG && S.adj_len[g] <= HUB_CAP) P.deferred[P.seg_cap-1-atomicAdd(&ctl->n_hub, 1)] = g;
+						else if (cnt-j > 128) P.defer_long[atomicAdd(&ctl->n_long, 1)] = g;
 						else P.deferred[atomicAdd(&ctl->n_deferred, 1)] = g;
 					}
 					else P.grp_cnt[g] = 0;                            // ready for the next segment
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			}
 			// ---- E2: one WARP per remaining group: full spreads strided over the lanes ----------------
 			{
-				const int n_def = ctl->n_deferred;
+				const int n_lg = ctl->n_long, n_def = n_lg+ctl->n_deferred;
 				Ctx c;
 				c.S = sp; c.st = st; c.lane = lane; c.par = 1; c.scalar = 0; c.ps = P.d_stage; c.now = m;
 				c.head = head; c.tail = 0; c.burns = 0; c.rec_len = 0; c.tr_len = 0;
@@ -327,7 +334,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 					if (lane == 0) k = atomicAdd(&ctl->work, 1);
 					k = __shfl_sync(FULLMASK, k, 0);
 					if (k >= n_def) break;
-					int g = P.deferred[k];
+					int g = k < n_lg ? P.defer_long[k] : P.deferred[k-n_lg];
 					int cnt = P.grp_cnt[g], off = P.grp_off[g];
 					int j = P.defer_pos[g];
 #ifdef NS_PROFILE
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				__syncthreads();
 				bool okc = sh_status == 0;            // block-uniform: the CAS below only fires when okc is false anyway
 				if (tail0+t_ins-st->head > S.ring_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RING_FULL); }
-				if (S.want_rec && rec0+t_rec > S.rec_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RECORDS_FULL); }
+				if (S.want_rec && rec0+t_rec > S.rec_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RECORDS_LOST); }
 				if (leader) { ctl->tot_ins = t_ins; ctl->tot_rec = t_rec; ctl->tot_tr = t_tr; }
 				if (okc) {
 					// block-wide running scan over the chunk, PAR_THREADS events at a time

@@ -27,6 +27,8 @@ struct ParScratch {
 	// grouping
 	int *grp_cnt, *grp_off, *grp_fill, *active, *grp_items, *b_grp;
 	int *deferred, *defer_pos;     // groups handed from the per-thread pass to the per-warp pass
+	int *defer_long;               // ... the ones with long chains (taken first)
+	int *srt_key, *srt_key2, *srt_val2, *rad_hist;   // stable partition of a segment by group (radix_pass)
 	// parallel module init: CREATE ops of group 0 scheduled into conflict-free waves (host, par_plan_init)
 	int n_init, n_waves; int *wave_off, *wave_ops; u64 *cta_draws;
 	// scan
@@ -35,6 +37,7 @@ struct ParScratch {
 	struct Ctl {
 		u64 tmin_bits, first_live;
 		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
+		int n_long;                                // chains of more than 128 events: taken first by the warp pass (defer_long)
 		int n_hub, hub_work;                       // groups handed to whole CTAs (hub_chain_cta); stored from the END of `deferred`
 		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
 		int small_streak;                          // consecutive small batches (sparse phase detection)
@@ -63,7 +66,8 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
 	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
 	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
-	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1);
+	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1); PA(p.defer_long, p.seg_cap/128+2);
+	PA(p.srt_key, p.seg_cap); PA(p.srt_key2, p.seg_cap); PA(p.srt_val2, p.seg_cap); PA(p.rad_hist, 512*4096);
 	PA(p.cta_ins, 4096); PA(p.cta_rec, 4096); PA(p.cta_tr, 4096); PA(p.cta_draws, 4096);
 	if (n_init) { PA(p.wave_off, n_init+2); PA(p.wave_ops, n_init); }
 	PA(p.ctl, 1);

@@ -167,6 +167,70 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 	__syncwarp();
 }
 
+// ---------------------------------------------------------------- stable partition of a segment by group
+// One LSD radix pass over ns (key, value) pairs by the whole grid: every CTA owns a contiguous chunk of the
+// current order, counts its digits, all CTAs derive their per-digit bases from the (digit, CTA) table, and the
+// chunk is scattered tile by tile in order (rank inside a warp by match_any, warps in order through shared
+// memory).  Stable, deterministic, no sorting by anyone afterwards.  The first pass takes value = position.
+#define RAD_BITS 9
+#define RAD_BINS (1 << RAD_BITS)
+struct RadSmem { int hist[RAD_BINS], base[RAD_BINS], wcnt[PAR_WARPS][RAD_BINS], scan_tmp[PAR_WARPS]; };
+static_assert(RAD_BINS == 2*PAR_THREADS, "the bin scan gives every thread two bins");
+__device__ __noinline__ void radix_pass(cgp::grid_group &grid, RadSmem &R, const int *src_key, const int *src_val, int *dst_key, int *dst_val,
+		int ns, int shift, int *ghist){
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int G = gridDim.x, b = blockIdx.x;
+	const int per = (ns+G-1)/G;
+	const int c_lo = b*per < ns ? b*per : ns, c_hi = c_lo+per < ns ? c_lo+per : ns;
+	for (int i = tid; i < RAD_BINS; i += PAR_THREADS) R.hist[i] = 0;
+	for (int i = tid; i < PAR_WARPS*RAD_BINS; i += PAR_THREADS) (&R.wcnt[0][0])[i] = 0;
+	__syncthreads();
+	for (int i = c_lo+tid; i < c_hi; i += PAR_THREADS) atomicAdd(&R.hist[(src_key[i] >> shift) & (RAD_BINS-1)], 1);
+	__syncthreads();
+	for (int i = tid; i < RAD_BINS; i += PAR_THREADS) ghist[i*G+b] = R.hist[i];
+	grid.sync();
+	for (int bin = tid; bin < RAD_BINS; bin += PAR_THREADS) {
+		int tot = 0, before = 0;
+		const int *row = ghist+bin*G;
+		for (int q = 0; q < G; q++) { int v = row[q]; if (q < b) before += v; tot += v; }
+		R.hist[bin] = tot; R.base[bin] = before;
+	}
+	__syncthreads();
+	{	// exclusive scan of the digit totals
+		const int a0 = R.hist[2*tid], a1 = R.hist[2*tid+1];
+		const int s = a0+a1;
+		int incl = s;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+		if (lane == 31) R.scan_tmp[warp] = incl;
+		__syncthreads();
+		int ex = incl-s;
+		for (int w = 0; w < warp; w++) ex += R.scan_tmp[w];
+		R.base[2*tid] += ex; R.base[2*tid+1] += ex+a0;
+	}
+	__syncthreads();
+	for (int t0 = c_lo; t0 < c_hi; t0 += PAR_THREADS) {
+		const int i = t0+tid;
+		const bool valid = i < c_hi;
+		const int k = valid ? src_key[i] : 0, v = valid ? (src_val ? src_val[i] : i) : 0;
+		const int d = valid ? ((k >> shift) & (RAD_BINS-1)) : RAD_BINS+lane;
+		const unsigned peers = __match_any_sync(FULLMASK, d);
+		const int rank = __popc(peers & ((1u << lane)-1));
+		const bool leader = valid && rank == 0;
+		if (leader) R.wcnt[warp][d] = __popc(peers);
+		__syncthreads();
+		if (valid) {
+			int o = R.base[d];
+			for (int w = 0; w < warp; w++) o += R.wcnt[w][d];
+			dst_key[o+rank] = k; dst_val[o+rank] = v;
+		}
+		__syncthreads();
+		if (leader) { atomicAdd(&R.base[d], __popc(peers)); R.wcnt[warp][d] = 0; }
+		__syncthreads();
+	}
+	grid.sync();
+}
+
 // ---------------------------------------------------------------- chains, second form
 // The same chain split the way its data dependences run.  Inside one (node,dir) group at one `now`
 // the only loop-carried state of the O(1) solves (flow.c:64-124) is the speed of each flow and the

@@ -204,12 +204,26 @@ __device__ bool seq_handle_ring(Ctx &c, double m, u64 seq){
 // records are appended by the handlers; a batch is only started when its worst case fits (two records
 // per SPEED_CHANGE, plus a reserve for the creates/closes of USER groups and FLOW_DONE handlers)
 #define NS_REC_PER_EVENT 64
+#define NS_REC_PER_OP 192          // one scripted create / close: its own records plus the usage records of its solves
 #define NS_REC_RESERVE (1u << 20)
-__device__ __forceinline__ bool rec_room_short(const Ctx &c, u64 n_events){
+// script operations an L-table event will run (a USER event's group, the on-done group of a FLOW_DONE)
+__device__ __forceinline__ int l_entry_ops(const Sim &S, int slot){
+	if (slot >= 2*S.cap_flows) { int g = S.u_group[slot-2*S.cap_flows]; return g >= 0 ? S.group_off[g+1]-S.group_off[g] : 0; }
+	if ((slot & 1) || !S.n_ondone) return 0;
+	const int ord = S.f_ord[slot >> 1];
+	int lo = 0, hi = S.n_ondone-1;
+	while (lo <= hi) {
+		int mid = (lo+hi)/2, fo = S.ondone[mid].flow_ord;
+		if (fo == ord) { int g = S.ondone[mid].group; return S.group_off[g+1]-S.group_off[g]; }
+		if (fo < ord) lo = mid+1; else hi = mid-1;
+	}
+	return 0;
+}
+__device__ __forceinline__ bool rec_room_short(const Ctx &c, u64 n_events, u64 n_ops){
 	const Sim &S = *c.S;
 	if (!S.want_rec) return false;
 	u64 reserve = S.rec_cap > 8ull*NS_REC_RESERVE ? NS_REC_RESERVE : S.rec_cap/8;
-	return c.rec_len+n_events*NS_REC_PER_EVENT+reserve > S.rec_cap;
+	return c.rec_len+n_events*NS_REC_PER_EVENT+n_ops*NS_REC_PER_OP+reserve > S.rec_cap;
 }
 __device__ __forceinline__ bool seq_should_stop(Ctx &c){
 	SimState *st = c.st;
@@ -276,7 +290,10 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 		if (nr < 0) { set_status(c, NS_E_BATCH_FULL); __syncwarp(); break; }
 		int nl = seq_collect_l(c, m, sc);
 		if (nr+nl == 0) continue;                                     // only stale lower bounds surfaced
-		if (rec_room_short(c, nr+nl)) {                               // soft stop BEFORE the batch: nothing is lost
+		u64 n_ops = 0;
+		for (int k = lane; k < nl; k += 32) n_ops += (u64)l_entry_ops(*c.S, sc.lb_ref[k]);
+		for (int d = 16; d; d >>= 1) n_ops += __shfl_xor_sync(FULLMASK, n_ops, d);
+		if (rec_room_short(c, nr+nl, n_ops)) {                        // soft stop BEFORE the batch: nothing is lost
 			seq_restore(c, m, 0, nr, 0, nl, sc);
 			L0 c.st->host_stop = 2;
 			__syncwarp();

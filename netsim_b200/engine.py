@@ -28,7 +28,8 @@ class NsError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int), ("mode", C.c_int), ("want_records", C.c_int), ("want_trace", C.c_int),
                 ("ring_cap", C.c_uint64), ("record_cap", C.c_uint64), ("trace_cap", C.c_uint64),
-                ("cap_flows", C.c_int), ("reserved", C.c_int * 5)]
+                ("cap_flows", C.c_int), ("features_off", C.c_int), ("cap_ord", C.c_int), ("cap_ranges", C.c_int),
+                ("cap_users", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class Digest(C.Structure):
@@ -155,6 +156,7 @@ class Engine:
         """run to the end (or max_events) with a bounded record buffer: every NS_E_RECORDS_FULL stop is
         answered by copying the records out and ns_dev_records_drain; returns the whole stream"""
         out, off = [], 0
+        last = None
         while True:
             rc = self.run(max_events)
             chunk = self.records(off)
@@ -164,6 +166,11 @@ class Engine:
                 if rc != 0:
                     raise NsError(rc, "ns_dev_run")
                 return b"".join(out)
+            # a soft stop must have made progress since the previous one, or record_cap can never hold one batch
+            progress = (self.counters()["events"], off)
+            if progress == last:
+                raise NsError(-13, "run_draining: no progress between two record-buffer stops (record_cap too small for one batch)")
+            last = progress
             rc2 = self.L.ns_dev_records_drain(self.h)
             if rc2:
                 raise NsError(rc2, "ns_dev_records_drain")

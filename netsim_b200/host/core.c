@@ -48,6 +48,8 @@ struct ns_host_core {
 	struct event **uev; int n_uev, cap_uev;                /* module-owned USER events by token */
 	struct handler *handlers[LAST_EVENT];
 	char *record_path; int want_records;
+	uint8_t *rec; size_t rec_len, rec_cap;                 /* record stream pulled from the device so far (+ module records) */
+	size_t dev_off;                                        /* device stream offset already pulled */
 	struct sim_state *s;
 	int device, mode;
 };
@@ -164,8 +166,15 @@ static int materialize(struct ns_host_core *c){
 	/* group_off = {0, 0}: the module itself is the script */
 	struct ns_dev_opts o;
 	memset(&o, 0, sizeof o);
-	o.device = c->device; o.mode = NS_MODE_SEQ; o.want_records = c->want_records; o.cap_flows = 4096;
-	o.ring_cap = 1u << 20; o.record_cap = 64u << 20;
+	/* the module is the script: nothing is known about how many flows it will establish, so the tables are
+	 * sized by the environment (defaults fit a p2p.c run of a few thousand clients) */
+	const char *ev;
+	o.device = c->device; o.mode = NS_MODE_SEQ; o.want_records = c->want_records;
+	o.cap_flows = (ev = getenv("NS_CAP_FLOWS")) ? atoi(ev) : 1 << 17;      /* concurrent flows */
+	o.cap_ord = (ev = getenv("NS_CAP_ORD")) ? atoi(ev) : 1 << 21;          /* flows ever created */
+	o.cap_ranges = 2*o.cap_flows+c->n_rsrc+c->n_copies+16;
+	o.cap_users = (ev = getenv("NS_CAP_USERS")) ? atoi(ev) : 1 << 17;      /* pending module-owned events */
+	o.ring_cap = 1u << 22; o.record_cap = 64u << 20;
 	int rc = ns_dev_create(&c->dev, buf, len, &o);
 	free(buf);
 	if (rc) { log_err("device core: %s\n", ns_strerror(rc)); exit(3); }
@@ -200,8 +209,14 @@ static void refresh_nodes(struct ns_host_core *c){
 void ns_host_refresh_ranges(struct resource *r){
 	struct ns_host_core *c = the_core;
 	if (!c || !c->dev) return;
-	struct ns_range_info ri[64]; int n = 0;
-	if (ns_dev_node_ranges(c->dev, r->owner->index, r->resource_id, ri, 64, &n)) return;
+	int cap = 64, n = 0;
+	struct ns_range_info *ri = malloc((size_t)cap*sizeof *ri);
+	for (;;) {                                              /* as many ranges as the resource has */
+		if (ns_dev_node_ranges(c->dev, r->owner->index, r->resource_id, ri, cap, &n)) { free(ri); return; }
+		if (n < cap) break;
+		cap *= 2;
+		ri = realloc(ri, (size_t)cap*sizeof *ri);
+	}
 	for (struct range *g = r->first, *nx; g; g = nx) { nx = g->next; free(g); }
 	r->first = NULL;
 	struct range **pp = &r->first;
@@ -212,6 +227,7 @@ void ns_host_refresh_ranges(struct resource *r){
 		g->producer = (ri[i].producer_ord >= 0 && ri[i].producer_ord < c->n_flows) ? c->flows[ri[i].producer_ord] : NULL;
 		*pp = g; pp = &g->next;
 	}
+	free(ri);
 }
 
 /* sim_establish_flow, sim.c:42-94 */
@@ -310,12 +326,30 @@ void open_record(const char *filename, int create, struct sim_state *s){
 	c->want_records = 1;
 }
 
+/* append what the device has produced since the last pull to the host copy of the record stream */
+static void rec_reserve(struct ns_host_core *c, size_t more){
+	if (c->rec_len+more <= c->rec_cap) return;
+	while (c->rec_len+more > c->rec_cap) c->rec_cap = c->rec_cap ? c->rec_cap*2 : 1 << 20;
+	c->rec = realloc(c->rec, c->rec_cap);
+}
+static void pull_records(struct ns_host_core *c){
+	if (!c->want_records || !c->dev) return;
+	for (;;) {
+		size_t got = 0, total = 0;
+		ns_dev_records(c->dev, NULL, 0, c->dev_off, &got, &total);
+		if (total <= c->dev_off) return;
+		rec_reserve(c, total-c->dev_off);
+		ns_dev_records(c->dev, c->rec+c->rec_len, total-c->dev_off, c->dev_off, &got, &total);
+		if (!got) return;
+		c->rec_len += got; c->dev_off += got;
+	}
+}
 static void save_records(struct ns_host_core *c){
 	if (!c->record_path || !c->dev) return;
-	size_t got = 0, total = 0;
-	ns_dev_records(c->dev, NULL, 0, 0, &got, &total);
+	pull_records(c);
+	size_t total = c->rec_len;
 	uint8_t *buf = malloc(total+4);
-	ns_dev_records(c->dev, buf+4, total, 0, &got, &total);
+	memcpy(buf+4, c->rec, total);
 	buf[0] = total >> 24; buf[1] = total >> 16; buf[2] = total >> 8; buf[3] = total;   /* record.c:111-115 */
 	size_t size = 1024*1024;                                /* record.c:133 initial size, doubled at :38-51 */
 	while (4+total+19 >= size) size <<= 1;
@@ -342,6 +376,16 @@ int ns_host_run(struct sim_state *s){
 		if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time\n"); abort(); }
 		if (rc) { log_err("device core: %s\n", ns_strerror(rc)); break; }
 		if (!ev.stopped) break;                             /* queue empty */
+		if (ev.stopped == 2) {                              /* record buffer nearly full BEFORE a batch: nothing was handled, */
+			size_t before = c->dev_off;                     /* no event to dispatch — copy the records out and go on */
+			pull_records(c);
+			if (ns_dev_records_drain(c->dev) || (c->dev_off == before && c->want_records)) {
+				log_err("device core: record buffer too small for one batch\n");
+				rc = NS_E_RECORDS_LOST;
+				break;
+			}
+			continue;
+		}
 		s->now = ev.time;                                   /* main.c:60 */
 		struct event tmp, *e = &tmp;
 		struct spd_event se;

@@ -320,3 +320,30 @@ def test_engine_config1_shape_1k_clients_one_seeder(mname, mode, built):
         r = refrun.run_reference(b, trace=False)
         assert r["returncode"] == 0 and r["records"] == e.records()
     e.close()
+
+
+def test_engine_bench_scale_matches_oracle(built):
+    """BASELINE.json configs[2] at the bench's own scale: the 100 032-peer / ~1M-flow script bench.py times
+    (same generator arguments), first 6 M events in three instalments — lock-step batches of ~1 M events, the
+    register-resident chains, the CTA-wide hub spreads and the parallel init all see their real sizes here.
+    Record stream, digest and every counter must equal the CPU oracle's."""
+    sc = S.swarm_fast(100032, 320, n_catalogue=64, seeds_per_peer=8, mean_strips=9.0, hub_frac=0.02, res_len=600000,
+                      seed=12345, rand_seed=1)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b, trace=False, records=True)
+    assert o.run(6_000_000) == 0
+    e = E.Engine(b, mode=E.MODE_AUTO, records=True, record_cap=(6_000_000 + 4 * sc.n_creates()) * 48 + (64 << 20), ring_cap=1 << 26)
+    for upto in (2_000_000, 4_000_000, 6_000_000):
+        assert e.run(upto) == 0
+    ce, co = e.counters(), o.counters()
+    assert {k: ce[k] for k in KEYS} == {k: co[k] for k in KEYS}
+    assert ce["par_events"] == ce["events"]               # the whole range ran on the grid-parallel path
+    ref = o.records()
+    d = e.digest()
+    assert d["record_bytes"] == len(ref)
+    assert d["record_hash"] == E.stream_hash(ref)
+    assert e.records() == ref
+    assert e.node_state(sc.n_nodes).tobytes() == o.node_state(sc.n_nodes).tobytes()
+    assert e.flow_state(sc.n_creates()).tobytes() == o.flow_state(sc.n_creates()).tobytes()
+    e.close()
+    o.close()

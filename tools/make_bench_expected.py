@@ -1,0 +1,47 @@
+"""Expected record digest of bench.py's default workload, computed HERE by the CPU oracle (oracle/ns_oracle.c,
+pinned to the compiled reference by tests/test_oracle_golden.py) and committed as tests/golden/bench_expected.json.
+bench.py compares the device engine's digest after its last window against it (outside the timed region).
+    python tools/make_bench_expected.py [ranks] [total_events]
+"""
+import json
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def one(rank, total_events, peers, hubs, hub_frac):
+    from netsim_b200 import engine as E
+    from netsim_b200 import scenario as S
+    from oracle import pyoracle
+    sc = S.swarm_fast(peers, hubs, n_catalogue=64, seeds_per_peer=8, mean_strips=9.0, hub_frac=hub_frac, res_len=600000,
+                      seed=12345 + rank, rand_seed=1 + rank)
+    t0 = time.time()
+    o = pyoracle.Oracle(sc.to_bytes(), trace=False, records=True)
+    st = o.run(total_events)
+    c = o.counters()
+    rec = o.records()
+    out = {"rank": rank, "status": st, "events": c["events"], "solves": c["solves"], "full_spreads": c["full_spreads"],
+           "seq": c["seq"], "record_bytes": len(rec), "record_hash": E.stream_hash(rec), "oracle_seconds": round(time.time() - t0, 1)}
+    o.close()
+    return out
+
+
+if __name__ == "__main__":
+    ranks = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    total = int(sys.argv[2]) if len(sys.argv) > 2 else 13_000_000
+    peers, hubs, hub_frac = 100032, 320, 0.02
+    with ProcessPoolExecutor(max_workers=min(ranks, 4)) as ex:
+        res = list(ex.map(one, range(ranks), [total] * ranks, [peers] * ranks, [hubs] * ranks, [hub_frac] * ranks))
+    path = os.path.join(ROOT, "tests", "golden", "bench_expected.json")
+    try:
+        cur = json.load(open(path))
+    except Exception:
+        cur = {}
+    for r in res:
+        cur[f"peers={peers},hubs={hubs},hub_frac={hub_frac},rank={r['rank']},events={total}"] = r
+        print(r)
+    json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
