@@ -29,7 +29,7 @@ __device__ __noinline__ void par_finish_piece(const Sim &S, SimState *st, ParScr
 	st->cnt[NS_CNT_SEQ] = st->tail;
 	for (int q = 0; q < LC_N; q++) ctl->lc[q] = 0;
 	ctl->pos = ctl->seg_hi;
-	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0; ctl->n_long = 0;
+	ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0; ctl->n_long = 0; ctl->n_big = 0;
 	ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 	*P.stage.ovf_top = 0;
 }
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 	__shared__ double sh_d[PAR_WARPS];
 	__shared__ u64 sh_u[PAR_WARPS];
 	__shared__ unsigned sh_r[PAR_WARPS], sh_t[PAR_WARPS];
-	__shared__ int sh_big[PAR_THREADS]; __shared__ int sh_nbig, sh_status;
-	__shared__ u64 sh_bseq[PAR_THREADS], sh_brec[PAR_THREADS], sh_btr[PAR_THREADS];
+	__shared__ int sh_status, sh_nbtot;
+	__shared__ int sh_ctab[1024];                                 // per-CTA tile-count prefixes (grid size <= 1024 CTAs)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int gw = blockIdx.x*PAR_WARPS+warp, nw = gridDim.x*PAR_WARPS;
 	const u64 gtid = (u64)blockIdx.x*PAR_THREADS+tid, gth = (u64)gridDim.x*PAR_THREADS;
@@ -127,15 +127,33 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 		const u64 mb = ctl->tmin_bits;
 		if (mb == ~0ull) break;                                       // queue empty
 		const double m = __longlong_as_double((long long)mb);
-		// ---- B1: per-tile match counts; block 0 warp 0 also extracts the long-lived events -----
+		// ---- B1: ONE sweep over the tiles that hit: match count, match bit mask (32 words per tile) and the tile's
+		//      new minimum; the last warp also extracts the long-lived events ------------------------------------
 		for (u64 k = gw; k < n_wt; k += nw) {
-			u64 at = t_first+k;
+			const u64 at = t_first+k;
 			int cnt = 0;
 			if (S.q_tmin[at & tmask] == m) {
-				u64 base = at << NS_TILE_SHIFT;
-				#pragma unroll
-				for (int i = 0; i < NS_TILE; i += 32) { u64 s = base+i+lane; cnt += (S.q_time[s & smask] == m && s >= head && s < tail); }
-				for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, d);
+				const u64 base = at << NS_TILE_SHIFT;
+				double nm = NS_INF;
+				unsigned my_word = 0;                                     // lane i keeps the ballot of row i
+				for (int i0 = 0; i0 < NS_TILE; i0 += 32*8) {                 // 8 independent loads in flight per lane
+					double tv[8];
+					#pragma unroll
+					for (int u = 0; u < 8; u++) tv[u] = S.q_time[(base+i0+32*u+lane) & smask];
+					#pragma unroll
+					for (int u = 0; u < 8; u++) {
+						const u64 s = base+i0+32*u+lane;
+						const double t = tv[u];
+						const bool match = t == m && s >= head && s < tail;
+						const unsigned mm = __ballot_sync(FULLMASK, match);
+						if (lane == (i0 >> 5)+u) my_word = mm;
+						cnt += __popc(mm);
+						if (!match) nm = fmin(nm, t);
+					}
+				}
+				nm = warp_min_d(nm);
+				P.tile_mask[k*32+lane] = my_word;
+				if (lane == 0) S.q_tmin[at & tmask] = nm;                 // nobody else looks at this tile's minimum before the next argmin
 			}
 			if (lane == 0) P.tile_cnt[k] = cnt;
 		}
@@ -145,47 +163,50 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			if (lane == 0) ctl->nl = nl;
 		}
 		grid.sync();
-		// ---- B2: exclusive scan of tile counts (block 0) ---------------------------------------
-		if (blockIdx.x == 0) {
-			__shared__ int sh_scan[PAR_THREADS];
-			u64 per = (n_wt+PAR_THREADS-1)/PAR_THREADS;
-			u64 lo = tid*per, hi = lo+per < n_wt ? lo+per : n_wt;
-			int s = 0;
-			for (u64 k = lo; k < hi; k++) s += P.tile_cnt[k];
-			sh_scan[tid] = s;
-			__syncthreads();
-			if (tid == 0) { int acc = 0; for (int i = 0; i < PAR_THREADS; i++) { int v = sh_scan[i]; sh_scan[i] = acc; acc += v; } ctl->nb = acc; }
-			__syncthreads();
-			int acc = sh_scan[tid];
-			for (u64 k = lo; k < hi; k++) { int v = P.tile_cnt[k]; P.tile_off[k] = acc; acc += v; }
+		// ---- B2: exclusive scan of the tile counts: every CTA scans a contiguous share, the CTA totals are
+		//      combined by everyone after the barrier -----------------------------------------------------------
+		const u64 t_per = (n_wt+gridDim.x-1)/gridDim.x;
+		{
+			const u64 lo = (u64)blockIdx.x*t_per < n_wt ? (u64)blockIdx.x*t_per : n_wt, hi = lo+t_per < n_wt ? lo+t_per : n_wt;
+			int carry = 0;
+			for (u64 k0 = lo; k0 < hi; k0 += PAR_THREADS) {
+				const u64 k = k0+tid;
+				const int v = k < hi ? P.tile_cnt[k] : 0;
+				int incl = v;
+				#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
+				__syncthreads();
+				if (lane == 31) sh_r[warp] = (unsigned)incl;
+				__syncthreads();
+				int wb = 0, tot = 0;
+				for (int w = 0; w < PAR_WARPS; w++) { if (w < warp) wb += (int)sh_r[w]; tot += (int)sh_r[w]; }
+				if (k < hi) P.tile_off[k] = carry+wb+incl-v;
+				carry += tot;
+			}
+			if (tid == 0) P.cta_tile[blockIdx.x] = carry;
 		}
 		grid.sync();
-		const int nb = ctl->nb, nl = ctl->nl;
-		if (nb > S.batch_cap) { if (leader) atomicCAS(&st->status, 0, NS_E_BATCH_FULL); continue; }
-		// ---- B3: write the batch in order, refresh the tile minima ------------------------------
+		{
+			int acc = 0;                                                  // exclusive prefix of the CTA totals, in shared memory
+			for (int q = tid; q < (int)gridDim.x; q += PAR_THREADS) sh_ctab[q] = P.cta_tile[q];
+			__syncthreads();
+			if (tid == 0) { for (int q = 0; q < (int)gridDim.x; q++) { int v = sh_ctab[q]; sh_ctab[q] = acc; acc += v; } sh_nbtot = acc; }
+			__syncthreads();
+		}
+		const int nb = sh_nbtot, nl = ctl->nl;
+		if (nb > S.batch_cap) { if (leader) atomicCAS(&st->status, 0, NS_E_BATCH_FULL); grid.sync(); continue; }
+		// ---- B3: write the batch in order from the bit masks (no second sweep over the ring) -----------------------
 		for (u64 k = gw; k < n_wt; k += nw) {
-			u64 at = t_first+k;
-			if (S.q_tmin[at & tmask] != m) continue;
-			u64 base = at << NS_TILE_SHIFT;
-			int off = P.tile_off[k];
-			double nm = NS_INF;
-			for (int i0 = 0; i0 < NS_TILE; i0 += 32*8) {                 // 8 independent loads in flight per lane
-				double tv[8];
-				#pragma unroll
-				for (int u = 0; u < 8; u++) tv[u] = S.q_time[(base+i0+32*u+lane) & smask];
-				#pragma unroll
-				for (int u = 0; u < 8; u++) {
-					u64 s = base+i0+32*u+lane;
-					double t = tv[u];
-					bool match = t == m && s >= head && s < tail;
-					unsigned mm = __ballot_sync(FULLMASK, match);
-					if (match) S.b_seq[off+__popc(mm & ((1u << lane)-1))] = s;
-					off += __popc(mm);
-					if (!match) nm = fmin(nm, t);
-				}
+			if (P.tile_cnt[k] == 0) continue;
+			const u64 base = (t_first+k) << NS_TILE_SHIFT;
+			int off = P.tile_off[k]+sh_ctab[k/t_per];
+			const unsigned my_word = P.tile_mask[k*32+lane];
+			#pragma unroll 8
+			for (int i = 0; i < 32; i++) {
+				const unsigned mm = __shfl_sync(FULLMASK, my_word, i);
+				if ((mm >> lane) & 1u) S.b_seq[off+__popc(mm & ((1u << lane)-1))] = base+(u64)(i*32+lane);
+				off += __popc(mm);
 			}
-			nm = warp_min_d(nm);
-			if (lane == 0) S.q_tmin[at & tmask] = nm;
 		}
 		if (leader) {
 			u64 fl = ctl->first_live;
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 			// sparse phase: many small batches in a row and event stores one warp can scan -> hand over to k_run_seq
 			ctl->small_streak = nb+nl < PAR_MIN_BATCH ? ctl->small_streak+1 : 0;
 			if (ctl->small_streak >= SPARSE_STREAK && n_wt+(u64)S.n_l_tiles <= SPARSE_MAX_TILES) { st->want_sparse = 1; ctl->small_streak = 0; }
-			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0; ctl->n_long = 0;
+			ctl->n_active = 0; ctl->cursor = 0; ctl->work = 0; ctl->n_deferred = 0; ctl->n_hub = 0; ctl->hub_work = 0; ctl->n_long = 0; ctl->n_big = 0;
 			ctl->tot_ins = 0; ctl->tot_rec = 0; ctl->tot_tr = 0;
 			*P.stage.ovf_top = 0;
 		}
@@ -265,6 +286,10 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				if (k >= NG) continue;
 				if (i == 0 || P.srt_key[i-1] != k) { P.grp_off[k] = (int)i; P.active[atomicAdd(&ctl->n_active, 1)] = k; }
 				if (i+1 == (u64)ns || P.srt_key[i+1] != k) P.grp_fill[k] = (int)i+1;
+				// the event itself, packed in partition order: the chains read these with coalesced loads
+				const u64 slot = S.b_seq[seg_lo+P.grp_items[i]] & smask;
+				const int fd = S.q_fd[slot];
+				P.pk_fd[i] = fd; P.pk_speed[i] = S.q_speed[slot]; P.pk_slot[i] = slot; P.pk_own[i] = S.f_pos[fd & 1][fd >> 1];
 			}
 			grid.sync();
 			const int n_active = ctl->n_active;
@@ -392,10 +417,15 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 				if (S.want_rec && rec0+t_rec > S.rec_cap) { okc = false; if (leader) atomicCAS(&st->status, 0, NS_E_RECORDS_LOST); }
 				if (leader) { ctl->tot_ins = t_ins; ctl->tot_rec = t_rec; ctl->tot_tr = t_tr; }
 				if (okc) {
-					// block-wide running scan over the chunk, PAR_THREADS events at a time
+					// block-wide running scan over the chunk, PAR_THREADS events at a time.  Small events (<= 32
+					// event_adds) are committed by their own thread with the loads batched; the records of the 256
+					// events are laid out contiguously in shared memory and leave as one coalesced copy; the
+					// event_adds of big events (full spreads) wait for F3, where the whole grid shares them.
+					CommitSmem &Cs = *reinterpret_cast<CommitSmem *>(dyn_smem);
 					u64 run_ins = tail0+b_ins, run_rec = rec0+b_rec, run_tr = tr0+b_tr;
+					if (tid < COMMIT_TILES) Cs.tmin[tid] = ~0ull;
 					for (int e0 = c_lo; e0 < c_hi; e0 += PAR_THREADS) {
-						int e = e0+tid;
+						const int e = e0+tid;
 						unsigned ni = 0, nr = 0, nt = 0;
 						if (e < c_hi) { ni = P.stage.ev_nins[e]; nr = P.stage.ev_nrec[e]; nt = P.stage.ev_ntr[e]; }
 						u64 xi = ni; unsigned xr = nr, xt = nt;
@@ -405,7 +435,6 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 						}
 						__syncthreads();
 						if (lane == 31) { sh_u[warp] = xi; sh_r[warp] = xr; sh_t[warp] = xt; }
-						if (tid == 0) sh_nbig = 0;
 						__syncthreads();
 						u64 wi = 0; unsigned wr = 0, wt = 0;
 						u64 tot_i = 0; unsigned tot_r = 0, tot_t = 0;
@@ -413,20 +442,55 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const S
 							if (w < warp) { wi += sh_u[w]; wr += sh_r[w]; wt += sh_t[w]; }
 							tot_i += sh_u[w]; tot_r += sh_r[w]; tot_t += sh_t[w];
 						}
-						u64 my_seq = run_ins+wi+xi-ni, my_rec = run_rec+wr+xr-nr, my_tr = run_tr+wt+xt-nt;
+						const u64 my_seq = run_ins+wi+xi-ni, my_rec = run_rec+wr+xr-nr, my_tr = run_tr+wt+xt-nt;
+						const unsigned pad = (unsigned)((uintptr_t)(S.rec+run_rec) & 15u);     // shared copy keeps the destination's alignment
 						if (e < c_hi) {
-							if (ni > 32) {                            // a full spread: copied by a whole warp below
-								int q = atomicAdd(&sh_nbig, 1);
-								sh_big[q] = e; sh_bseq[q] = my_seq; sh_brec[q] = my_rec; sh_btr[q] = my_tr;
-							} else par_commit_event(S, P.stage, e, my_seq, my_rec, my_tr, 0, 1);
+							if (ni > 32) {                            // a full spread: its event_adds go to F3
+								int q = atomicAdd(&ctl->n_big, 1);
+								if (q < P.big_cap) { P.big_e[q] = e; P.big_seq[q] = my_seq; }
+								else atomicCAS(&st->status, 0, NS_E_INTERNAL);
+							} else if (ni) commit_small_inserts(S, P.stage, Cs, e, ni, my_seq, run_ins);
+							if (nr) {                                 // record bytes -> shared memory at their final relative offset
+								const u64 *src = (const u64 *)(P.stage.st_rec+(u64)e*NS_STAGE_REC);
+								unsigned char *dstb = Cs.rec+pad+(unsigned)(my_rec-run_rec);
+								#pragma unroll
+								for (int w = 0; w < NS_STAGE_REC/8; w++) {
+									if (8u*w < nr) {
+										const u64 x = src[w];
+										#pragma unroll
+										for (int bb = 0; bb < 8; bb++) if (8u*w+bb < nr) dstb[8*w+bb] = (unsigned char)(x >> (8*bb));
+									}
+								}
+							}
+							if (nt && my_tr < S.tr_cap) S.tr[my_tr] = P.stage.st_tr[e];
 						}
 						__syncthreads();
-						int nbig = sh_nbig;
-						for (int q = warp; q < nbig; q += PAR_WARPS)
-							par_commit_event(S, P.stage, sh_big[q], sh_bseq[q], sh_brec[q], sh_btr[q], lane, 32);
+						if (tot_r) {                                  // one coalesced copy of the iteration's records
+							unsigned char *dst = S.rec+run_rec;
+							const unsigned n = tot_r, head = n < ((16u-pad) & 15u) ? n : ((16u-pad) & 15u);
+							for (unsigned i = tid; i < head; i += PAR_THREADS) dst[i] = Cs.rec[pad+i];
+							const unsigned nvec = (n-head) >> 4;
+							for (unsigned v = tid; v < nvec; v += PAR_THREADS) *(uint4 *)(dst+head+16u*v) = *(const uint4 *)(Cs.rec+pad+head+16u*v);
+							for (unsigned i = head+16u*nvec+tid; i < n; i += PAR_THREADS) dst[i] = Cs.rec[pad+i];
+						}
+						if (tid < COMMIT_TILES) {                     // one tile-minimum update per touched ring tile
+							const u64 tb = Cs.tmin[tid];
+							if (tb != ~0ull) {
+								const double t = __longlong_as_double((long long)tb);
+								double *tm = &S.q_tmin[((run_ins >> NS_TILE_SHIFT)+tid) & tmask];
+								if (*(volatile double *)tm > t) tmin_lower(tm, t);
+								Cs.tmin[tid] = ~0ull;
+							}
+						}
 						run_ins += tot_i; run_rec += tot_r; run_tr += tot_t;
 					}
 				}
+			}
+			grid.sync();
+			// ---- F3: the event_adds of the big events, one warp per event, over the whole grid -------------------
+			{
+				const int n_big = ctl->n_big < P.big_cap ? ctl->n_big : P.big_cap;
+				for (int q = gw; q < n_big; q += nw) par_commit_event(S, P.stage, P.big_e[q], P.big_seq[q], 0, 0, lane, 32, false);
 			}
 			grid.sync();
 			PHASE_MARK(PH_COMMIT);
@@ -461,7 +525,7 @@ int par_grid(const void *kernel, int sm_count, int *grid, size_t dyn_smem){
 	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PAR_THREADS, dyn_smem);
 	if (e != cudaSuccess) return (int)e;
 	if (per_sm < 1) return NS_E_ARG;
-	*grid = std::min(sm_count*per_sm, 4096);
+	*grid = std::min(sm_count*per_sm, 1024);                                 // k_run_par keeps per-CTA tables of 1024 entries
 	return 0;
 }
 int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){

@@ -24,11 +24,14 @@ struct ParScratch {
 	ParStage *d_stage;
 	// per-timestamp
 	int *tile_cnt, *tile_off;     // per ring-window tile: matches, exclusive offset
+	unsigned *tile_mask; int *cta_tile;   // ... the match bits of a tile (32 words), per-CTA totals of the count scan
 	// grouping
 	int *grp_cnt, *grp_off, *grp_fill, *active, *grp_items, *b_grp;
 	int *deferred, *defer_pos;     // groups handed from the per-thread pass to the per-warp pass
 	int *defer_long;               // ... the ones with long chains (taken first)
 	int *srt_key, *srt_key2, *srt_val2, *rad_hist;   // stable partition of a segment by group (radix_pass)
+	int *big_e; u64 *big_seq; int big_cap;           // ... their segment index and first sequence number
+	int *pk_fd, *pk_own; double *pk_speed; u64 *pk_slot;   // the events in partition order: flow*2+dir, list position of the flow, speed, ring slot
 	// parallel module init: CREATE ops of group 0 scheduled into conflict-free waves (host, par_plan_init)
 	int n_init, n_waves; int *wave_off, *wave_ops; u64 *cta_draws;
 	// scan
@@ -38,6 +41,7 @@ struct ParScratch {
 		u64 tmin_bits, first_live;
 		int nb, nl, n_active, cursor, work, seg_lo, seg_hi, n_deferred, dbg_g, dbg_deg;
 		int n_long;                                // chains of more than 128 events: taken first by the warp pass (defer_long)
+		int n_big;                                 // events with more than 32 event_adds: committed by the whole grid (F3)
 		int n_hub, hub_work;                       // groups handed to whole CTAs (hub_chain_cta); stored from the END of `deferred`
 		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
 		int small_streak;                          // consecutive small batches (sparse phase detection)
@@ -64,10 +68,13 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 	PA(st.ev_nins, p.seg_cap); PA(st.ev_ovf, p.seg_cap); PA(st.ev_nrec, p.seg_cap); PA(st.ev_ntr, p.seg_cap); PA(st.ev_idpos, p.seg_cap);
 	PA(p.d_stage, 1);
 	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
+	PA(p.tile_mask, (size_t)(S.n_ring_tiles+1)*32); PA(p.cta_tile, 4096);
 	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
 	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
 	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1); PA(p.defer_long, p.seg_cap/128+2);
 	PA(p.srt_key, p.seg_cap); PA(p.srt_key2, p.seg_cap); PA(p.srt_val2, p.seg_cap); PA(p.rad_hist, 512*4096);
+	p.big_cap = 1 << 18; PA(p.big_e, p.big_cap); PA(p.big_seq, p.big_cap);
+	PA(p.pk_fd, p.seg_cap); PA(p.pk_own, p.seg_cap); PA(p.pk_speed, p.seg_cap); PA(p.pk_slot, p.seg_cap);
 	PA(p.cta_ins, 4096); PA(p.cta_rec, 4096); PA(p.cta_tr, 4096); PA(p.cta_draws, 4096);
 	if (n_init) { PA(p.wave_off, n_init+2); PA(p.wave_ops, n_init); }
 	PA(p.ctl, 1);

@@ -274,7 +274,6 @@ __device__ void ge_chain2(Ctx &c, const ParScratch &P, int g, int seg_lo, int of
 	const Sim &S = *c.S;
 	SimState *st = c.st;
 	const int lane = c.lane, n = g >> 1, dir = g & 1;
-	const u64 smask = S.ring_cap-1;
 	const int a_off = S.adj_off[g], a_len = S.adj_len[g];
 	const double total = S.n_total[dir][n], mx = S.n_max[dir][n];
 	double usage = S.n_usage[dir][n];
@@ -288,18 +287,18 @@ __device__ void ge_chain2(Ctx &c, const ParScratch &P, int g, int seg_lo, int of
 	u64 h0, h1;
 	rec19_time(now, h0, h1);
 	unsigned n_simple = 0;
+	// the events of the chain come packed in partition order (k_run_par phase D3): one coalesced load per field,
+	// and the next block is fetched while this one runs
+	int nx_e = -1, nx_fd = 0, nx_own = lane; double nx_speed = 0; u64 nx_slot = 0;
+	if (j+lane < cnt) { const int q = off+j+lane; nx_e = P.grp_items[q]; nx_fd = P.pk_fd[q]; nx_speed = P.pk_speed[q]; nx_slot = P.pk_slot[q]; nx_own = P.pk_own[q]; }
 	for (int j0 = j; j0 < cnt; j0 += 32) {
 		const int nev = cnt-j0 < 32 ? cnt-j0 : 32;
-		// ---- fetch: lane k holds event k of the block and the lane that owns its flow
-		int my_e = -1, my_fd = 0, own = lane; double my_speed = 0; u64 my_slot = 0;
+		// ---- fetch: lane k holds event k of the block and the lane that owns its flow (list position == lane, ge_load)
+		int my_e = nx_e, my_fd = nx_fd, own = nx_own; double my_speed = nx_speed; u64 my_slot = nx_slot;
+		nx_e = -1; nx_own = lane;
+		if (j0+32+lane < cnt) { const int q = off+j0+32+lane; nx_e = P.grp_items[q]; nx_fd = P.pk_fd[q]; nx_speed = P.pk_speed[q]; nx_slot = P.pk_slot[q]; nx_own = P.pk_own[q]; }
 		bool bad = false;
-		if (lane < nev) {
-			my_e = P.grp_items[off+j0+lane];
-			my_slot = S.b_seq[seg_lo+my_e] & smask;
-			my_fd = S.q_fd[my_slot]; my_speed = S.q_speed[my_slot];
-			own = S.f_pos[dir][my_fd >> 1];                           // list position == lane (ge_load)
-			if ((unsigned)own >= 32u) { bad = true; own = lane; }
-		}
+		if (lane < nev && (unsigned)own >= 32u) { bad = true; own = lane; }
 		{
 			const int own_nf = __shfl_sync(FULLMASK, gf.nf, own);
 			if (lane < nev && own_nf != (my_fd >> 1)) bad = true;
@@ -320,10 +319,17 @@ __device__ void ge_chain2(Ctx &c, const ParScratch &P, int g, int seg_lo, int of
 			double ev_fs = 0, ev_use = 0; unsigned ev_fl = 0;
 			bool hit_full = false;
 			int k = k0;
+			int owner_n = __shfl_sync(FULLMASK, own, k0 & 31);
+			double speed_n = __shfl_sync(FULLMASK, my_speed, k0 & 31), share_n = __shfl_sync(FULLMASK, gf.share, owner_n);
 			for (; k < nev; k++) {
-				const int owner = __shfl_sync(FULLMASK, own, k);
-				const double speed = __shfl_sync(FULLMASK, my_speed, k);
-				const double fs = __shfl_sync(FULLMASK, gf.sp, owner), share = __shfl_sync(FULLMASK, gf.share, owner);
+				// what does not depend on the carried state (the event, its owner, the owner's share) is fetched one
+				// iteration ahead, so only the speed shuffle and the arithmetic sit on the chain
+				const int owner = owner_n;
+				const double speed = speed_n, share = share_n;
+				owner_n = __shfl_sync(FULLMASK, own, (k+1) & 31);
+				speed_n = __shfl_sync(FULLMASK, my_speed, (k+1) & 31);
+				share_n = __shfl_sync(FULLMASK, gf.share, owner_n);
+				const double fs = __shfl_sync(FULLMASK, gf.sp, owner);
 				double amount = speed-fs;                                 // flow.c:359
 				unsigned fl = amount > 0 ? GE_DELTA_POS : 0u;
 				if (amount > NS_EPS && fs+amount > share) {               // flow.c:64-78
@@ -515,7 +521,6 @@ __device__ void hub_chain_cta(const Sim &S, SimState *st, const ParScratch &P, H
 	const double total = S.n_total[SND][n], mx = S.n_max[SND][n];
 	double usage = S.n_usage[SND][n];
 	const unsigned node_id = S.n_id[n];
-	const u64 smask = S.ring_cap-1;
 	const bool sat = !(total < mx+NS_EPS);
 	const int rows = (len+PAR_THREADS-1)/PAR_THREADS;
 	u64 h0, h1;
@@ -558,12 +563,11 @@ __device__ void hub_chain_cta(const Sim &S, SimState *st, const ParScratch &P, H
 		const int nev = cnt-j0 < PAR_THREADS ? cnt-j0 : PAR_THREADS;
 		__syncthreads();
 		if (tid < nev) {
-			int e = P.grp_items[off+j0+tid];
-			u64 slot = S.b_seq[seg_lo+e] & smask;
-			int f = S.q_fd[slot] >> 1;
-			int pf = S.f_pos[SND][f];
+			const int q = off+j0+tid;
+			const int f = P.pk_fd[q] >> 1;
+			int pf = P.pk_own[q];
 			if ((unsigned)pf >= (unsigned)len || H.nf[pf] != f) pf = -1;
-			H.ev_e[tid] = e; H.ev_pf[tid] = pf; H.ev_speed[tid] = S.q_speed[slot]; H.ev_slot[tid] = slot;
+			H.ev_e[tid] = P.grp_items[q]; H.ev_pf[tid] = pf; H.ev_speed[tid] = P.pk_speed[q]; H.ev_slot[tid] = P.pk_slot[q];
 		}
 		__syncthreads();
 		for (int i = 0; i < nev; i++) {
@@ -735,7 +739,40 @@ __device__ void hub_chain_cta(const Sim &S, SimState *st, const ParScratch &P, H
 }
 
 // copy the staged outputs of segment-local event e to their final places
-__device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep){
+// the commit pass of k_run_par: per-iteration scratch in dynamic shared memory
+#define COMMIT_TILES 8
+struct CommitSmem { u64 tmin[COMMIT_TILES]; u64 pad_[2]; unsigned char rec[PAR_THREADS*NS_STAGE_REC+32]; };
+// the event_adds of one small event (<= 32), by its own thread: inline stage slots loaded together, ring tile
+// minima collected in shared memory (one global update per tile and iteration instead of one per event_add)
+__device__ __forceinline__ void commit_small_inserts(const Sim &S, const ParStage &ps, CommitSmem &Cs, int e, unsigned nins, u64 seq0, u64 run_ins){
+	const long long ovf = nins > NS_STAGE_INLINE ? ps.ev_ovf[e] : -1;
+	int fdv[NS_STAGE_INLINE]; double tv[NS_STAGE_INLINE], sv[NS_STAGE_INLINE]; uint32_t gv[NS_STAGE_INLINE];
+	#pragma unroll
+	for (int j = 0; j < NS_STAGE_INLINE; j++) {
+		fdv[j] = NS_HOLE_PURE; tv[j] = 0; sv[j] = 0;
+		if ((unsigned)j < nins) { const u64 si = (u64)e*NS_STAGE_INLINE+j; fdv[j] = ps.st_fd[si]; tv[j] = ps.st_time[si]; sv[j] = ps.st_speed[si]; }
+	}
+	#pragma unroll
+	for (int j = 0; j < NS_STAGE_INLINE; j++) gv[j] = fdv[j] >= 0 ? S.f_gen[fdv[j] >> 1] : 0u;
+	for (unsigned j = 0; j < nins; j++) {
+		int fd; double t, sp; uint32_t gen;
+		if (j < NS_STAGE_INLINE) { fd = fdv[j]; t = tv[j]; sp = sv[j]; gen = gv[j]; }
+		else { const u64 si = ps.inline_n+(u64)ovf+(j-NS_STAGE_INLINE); fd = ps.st_fd[si]; t = ps.st_time[si]; sp = ps.st_speed[si]; gen = fd >= 0 ? S.f_gen[fd >> 1] : 0u; }
+		const u64 seq = seq0+j;
+		if (fd >= 0) {
+			const u64 slot = seq & (S.ring_cap-1);
+			S.q_time[slot] = t; S.q_speed[slot] = sp; S.q_fd[slot] = fd; S.q_gen[slot] = gen;
+			const u64 rel = (seq >> NS_TILE_SHIFT)-(run_ins >> NS_TILE_SHIFT);
+			if (rel < COMMIT_TILES) atomicMin((unsigned long long *)&Cs.tmin[rel], (unsigned long long)__double_as_longlong(t));
+			else { double *tm = &S.q_tmin[slot >> NS_TILE_SHIFT]; if (*(volatile double *)tm > t) tmin_lower(tm, t); }
+		} else if (fd != NS_HOLE_PURE) {
+			const int ls = -fd-1;
+			const u64 prov = NS_SEQ_PROV | ((u64)e << 24) | j;
+			if (S.l_seq[ls] == prov) S.l_seq[ls] = seq;                   // only the last add of a slot survives
+		}
+	}
+}
+__device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep, bool with_records = true){
 	unsigned nins = ps.ev_nins[e];
 	long long ovf = ps.ev_ovf[e];
 	for (unsigned j = lane0; j < nins; j += lstep) {
@@ -754,7 +791,7 @@ __device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &p
 			if (S.l_seq[ls] == prov) S.l_seq[ls] = seq;               // only the last add of a slot survives
 		}
 	}
-	if (lane0 == 0) {
+	if (lane0 == 0 && with_records) {
 		unsigned nrec = ps.ev_nrec[e];
 		if (nrec) { const uint8_t *src = ps.st_rec+(u64)e*NS_STAGE_REC; uint8_t *dst = S.rec+rec0; for (unsigned k = 0; k < nrec; k++) dst[k] = src[k]; }
 		if (ps.ev_ntr[e] && tr0 < S.tr_cap) S.tr[tr0] = ps.st_tr[e];
