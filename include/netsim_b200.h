@@ -146,11 +146,15 @@ int  ns_dev_phase_ns(ns_dev *d, uint64_t out[16]);
 uint64_t ns_dev_launches(ns_dev *d);
 void ns_dev_destroy(ns_dev *d);
 
-/* replica ensembles: n independent scenarios resident on one GPU, stepped together */
+/* replica ensembles: n independent scenarios resident on one GPU.  opts->mode NS_MODE_AUTO: one CTA per replica, the
+ * hardware block scheduler is the replicas' work queue; NS_MODE_SEQ: one warp per replica.  ns_ens_run returns when
+ * every replica is done (or has handled max_events_each events); the records are not copied out: a replica whose
+ * bounded record buffer fills up is folded into its running digest on the device and resumed. */
 int  ns_ens_create(ns_ens **out, const void *const *scenarios, const size_t *lens, int n,
 		   const struct ns_dev_opts *opts);
 int  ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms);
 int  ns_ens_digests(ns_ens *e, struct ns_digest *out, int n);
+int  ns_ens_counters_sum(ns_ens *e, uint64_t out[NS_CNT_COUNT]);   /* enum ns_counter, summed over the replicas (max for NS_CNT_MAX_BATCH) */
 uint64_t ns_ens_launches(ns_ens *e);
 void ns_ens_destroy(ns_ens *e);
 

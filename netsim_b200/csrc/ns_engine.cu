@@ -123,10 +123,21 @@ struct HostSim {
 	size_t bytes = 0;
 	uint32_t seed = 1;
 	int n_creates = 0;
+	// ensembles put all tables of all replicas into ONE allocation: a measuring pass (arena_mode 1) sums the sizes,
+	// the real pass (arena_mode 2) carves them out of [arena, arena+arena_size)
+	int arena_mode = 0;
+	char *arena = nullptr; size_t arena_size = 0, arena_used = 0;
 };
 
 static int dev_alloc(HostSim &h, void **p, size_t bytes){
 	if (bytes == 0) bytes = 8;
+	if (h.arena_mode) {
+		const size_t b = (bytes+255) & ~(size_t)255;
+		if (h.arena_mode == 1) { *p = (void *)(uintptr_t)256; h.arena_used += b; return 0; }
+		if (h.arena_used+b > h.arena_size) return NS_E_INTERNAL;
+		*p = h.arena+h.arena_used; h.arena_used += b; h.bytes += b;
+		return 0;
+	}
 	CK(cudaMalloc(p, bytes));
 	h.allocs.push_back(*p);
 	h.bytes += bytes;
@@ -166,7 +177,7 @@ static int host_rec(std::vector<uint8_t> &rec, double now, uint8_t minor, uint32
 }
 
 // Build one simulation's device tables from a scenario script.
-static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_opts &o, bool parallel_scratch){
+static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_opts &o, bool parallel_scratch, bool ens_cta = false){
 	if (len < sizeof(ns_sc_header)) return NS_E_BAD_SCENARIO;
 	ns_sc_header H;
 	memcpy(&H, scenario, sizeof H);
@@ -276,9 +287,13 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 			}
 		}
 	}
-	if ((rc = par_alloc(h.par, S, parallel_scratch, n_init, [&](void **pp, size_t b){ return dev_alloc(h, pp, b); }))) return rc;
+	ParSizes psz;
+	if (ens_cta) { psz.max_seg = 1u << 14; psz.min_ovf = 1u << 16; psz.ovf_per_flow = 8; psz.grid_max = 1; n_init = 0; }   // one CTA per replica (ns_ens.cu)
+	psz.dry = h.arena_mode == 1;
+	if ((rc = par_alloc(h.par, S, parallel_scratch, n_init, [&](void **pp, size_t b){ return dev_alloc(h, pp, b); }, psz))) return rc;
 	if (n_init && (rc = par_plan_init(h.par, ops, n_init, N))) return rc;
 #undef DA
+	if (h.arena_mode == 1) return 0;                                  // measuring pass: sizes only
 
 	// ---- host-side init: sim_create_node (sim.c:113-125), sim_node_new_resource (:129-140),
 	//      sim_node_add_resource (:141-154)
@@ -700,13 +715,78 @@ extern "C" void ns_dev_destroy(ns_dev *d){
 }
 
 // ---------------------------------------------------------------- C ABI: replica ensembles
+// Per-replica record digest without ever copying the records out: the stream hash is a sum over the stream's
+// 64-bit words (k_stream_hash), so a bounded record buffer can be folded into a running sum whenever it fills
+// up (the engine's soft stop, host_stop == 2) — a word-aligned prefix is hashed at its stream position, the
+// odd tail bytes move to the front of the buffer — and the simulation goes on.  One CTA per replica, one
+// launch for the whole ensemble, one 4-byte read-back per round (how many replicas still want to run).
+struct EnsAcc { u64 hash; };
+__global__ void __launch_bounds__(256) k_ens_drain(const Sim *sims, EnsAcc *acc, int n, int *n_more){
+	const int s = blockIdx.x;
+	if (s >= n) return;
+	const Sim &S = sims[s];
+	SimState *st = S.st;
+	__shared__ u64 sh[8];
+	__shared__ uint8_t tailb[8];
+	const u64 len = st->rec_len, base = st->rec_base;
+	const bool soft = st->status == 0 && st->host_stop == 2;
+	if (!soft) return;                                                // finished, failed or bounded by max_events: nothing to fold
+	const u64 nw = len >> 3;                                          // whole words (rec_base stays a multiple of 8)
+	u64 a = 0;
+	const u64 *w = (const u64 *)S.rec;
+	for (u64 j = threadIdx.x; j < nw; j += blockDim.x) a += ns_mix64(w[j]+0x9e3779b97f4a7c15ULL*((base >> 3)+j+1));
+	for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(FULLMASK, a, d);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+	const u64 tail = len & 7;
+	if (threadIdx.x < tail) tailb[threadIdx.x] = S.rec[(nw << 3)+threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x < tail) S.rec[threadIdx.x] = tailb[threadIdx.x];
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < 8; k++) a += sh[k];
+		acc[s].hash += a;
+		st->rec_base = base+(nw << 3); st->rec_len = tail;
+		st->host_stop = 0;
+		atomicAdd(n_more, 1);
+	}
+}
+__global__ void __launch_bounds__(256) k_ens_digest(const Sim *sims, const EnsAcc *acc, int n, ns_digest *out){
+	const int s = blockIdx.x;
+	if (s >= n) return;
+	const Sim &S = sims[s];
+	const SimState *st = S.st;
+	__shared__ u64 sh[8];
+	const u64 len = st->rec_len, base = st->rec_base;
+	const u64 nw = (len+7) >> 3;
+	u64 a = 0;
+	for (u64 j = threadIdx.x; j < nw; j += blockDim.x) {
+		u64 x = 0;
+		const u64 b0 = j*8;
+		if (b0+8 <= len) x = ((const u64 *)S.rec)[j];
+		else for (int k = 0; k < 8; k++) if (b0+k < len) x |= (u64)S.rec[b0+k] << (8*k);
+		a += ns_mix64(x+0x9e3779b97f4a7c15ULL*((base >> 3)+j+1));
+	}
+	for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(FULLMASK, a, d);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < 8; k++) a += sh[k];
+		ns_digest d;
+		d.seed = st->seed; d.events = st->cnt[NS_CNT_EVENTS]; d.solves = st->cnt[NS_CNT_SOLVES];
+		d.record_bytes = base+len; d.record_fnv1a = ns_mix64((acc[s].hash+a) ^ (base+len)); d.t_end = st->now;
+		d.status = st->status ? st->status : (st->host_stop == 2 ? NS_E_RECORDS_FULL : 0);
+		out[s] = d;
+	}
+}
+
 struct ns_ens {
 	int device = 0, n = 0;
 	std::vector<HostSim> sims;
-	Sim *d_sims = nullptr; SeqScratch *d_scr = nullptr;
+	Sim *d_sims = nullptr; SeqScratch *d_scr = nullptr; ParScratch *d_pars = nullptr;
+	int cta_engine = 1;             // one CTA per replica (k_run_ens); 0 (ns_dev_opts.mode == NS_MODE_SEQ): one warp per replica (k_run_seq)
 	cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
 	uint64_t launches = 0;
-	u64 *d_hash = nullptr;
+	char *arena = nullptr;          // every table of every replica
+	EnsAcc *d_acc = nullptr; int *d_more = nullptr; ns_digest *d_dig = nullptr;
 };
 
 static int ens_init(ns_ens *e, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts &o);
@@ -728,51 +808,102 @@ extern "C" int ns_ens_create(ns_ens **out, const void *const *scenarios, const s
 }
 static int ens_init(ns_ens *e, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts &o){
 	e->sims.resize(n);
-	std::vector<Sim> hs(n); std::vector<SeqScratch> hscr(n);
-	for (int i = 0; i < n; i++) {
-		int rc = build_sim(e->sims[i], scenarios[i], lens[i], o, false);
+	e->cta_engine = o.mode != NS_MODE_SEQ;
+	const bool cta = e->cta_engine != 0;
+	std::vector<Sim> hs(n); std::vector<SeqScratch> hscr(n); std::vector<ParScratch> hpar(n);
+	size_t total = 0;
+	std::vector<size_t> need(n);
+	for (int i = 0; i < n; i++) {                                     // measuring pass
+		e->sims[i].arena_mode = 1; e->sims[i].arena_used = 0;
+		int rc = build_sim(e->sims[i], scenarios[i], lens[i], o, cta, cta);
 		if (rc) return rc;
-		hs[i] = e->sims[i].S; hscr[i] = e->sims[i].scr;
+		need[i] = e->sims[i].arena_used; total += need[i];
 	}
+	CK(cudaMalloc(&e->arena, total ? total : 8));
 	CK(cudaStreamCreate(&e->stream));
+	size_t off = 0;
+	for (int i = 0; i < n; i++) {
+		HostSim &h = e->sims[i];
+		h.arena_mode = 2; h.arena = e->arena+off; h.arena_size = need[i]; h.arena_used = 0;
+		off += need[i];
+		int rc = build_sim(h, scenarios[i], lens[i], o, cta, cta);
+		if (rc) return rc;
+		hs[i] = h.S; hscr[i] = h.scr; hpar[i] = h.par;
+	}
 	CK(cudaEventCreate(&e->e0)); CK(cudaEventCreate(&e->e1));
-	CK(cudaMalloc(&e->d_sims, sizeof(Sim)*n)); CK(cudaMalloc(&e->d_scr, sizeof(SeqScratch)*n)); CK(cudaMalloc(&e->d_hash, 8));
+	CK(cudaMalloc(&e->d_sims, sizeof(Sim)*n)); CK(cudaMalloc(&e->d_scr, sizeof(SeqScratch)*n));
+	CK(cudaMalloc(&e->d_acc, sizeof(EnsAcc)*n)); CK(cudaMalloc(&e->d_more, 4)); CK(cudaMalloc(&e->d_dig, sizeof(ns_digest)*std::max(n, 4)));
+	CK(cudaMemset(e->d_acc, 0, sizeof(EnsAcc)*n));
 	CK(cudaMemcpy(e->d_sims, hs.data(), sizeof(Sim)*n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(e->d_scr, hscr.data(), sizeof(SeqScratch)*n, cudaMemcpyHostToDevice));
+	if (cta) {
+		CK(cudaMalloc(&e->d_pars, sizeof(ParScratch)*n));
+		CK(cudaMemcpy(e->d_pars, hpar.data(), sizeof(ParScratch)*n, cudaMemcpyHostToDevice));
+		int rc = ens_preload(); if (rc) return rc;
+	}
 	CK(cudaDeviceSynchronize());
 	{ int rc = seq_launch_init_groups(e->d_sims, n, e->stream); if (rc) return rc; }
 	e->launches++;
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
 }
+// every replica runs until its queue is empty, its script ends it, or it has handled max_events_each events; a
+// replica whose record buffer fills up is folded into its running digest and resumed (no host copy of records)
 extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms){
 	if (!e) return NS_E_ARG;
 	CK(cudaSetDevice(e->device));
 	for (int i = 0; i < e->n; i++)
 		CK(cudaMemcpyAsync(&e->sims[i].S.st->max_events, &max_events_each, 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaEventRecord(e->e0, e->stream));
-	{ int rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc; }
-	e->launches++;
+	for (int round = 0; round < 1 << 20; round++) {
+		{ int rc = e->cta_engine ? ens_launch_run(e->d_sims, e->d_scr, e->d_pars, e->n, e->stream) : seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc; }
+		CK(cudaMemsetAsync(e->d_more, 0, 4, e->stream));
+		k_ens_drain<<<e->n, 256, 0, e->stream>>>(e->d_sims, e->d_acc, e->n, e->d_more);
+		CK(cudaGetLastError());
+		e->launches += 2;
+		int more = 0;
+		CK(cudaMemcpyAsync(&more, e->d_more, 4, cudaMemcpyDeviceToHost, e->stream));
+		CK(cudaStreamSynchronize(e->stream));
+		if (!more) break;
+	}
 	CK(cudaEventRecord(e->e1, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	if (device_ms) CK(cudaEventElapsedTime(device_ms, e->e0, e->e1));
 	return 0;
 }
+// one kernel for all replicas (hash of what is still buffered + the running sums), one copy back
 extern "C" int ns_ens_digests(ns_ens *e, ns_digest *out, int n){
 	if (!e || !out) return NS_E_ARG;
-	for (int i = 0; i < n && i < e->n; i++) {
-		SimState st;
-		CK(cudaMemcpy(&st, e->sims[i].S.st, sizeof st, cudaMemcpyDeviceToHost));
-		out[i].seed = st.seed; out[i].events = st.cnt[NS_CNT_EVENTS]; out[i].solves = st.cnt[NS_CNT_SOLVES];
-		out[i].record_bytes = st.rec_base+st.rec_len; out[i].t_end = st.now;
-		out[i].status = st.status ? st.status : (st.host_stop == 2 ? NS_E_RECORDS_FULL : 0);   // a replica that ran out of record room did not finish
-		u64 hsum = 0;
-		CK(cudaMemsetAsync(e->d_hash, 0, 8, e->stream));
-		if (st.rec_len) { k_stream_hash<<<64, 256, 0, e->stream>>>(e->sims[i].S.rec, st.rec_len, e->d_hash); e->launches++; }
-		CK(cudaMemcpyAsync(&hsum, e->d_hash, 8, cudaMemcpyDeviceToHost, e->stream));
-		CK(cudaStreamSynchronize(e->stream));
-		out[i].record_fnv1a = ns_mix64(hsum ^ st.rec_len);
+	if (n > e->n) n = e->n;
+	if (n <= 0) return 0;
+	CK(cudaSetDevice(e->device));
+	k_ens_digest<<<n, 256, 0, e->stream>>>(e->d_sims, e->d_acc, n, e->d_dig);
+	CK(cudaGetLastError());
+	e->launches++;
+	CK(cudaMemcpyAsync(out, e->d_dig, sizeof(ns_digest)*n, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+// the engine counters of all replicas, summed on the device (one kernel, one copy)
+__global__ void k_ens_counters(const Sim *sims, int n, u64 *out){
+	for (int s = blockIdx.x*blockDim.x+threadIdx.x; s < n; s += gridDim.x*blockDim.x) {
+		const SimState *st = sims[s].st;
+		for (int q = 0; q < NS_CNT_COUNT; q++) {
+			u64 v = q == NS_CNT_SEQ ? st->tail : q == NS_CNT_DRAWS ? st->cnt[q]+st->burns : st->cnt[q];
+			if (q == NS_CNT_MAX_BATCH) atomicMax((unsigned long long *)&out[q], v); else atomicAdd((unsigned long long *)&out[q], v);
+		}
 	}
+}
+extern "C" int ns_ens_counters_sum(ns_ens *e, uint64_t out[NS_CNT_COUNT]){
+	if (!e || !out) return NS_E_ARG;
+	CK(cudaSetDevice(e->device));
+	u64 *d_out = (u64 *)e->d_dig;                                     // the digest buffer is free between digests
+	CK(cudaMemsetAsync(d_out, 0, sizeof(u64)*NS_CNT_COUNT, e->stream));
+	k_ens_counters<<<(e->n+127)/128, 128, 0, e->stream>>>(e->d_sims, e->n, d_out);
+	CK(cudaGetLastError());
+	e->launches++;
+	CK(cudaMemcpyAsync(out, d_out, sizeof(u64)*NS_CNT_COUNT, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
 	return 0;
 }
 extern "C" uint64_t ns_ens_launches(ns_ens *e){ return e ? e->launches : 0; }
@@ -780,9 +911,13 @@ extern "C" void ns_ens_destroy(ns_ens *e){
 	if (!e) return;
 	cudaSetDevice(e->device);
 	for (auto &h : e->sims) free_sim(h);
+	if (e->arena) cudaFree(e->arena);
 	if (e->d_sims) cudaFree(e->d_sims);
 	if (e->d_scr) cudaFree(e->d_scr);
-	if (e->d_hash) cudaFree(e->d_hash);
+	if (e->d_pars) cudaFree(e->d_pars);
+	if (e->d_acc) cudaFree(e->d_acc);
+	if (e->d_more) cudaFree(e->d_more);
+	if (e->d_dig) cudaFree(e->d_dig);
 	if (e->e0) cudaEventDestroy(e->e0);
 	if (e->e1) cudaEventDestroy(e->e1);
 	if (e->stream) cudaStreamDestroy(e->stream);

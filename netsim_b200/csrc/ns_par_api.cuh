@@ -13,7 +13,9 @@
 #define PAR_MIN_BLOCKS 1       // CTAs per SM the persistent kernel is compiled for (register budget)
 #endif
 #define PAR_WARPS (PAR_THREADS/32)
+#ifndef PAR_MIN_BATCH
 #define PAR_MIN_BATCH 48          // smaller batches are cheaper on the single-warp path
+#endif
 #define SPARSE_STREAK 6            // that many small batches in a row: the grid barriers cost more than the events
 #define SPARSE_MAX_TILES 4096     // ... provided one warp can scan the tile minima of both event stores
 
@@ -51,16 +53,18 @@ struct ParScratch {
 	} *ctl;
 };
 
-template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool enable, int n_init, A alloc){
+// sizes of the scratch: the grid engine of one big simulation (defaults) or one CTA per replica of an ensemble (small)
+struct ParSizes { u64 max_seg = 1u << 20, min_ovf = 1u << 22, ovf_per_flow = 64; int grid_max = 4096; bool dry = false; };
+template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool enable, int n_init, A alloc, const ParSizes &z = ParSizes()){
 	memset(&p, 0, sizeof p);
 	p.enabled = enable;
 	if (!enable) return 0;
 	int rc;
 	p.n_init = n_init;
-	p.seg_cap = std::max((int)std::min<u64>((u64)S.batch_cap, 1u << 20), n_init);
+	p.seg_cap = std::max((int)std::min<u64>((u64)S.batch_cap, z.max_seg), n_init);
 	ParStage &st = p.stage;
 	st.inline_n = (u64)NS_STAGE_INLINE*p.seg_cap;
-	st.ovf_cap = std::max<u64>(1u << 22, 64ull*S.cap_flows);
+	st.ovf_cap = std::max<u64>(z.min_ovf, z.ovf_per_flow*(u64)S.cap_flows);
 	u64 n = st.inline_n+st.ovf_cap;
 #define PA(ptr, cnt) if ((rc = alloc((void **)&(ptr), (size_t)(cnt)*sizeof(*(ptr))))) return rc
 	PA(st.st_time, n); PA(st.st_speed, n); PA(st.st_fd, n); PA(st.ovf_top, 1);
@@ -68,17 +72,18 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 	PA(st.ev_nins, p.seg_cap); PA(st.ev_ovf, p.seg_cap); PA(st.ev_nrec, p.seg_cap); PA(st.ev_ntr, p.seg_cap); PA(st.ev_idpos, p.seg_cap);
 	PA(p.d_stage, 1);
 	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
-	PA(p.tile_mask, (size_t)(S.n_ring_tiles+1)*32); PA(p.cta_tile, 4096);
+	PA(p.tile_mask, (size_t)(S.n_ring_tiles+1)*32); PA(p.cta_tile, z.grid_max);
 	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
 	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
 	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1); PA(p.defer_long, p.seg_cap/128+2);
-	PA(p.srt_key, p.seg_cap); PA(p.srt_key2, p.seg_cap); PA(p.srt_val2, p.seg_cap); PA(p.rad_hist, 512*4096);
-	p.big_cap = 1 << 18; PA(p.big_e, p.big_cap); PA(p.big_seq, p.big_cap);
+	PA(p.srt_key, p.seg_cap); PA(p.srt_key2, p.seg_cap); PA(p.srt_val2, p.seg_cap); PA(p.rad_hist, 512*z.grid_max);
+	p.big_cap = (int)std::min<u64>(1u << 18, (u64)p.seg_cap); PA(p.big_e, p.big_cap); PA(p.big_seq, p.big_cap);
 	PA(p.pk_fd, p.seg_cap); PA(p.pk_own, p.seg_cap); PA(p.pk_speed, p.seg_cap); PA(p.pk_slot, p.seg_cap);
-	PA(p.cta_ins, 4096); PA(p.cta_rec, 4096); PA(p.cta_tr, 4096); PA(p.cta_draws, 4096);
+	PA(p.cta_ins, z.grid_max); PA(p.cta_rec, z.grid_max); PA(p.cta_tr, z.grid_max); PA(p.cta_draws, z.grid_max);
 	if (n_init) { PA(p.wave_off, n_init+2); PA(p.wave_ops, n_init); }
 	PA(p.ctl, 1);
 #undef PA
+	if (z.dry) return 0;                                              // measuring pass of an arena (ns_engine.cu)
 	cudaError_t e;
 	if ((e = cudaMemcpy(p.d_stage, &p.stage, sizeof p.stage, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
 	if ((e = cudaMemset(p.grp_cnt, 0, (size_t)(2*S.n_nodes+1)*4)) != cudaSuccess) return (int)e;
@@ -97,6 +102,9 @@ int seq_preload(void);
 // ns_init.cu
 int par_plan_init(ParScratch &p, const ns_sc_op *ops, int n0, int n_nodes);
 int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
+// ns_ens.cu: one CTA per replica (the batch engine at CTA scope)
+int ens_launch_run(const Sim *d_sims, const SeqScratch *d_scr, const ParScratch *d_pars, int n, cudaStream_t stream);
+int ens_preload(void);
 // ns_par.cu
 int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
 int par_preload(void);

@@ -176,10 +176,23 @@ __device__ void ge_chain(Ctx &c, const ParScratch &P, int g, int seg_lo, int off
 #define RAD_BINS (1 << RAD_BITS)
 struct RadSmem { int hist[RAD_BINS], base[RAD_BINS], wcnt[PAR_WARPS][RAD_BINS], scan_tmp[PAR_WARPS]; };
 static_assert(RAD_BINS == 2*PAR_THREADS, "the bin scan gives every thread two bins");
-__device__ __noinline__ void radix_pass(cgp::grid_group &grid, RadSmem &R, const int *src_key, const int *src_val, int *dst_key, int *dst_val,
+// scope of the engine's barriers: the whole cooperative grid (one simulation per GPU) or one CTA (one replica per CTA)
+#ifndef NS_SCOPE_CTA
+#define NS_GRID_T cgp::grid_group
+#define NS_SYNC(g) (g).sync()
+#define NS_NB ((int)gridDim.x)
+#define NS_BID ((int)blockIdx.x)
+#else
+struct CtaScope { };
+#define NS_GRID_T CtaScope
+#define NS_SYNC(g) __syncthreads()
+#define NS_NB 1
+#define NS_BID 0
+#endif
+__device__ __noinline__ void radix_pass(NS_GRID_T &grid, RadSmem &R, const int *src_key, const int *src_val, int *dst_key, int *dst_val,
 		int ns, int shift, int *ghist){
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int G = gridDim.x, b = blockIdx.x;
+	const int G = NS_NB, b = NS_BID;
 	const int per = (ns+G-1)/G;
 	const int c_lo = b*per < ns ? b*per : ns, c_hi = c_lo+per < ns ? c_lo+per : ns;
 	for (int i = tid; i < RAD_BINS; i += PAR_THREADS) R.hist[i] = 0;
@@ -188,7 +201,7 @@ __device__ __noinline__ void radix_pass(cgp::grid_group &grid, RadSmem &R, const
 	for (int i = c_lo+tid; i < c_hi; i += PAR_THREADS) atomicAdd(&R.hist[(src_key[i] >> shift) & (RAD_BINS-1)], 1);
 	__syncthreads();
 	for (int i = tid; i < RAD_BINS; i += PAR_THREADS) ghist[i*G+b] = R.hist[i];
-	grid.sync();
+	NS_SYNC(grid);
 	for (int bin = tid; bin < RAD_BINS; bin += PAR_THREADS) {
 		int tot = 0, before = 0;
 		const int *row = ghist+bin*G;
@@ -228,7 +241,7 @@ __device__ __noinline__ void radix_pass(cgp::grid_group &grid, RadSmem &R, const
 		if (leader) { atomicAdd(&R.base[d], __popc(peers)); R.wcnt[warp][d] = 0; }
 		__syncthreads();
 	}
-	grid.sync();
+	NS_SYNC(grid);
 }
 
 // ---------------------------------------------------------------- chains, second form
@@ -770,31 +783,6 @@ __device__ __forceinline__ void commit_small_inserts(const Sim &S, const ParStag
 			const u64 prov = NS_SEQ_PROV | ((u64)e << 24) | j;
 			if (S.l_seq[ls] == prov) S.l_seq[ls] = seq;                   // only the last add of a slot survives
 		}
-	}
-}
-__device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep, bool with_records = true){
-	unsigned nins = ps.ev_nins[e];
-	long long ovf = ps.ev_ovf[e];
-	for (unsigned j = lane0; j < nins; j += lstep) {
-		u64 si = j < NS_STAGE_INLINE ? (u64)e*NS_STAGE_INLINE+j : ps.inline_n+(u64)ovf+(j-NS_STAGE_INLINE);
-		int fd = ps.st_fd[si];
-		u64 seq = seq0+j;
-		if (fd >= 0) {
-			u64 slot = seq & (S.ring_cap-1);
-			double t = ps.st_time[si];
-			S.q_time[slot] = t; S.q_speed[slot] = ps.st_speed[si]; S.q_fd[slot] = fd; S.q_gen[slot] = S.f_gen[fd >> 1];
-			double *tm = &S.q_tmin[slot >> NS_TILE_SHIFT];
-			if (*(volatile double *)tm > t) tmin_lower(tm, t);            // minima only fall during a commit
-		} else if (fd != NS_HOLE_PURE) {
-			int ls = -fd-1;
-			u64 prov = NS_SEQ_PROV | ((u64)e << 24) | j;
-			if (S.l_seq[ls] == prov) S.l_seq[ls] = seq;               // only the last add of a slot survives
-		}
-	}
-	if (lane0 == 0 && with_records) {
-		unsigned nrec = ps.ev_nrec[e];
-		if (nrec) { const uint8_t *src = ps.st_rec+(u64)e*NS_STAGE_REC; uint8_t *dst = S.rec+rec0; for (unsigned k = 0; k < nrec; k++) dst[k] = src[k]; }
-		if (ps.ev_ntr[e] && tr0 < S.tr_cap) S.tr[tr0] = ps.st_tr[e];
 	}
 }
 

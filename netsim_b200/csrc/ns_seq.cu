@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(32) k_exec_ops(const Sim *sp, int n_ops){
 __global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n){
 	int s = blockIdx.x;
 	if (s >= n) return;
-	seq_run(&sims[s], scr[s], threadIdx.x);
+	__shared__ WideSmem W;
+	seq_run(&sims[s], scr[s], threadIdx.x, &W);
 }
 
 static int launched(void){ cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : (int)e; }

@@ -65,17 +65,23 @@ __device__ int seq_collect_ring(Ctx &c, double m){
 			u64 at = a0+b;
 			u64 base = at << NS_TILE_SHIFT;
 			double nm = NS_INF;
-			for (int i = 0; i < NS_TILE; i += 32) {
-				u64 seq = base+i+lane;
-				double t = S.q_time[seq & smask];
-				bool match = t == m && seq >= c.head && seq < c.tail;
-				unsigned mm = __ballot_sync(FULLMASK, match);
-				if (mm) {
-					if (nb+__popc(mm) > S.batch_cap) return -1;
-					if (match) { int pos = nb+__popc(mm & ((1u << lane)-1)); S.b_seq[pos] = seq; }
-					nb += __popc(mm);
+			for (int i0 = 0; i0 < NS_TILE; i0 += 32*8) {              // 8 independent loads in flight per lane
+				double tv[8];
+				#pragma unroll
+				for (int u = 0; u < 8; u++) tv[u] = S.q_time[(base+i0+32*u+lane) & smask];
+				#pragma unroll
+				for (int u = 0; u < 8; u++) {
+					u64 seq = base+i0+32*u+lane;
+					double t = tv[u];
+					bool match = t == m && seq >= c.head && seq < c.tail;
+					unsigned mm = __ballot_sync(FULLMASK, match);
+					if (mm) {
+						if (nb+__popc(mm) > S.batch_cap) return -1;
+						if (match) { int pos = nb+__popc(mm & ((1u << lane)-1)); S.b_seq[pos] = seq; }
+						nb += __popc(mm);
+					}
+					if (!match) nm = fmin(nm, t);
 				}
-				if (!match) nm = fmin(nm, t);
 			}
 			nm = warp_min_d(nm);
 			if (lane == 0) S.q_tmin[at & tmask] = nm;
@@ -99,14 +105,20 @@ __device__ __noinline__ int seq_collect_l(Ctx &c, double m, const SeqScratch &sc
 			int tile = t0+b;
 			int base = tile << NS_TILE_SHIFT;
 			double nm = NS_INF;
-			for (int i = 0; i < NS_TILE; i += 32) {
-				int slot = base+i+lane;
-				double tt = slot < S.n_l ? S.l_time[slot] : NS_INF;
-				bool match = tt == m;
-				unsigned mm = __ballot_sync(FULLMASK, match);
-				if (match) { int pos = nl+__popc(mm & ((1u << lane)-1)); sc.lb_seq[pos] = S.l_seq[slot]; sc.lb_ref[pos] = slot; }
-				nl += __popc(mm);
-				if (!match) nm = fmin(nm, tt);
+			for (int i0 = 0; i0 < NS_TILE; i0 += 32*8) {              // 8 independent loads in flight per lane
+				double tv[8];
+				#pragma unroll
+				for (int u = 0; u < 8; u++) { int slot = base+i0+32*u+lane; tv[u] = slot < S.n_l ? S.l_time[slot] : NS_INF; }
+				#pragma unroll
+				for (int u = 0; u < 8; u++) {
+					int slot = base+i0+32*u+lane;
+					double tt = tv[u];
+					bool match = tt == m;
+					unsigned mm = __ballot_sync(FULLMASK, match);
+					if (match) { int pos = nl+__popc(mm & ((1u << lane)-1)); sc.lb_seq[pos] = S.l_seq[slot]; sc.lb_ref[pos] = slot; }
+					nl += __popc(mm);
+					if (!match) nm = fmin(nm, tt);
+				}
 			}
 			nm = warp_min_d(nm);
 			if (lane == 0) S.l_tmin[tile] = nm;
@@ -232,6 +244,168 @@ __device__ __forceinline__ bool seq_should_stop(Ctx &c){
 	return false;
 }
 
+// the staged event_adds / records of one event, written at their final positions (shared with the grid engine)
+__device__ __forceinline__ void par_commit_event(const Sim &S, const ParStage &ps, int e, u64 seq0, u64 rec0, u64 tr0, int lane0, int lstep, bool with_records = true){
+	unsigned nins = ps.ev_nins[e];
+	long long ovf = ps.ev_ovf[e];
+	for (unsigned j = lane0; j < nins; j += lstep) {
+		u64 si = j < NS_STAGE_INLINE ? (u64)e*NS_STAGE_INLINE+j : ps.inline_n+(u64)ovf+(j-NS_STAGE_INLINE);
+		int fd = ps.st_fd[si];
+		u64 seq = seq0+j;
+		if (fd >= 0) {
+			u64 slot = seq & (S.ring_cap-1);
+			double t = ps.st_time[si];
+			S.q_time[slot] = t; S.q_speed[slot] = ps.st_speed[si]; S.q_fd[slot] = fd; S.q_gen[slot] = S.f_gen[fd >> 1];
+			double *tm = &S.q_tmin[slot >> NS_TILE_SHIFT];
+			if (*(volatile double *)tm > t) tmin_lower(tm, t);            // minima only fall during a commit
+		} else if (fd != NS_HOLE_PURE) {
+			int ls = -fd-1;
+			u64 prov = NS_SEQ_PROV | ((u64)e << 24) | j;
+			if (S.l_seq[ls] == prov) S.l_seq[ls] = seq;               // only the last add of a slot survives
+		}
+	}
+	if (lane0 == 0 && with_records) {
+		unsigned nrec = ps.ev_nrec[e];
+		if (nrec) { const uint8_t *src = ps.st_rec+(u64)e*NS_STAGE_REC; uint8_t *dst = S.rec+rec0; for (unsigned k = 0; k < nrec; k++) dst[k] = src[k]; }
+		if (ps.ev_ntr[e] && tr0 < S.tr_cap) S.tr[tr0] = ps.st_tr[e];
+	}
+}
+
+// ---------------------------------------------------------------- wide runs: one event per LANE
+// A run of SPEED_CHANGE events of one timestamp, handled 32 at a time by the lanes of the stepping warp.
+// Same legality argument as the grid engine (SURVEY §8a conflict analysis): the unit of mutual exclusion is
+// the (node, direction) group, so inside a chunk of 32 consecutive events a lane may run as soon as every
+// EARLIER event of its group is done; events whose solve takes one of bwspread's O(1) exits run as scalar
+// threads with their event_adds / records staged in shared memory (the latency of 32 dependent table walks
+// overlaps instead of adding up).  An event that needs a full spread waits until everything before it has
+// been committed and is then handled by the whole warp, unstaged, at its final sequence numbers.  The
+// commit is an in-order prefix scan, so sequence numbers, random() burns and the record stream are those of
+// the strictly sequential order.  Not used for relay topologies (a range with a producer that is also
+// consumed couples groups) and in host-callback mode (every event stops).
+#define NS_WIDE 32
+struct WideSmem {
+	double st_time[NS_STAGE_INLINE*NS_WIDE], st_speed[NS_STAGE_INLINE*NS_WIDE];
+	int st_fd[NS_STAGE_INLINE*NS_WIDE];
+	ns_trace_row32 st_tr[NS_WIDE];
+	long long ev_ovf[NS_WIDE];
+	u64 ovf_top;
+	unsigned ev_nins[NS_WIDE], ev_idpos[NS_WIDE];
+	uint8_t ev_nrec[NS_WIDE], ev_ntr[NS_WIDE];
+	uint8_t st_rec[NS_STAGE_REC*NS_WIDE];
+	ParStage ps;
+};
+__device__ __forceinline__ void wide_init(WideSmem &W, int lane){
+	if (lane == 0) {
+		ParStage &ps = W.ps;
+		ps.st_time = W.st_time; ps.st_speed = W.st_speed; ps.st_fd = W.st_fd;
+		ps.inline_n = NS_STAGE_INLINE*NS_WIDE; ps.ovf_cap = 0; ps.ovf_top = &W.ovf_top;
+		ps.st_rec = W.st_rec; ps.st_tr = W.st_tr;
+		ps.ev_nins = W.ev_nins; ps.ev_ovf = W.ev_ovf; ps.ev_nrec = W.ev_nrec; ps.ev_ntr = W.ev_ntr; ps.ev_idpos = W.ev_idpos;
+		W.ovf_top = 0;
+	}
+	__syncwarp();
+}
+
+// in-order commit of the staged events [a, b) of the chunk (one lane per event)
+__device__ __forceinline__ void wide_commit(Ctx &c, WideSmem &W, int a, int b){
+	if (a >= b) return;
+	const Sim &S = *c.S;
+	const int lane = c.lane;
+	const bool mine = lane >= a && lane < b;
+	unsigned ni = mine ? W.ev_nins[lane] : 0u, nr = mine ? W.ev_nrec[lane] : 0u, nt = mine ? W.ev_ntr[lane] : 0u;
+	unsigned xi = ni, xr = nr, xt = nt;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		unsigned yi = __shfl_up_sync(FULLMASK, xi, d), yr = __shfl_up_sync(FULLMASK, xr, d), yt = __shfl_up_sync(FULLMASK, xt, d);
+		if (lane >= d) { xi += yi; xr += yr; xt += yt; }
+	}
+	const unsigned ti = __shfl_sync(FULLMASK, xi, 31), tr = __shfl_sync(FULLMASK, xr, 31), tt = __shfl_sync(FULLMASK, xt, 31);
+	if (c.tail+ti-c.head > S.ring_cap) { set_status(c, NS_E_RING_FULL); return; }
+	if (S.want_rec && c.rec_len+tr > S.rec_cap) { set_status(c, NS_E_RECORDS_LOST); return; }
+	if (mine && (ni|nr|nt)) par_commit_event(S, W.ps, lane, c.tail+(xi-ni), c.rec_len+(xr-nr), c.tr_len+(xt-nt), 0, 1, true);
+	c.tail += ti; c.burns += ti;
+	if (S.want_rec) c.rec_len += tr;
+	if (S.want_tr) { c.tr_len += tt; if (c.tr_len > S.tr_cap) c.tr_len = S.tr_cap; }
+	__syncwarp();
+}
+
+#ifndef NS_NO_WIDE
+// ring entries b_seq[i, end) of timestamp m, all SPEED_CHANGE events; advances i past what it handled
+__device__ __noinline__ void seq_wide_run(Ctx &c, double m, int &i, int end, WideSmem &W){
+	const Sim &S = *c.S;
+	const int lane = c.lane;
+	const u64 smask = S.ring_cap-1;
+	while (i < end) {
+		if (seq_should_stop(c)) return;
+		int n = end-i < NS_WIDE ? end-i : NS_WIDE;
+		{	// a max_events bound counts handled (live) events: never take more entries than the budget allows
+			const u64 ev_max = c.st->max_events;
+			if (ev_max) { const u64 left = ev_max-c.st->cnt[NS_CNT_EVENTS]; if ((u64)n > left) n = (int)left; }
+		}
+		u64 seq = 0, slot = 0; int f = -1, dir = 0, key = -1-lane; double speed = 0; bool live = false;
+		if (lane < n) {
+			seq = S.b_seq[i+lane]; slot = seq & smask;
+			if (S.q_time[slot] == m) {
+				const int fd = S.q_fd[slot];
+				f = fd >> 1; dir = fd & 1; speed = S.q_speed[slot];
+				live = S.f_gen[f] == S.q_gen[slot] && S.f_alive[f];
+				if (live) key = S.f_peer[dir][f]*2+dir;
+				else S.q_time[slot] = NS_INF;                             // cancelled by flow_close (flow.c:260-270): popped, not handled
+			}
+			W.ev_nins[lane] = 0; W.ev_nrec[lane] = 0; W.ev_ntr[lane] = 0; W.ev_ovf[lane] = -1;
+		}
+		__syncwarp();
+		const unsigned peers = __match_any_sync(FULLMASK, key);
+		const unsigned pred = peers & ((1u << lane)-1u);                  // earlier events of my group
+		unsigned done = __ballot_sync(FULLMASK, !live);
+		int committed = 0;
+		u64 lc[LC_N];
+		#pragma unroll
+		for (int q = 0; q < LC_N; q++) lc[q] = 0;
+		while (done != FULLMASK) {
+			const bool ready = !((done >> lane) & 1u) && (pred & ~done) == 0u;
+			const bool full = ready && sc_needs_full_spread(S, f, dir, speed);
+			if (ready && !full) {
+				Ctx cs = c;
+				cs.lane = 0; cs.par = 1; cs.scalar = 1; cs.ps = &W.ps;
+				cs.ev = (unsigned)lane; cs.lseq = 0; cs.rec_n = 0; cs.tr_n = 0; cs.ovf_base = -1;
+				#pragma unroll
+				for (int q = 0; q < LC_N; q++) cs.lc[q] = 0;
+				cs.lc[LC_EVENTS] = 1; cs.lc[LC_SPEED_CHANGE] = 1;
+				handle_speed_change(cs, f, dir, speed);
+				W.ev_nins[lane] = cs.lseq; W.ev_nrec[lane] = (uint8_t)cs.rec_n; W.ev_ntr[lane] = (uint8_t)cs.tr_n;
+				S.q_time[slot] = NS_INF;                                  // event_pop
+				#pragma unroll
+				for (int q = 0; q < LC_N; q++) lc[q] += cs.lc[q];
+			}
+			__syncwarp();
+			const unsigned newly = __ballot_sync(FULLMASK, ready && !full);
+			done |= newly;
+			if (newly == 0u) {
+				// no lane could run: the earliest pending event needs a full spread (everything before it is done)
+				const int F = __ffs(~done)-1;
+				wide_commit(c, W, committed, F);
+				const u64 sF = __shfl_sync(FULLMASK, seq, F);
+				if (!c.st->status) seq_handle_ring(c, m, sF);
+				committed = F+1;
+				done |= 1u << F;
+			}
+		}
+		wide_commit(c, W, committed, n);
+		#pragma unroll
+		for (int q = 0; q < LC_N; q++) for (int d = 16; d; d >>= 1) lc[q] += __shfl_xor_sync(FULLMASK, lc[q], d);
+		L0 {
+			u64 *cn = c.st->cnt;
+			cn[NS_CNT_EVENTS] += lc[LC_EVENTS]; cn[NS_CNT_SPEED_CHANGE] += lc[LC_SPEED_CHANGE]; cn[NS_CNT_SOLVES] += lc[LC_SOLVES];
+			cn[NS_CNT_FULL_SPREADS] += lc[LC_FULL_SPREADS]; cn[NS_CNT_FLOW_VISITS] += lc[LC_FLOW_VISITS]; cn[NS_CNT_RETIMES] += lc[LC_RETIMES];
+			cn[NS_CNT_PAR_EVENTS] += lc[LC_EVENTS];
+		}
+		__syncwarp();
+		i += n;
+	}
+}
+#endif
+
 // put the unprocessed tail of a batch back under the tile minima (max_events / sim_end mid-batch)
 __device__ __noinline__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
 	const Sim &S = *c.S;
@@ -249,21 +423,38 @@ __device__ __noinline__ void seq_restore(Ctx &c, double m, int i, int nr, int j,
 
 // process batch entries [i,nr) x [j,nl) in sequence order, strictly sequentially; stops early on
 // status / sim_end / max_events / host stop and reports how far it got
-__device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &j, int nl, const SeqScratch &sc){
+#define NS_WIDE_MIN_RUN 4
+__device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &j, int nl, const SeqScratch &sc, WideSmem *W){
 	const Sim &S = *c.S;
+#ifdef NS_NO_WIDE      // the grid engine's translation unit: its sparse phases go to k_run_seq anyway, and k_run_par's code layout is touchy (profiles/README.md r1-f)
+	const bool wide_on = false;
+#else
+	const bool wide_on = W && (S.features & NS_FEAT_WIDE) && !c.st->host_mask;
+#endif
 	while (i < nr || j < nl) {
 		if (seq_should_stop(c)) return;
 		u64 sr = i < nr ? S.b_seq[i] : ~0ull;
 		u64 sl = j < nl ? sc.lb_seq[j] : ~0ull;
-		if (sr < sl) { seq_handle_ring(c, m, sr); i++; }
+		if (sr < sl) {
+			if (wide_on && nr-i >= NS_WIDE_MIN_RUN && !c.st->relay_seen) {
+				// the run of SPEED_CHANGE events up to the next long-lived event of the batch
+				int end = nr;
+				if (j < nl) { int lo = i+1, hi = nr; while (lo < hi) { int mid = (lo+hi) >> 1; if (S.b_seq[mid] < sl) lo = mid+1; else hi = mid; } end = lo; }
+#ifndef NS_NO_WIDE
+				if (end-i >= NS_WIDE_MIN_RUN) { seq_wide_run(c, m, i, end, *W); continue; }
+#endif
+			}
+			seq_handle_ring(c, m, sr); i++;
+		}
 		else { seq_handle_l(c, m, sl, sc.lb_ref[j]); j++; }
 	}
 }
 
 #define NS_SPARSE_MAX_HIT_TILES 4
-__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
+__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem *W){
 	Ctx c;
 	ctx_load(c, Sp, lane);
+	if (W) wide_init(*W, lane);
 	if (c.st->pending_close >= 0) {                                   // flow_done_cleaner of the event the host just saw
 		int f = c.st->pending_close;
 		WSYNC();
@@ -303,7 +494,7 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane){
 		cnt_add(c, NS_CNT_BATCHES, 1);
 		L0 { if ((u64)(nr+nl) > c.st->cnt[NS_CNT_MAX_BATCH]) c.st->cnt[NS_CNT_MAX_BATCH] = nr+nl; }
 		int pi = 0, pj = 0;
-		seq_process(c, m, pi, nr, pj, nl, sc);
+		seq_process(c, m, pi, nr, pj, nl, sc, W);
 		if (pi < nr || pj < nl) seq_restore(c, m, pi, nr, pj, nl, sc);   // max_events / sim_end mid-batch
 		__syncwarp();
 	}

@@ -27,6 +27,7 @@
 #define FULLMASK 0xffffffffu
 #define NS_FEAT_CHAIN2 1u   /* small-node event chains: scalar recurrence pass + lane-parallel emission pass */
 #define NS_FEAT_HUBCTA 2u   /* full spreads of large SND groups by a whole CTA from shared memory */
+#define NS_FEAT_WIDE 4u     // single-warp engine: runs of SPEED_CHANGE events handled one event per lane (ns_seq.cuh)
 #define NS_FEAT_ALL 0xffffu
 
 enum { SND = 0, RCV = 1 };

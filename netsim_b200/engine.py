@@ -78,6 +78,7 @@ def lib():
         L.ns_ens_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.POINTER(Opts)]
         L.ns_ens_run.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]
         L.ns_ens_digests.argtypes = [C.c_void_p, C.POINTER(Digest), C.c_int]
+        L.ns_ens_counters_sum.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.ns_ens_launches.restype = C.c_uint64
         L.ns_ens_launches.argtypes = [C.c_void_p]
         L.ns_ens_destroy.argtypes = [C.c_void_p]
@@ -255,16 +256,18 @@ class Engine:
 
 
 class Ensemble:
-    """Independent replicas side by side on one GPU (ns_ens_*), one warp each."""
+    """Independent replicas side by side on one GPU (ns_ens_*): one CTA per replica (mode AUTO, the batch engine at
+    CTA scope) or one warp per replica (mode SEQ)."""
 
-    def __init__(self, scenarios, device: int = 0, records: bool = True, ring_cap: int = 0, record_cap: int = 0):
+    def __init__(self, scenarios, device: int = 0, records: bool = True, ring_cap: int = 0, record_cap: int = 0,
+                 mode: int = MODE_AUTO, cap_flows: int = 0):
         self.L = lib()
         n = len(scenarios)
         self._keep = [bytes(s) for s in scenarios]
         arr = (C.c_char_p * n)(*self._keep)
         lens = (C.c_size_t * n)(*[len(s) for s in self._keep])
-        o = Opts(device=device, mode=MODE_SEQ, want_records=int(records), want_trace=0, ring_cap=ring_cap,
-                 record_cap=record_cap)
+        o = Opts(device=device, mode=mode, want_records=int(records), want_trace=0, ring_cap=ring_cap,
+                 record_cap=record_cap, cap_flows=cap_flows)
         self.h = C.c_void_p()
         self.n = n
         rc = self.L.ns_ens_create(C.byref(self.h), arr, lens, n, C.byref(o))
@@ -286,6 +289,13 @@ class Ensemble:
         if rc:
             raise NsError(rc, "ns_ens_digests")
         return [{k: getattr(x, k) for k, _ in Digest._fields_} for x in d]
+
+    def counters_sum(self) -> dict:
+        out = (C.c_uint64 * len(COUNTERS))()
+        rc = self.L.ns_ens_counters_sum(self.h, out)
+        if rc:
+            raise NsError(rc, "ns_ens_counters_sum")
+        return {k: int(out[i]) for i, k in enumerate(COUNTERS)}
 
     @property
     def launches(self) -> int:

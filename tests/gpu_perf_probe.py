@@ -56,19 +56,21 @@ if __name__ == "__main__":
         nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 128
         npeers = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
         maxev = int(sys.argv[4]) if len(sys.argv) > 4 else 200000
-        scs = [S.swarm_fast(npeers, max(2, npeers // 250), n_catalogue=16, seeds_per_peer=4, seed=100 + i, rand_seed=1 + i).to_bytes() for i in range(nrep)]
-        t0 = time.time()
-        ens = E.Ensemble(scs, records=True, ring_cap=1 << 22, record_cap=maxev * 48 + (16 << 20))
-        t1 = time.time()
-        ens.run(maxev)
-        t2 = time.time()
-        dg = ens.digests()
-        ev = sum(d["events"] for d in dg)
-        bad = [d["status"] for d in dg if d["status"] != 0]
-        print(f"ensemble {nrep} x swarm{npeers}: create+init {t1-t0:.1f}s run device {ens.device_ms:.1f} ms -> {ev/(ens.device_ms/1e3):.0f} ev/s aggregate; events {ev}; bad status {bad[:5]}", flush=True)
+        hub_frac = float(sys.argv[5]) if len(sys.argv) > 5 else 0.1
+        scs = [S.swarm_fast(npeers, max(2, npeers // 250), n_catalogue=16, seeds_per_peer=4, seed=100 + i, rand_seed=1 + i, hub_frac=hub_frac).to_bytes() for i in range(nrep)]
         o = pyoracle.Oracle(scs[3], trace=False); o.run(maxev)
-        print("   replica 3 digest ok:", dg[3]["record_hash"] == E.stream_hash(o.records()), dg[3]["events"], o.counters()["events"])
-        ens.close()
+        for mname, mode in (("cta/replica", E.MODE_AUTO), ("warp/replica", E.MODE_SEQ)):
+            t0 = time.time()
+            ens = E.Ensemble(scs, records=True, ring_cap=1 << 21, record_cap=8 << 20, mode=mode)
+            t1 = time.time()
+            ens.run(maxev)
+            t2 = time.time()
+            dg = ens.digests()
+            ev = sum(d["events"] for d in dg)
+            bad = [d["status"] for d in dg if d["status"] != 0]
+            print(f"ensemble {nrep} x swarm{npeers} hub_frac {hub_frac} [{mname}]: create+init {t1-t0:.1f}s run device {ens.device_ms:.1f} ms wall {t2-t1:.2f}s -> {ev/(ens.device_ms/1e3):.0f} ev/s aggregate; "
+                  f"events {ev}; launches {ens.launches}; bad status {bad[:5]}; replica 3 digest ok: {dg[3]['record_hash'] == E.stream_hash(o.records())} {dg[3]['events']} {o.counters()['events']}", flush=True)
+            ens.close()
     elif which == "sparse":
         # small batches: a swarm run to completion (FLOW_DONE dominated tail) and a churn script
         for name, sc in (("complete2000", S.swarm(2000, 8, n_catalogue=8, seeds_per_peer=3, mean_strips=4.0, res_len=40000)),

@@ -106,9 +106,10 @@ def test_reference_abort_is_reported(built):
     assert found >= 1
 
 
-def test_ensemble_digests_match_single_runs(built):
+@pytest.mark.parametrize("mode", [E.MODE_AUTO, E.MODE_SEQ], ids=["cta_per_replica", "warp_per_replica"])
+def test_ensemble_digests_match_single_runs(built, mode):
     scs = [S.random_small(300 + i, n_nodes=7, n_flows=10).to_bytes() for i in range(12)]
-    ens = E.Ensemble(scs)
+    ens = E.Ensemble(scs, mode=mode)
     ens.run(0)
     dig = ens.digests()
     for i, b in enumerate(scs):
@@ -120,6 +121,25 @@ def test_ensemble_digests_match_single_runs(built):
             assert dig[i]["solves"] == o.counters()["solves"]
             assert dig[i]["record_bytes"] == len(o.records())
             assert dig[i]["record_hash"] == E.stream_hash(o.records())
+    ens.close()
+
+
+@pytest.mark.parametrize("mode", [E.MODE_AUTO, E.MODE_SEQ], ids=["cta_per_replica", "warp_per_replica"])
+def test_ensemble_swarm_replicas_with_record_folding(built, mode):
+    """replicas big enough for the batch engine (grouping, chains, hub spreads inside one CTA), to completion
+    (FLOW_DONE, merges, closes), with a record buffer so small that it is folded into the running digest many times"""
+    scs = [S.swarm(300 + 40 * i, 3, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0, res_len=30000, seed=50 + i).to_bytes()
+           for i in range(6)]
+    ens = E.Ensemble(scs, mode=mode, record_cap=1 << 18, ring_cap=1 << 18)
+    ens.run(0)
+    dig = ens.digests()
+    for i, b in enumerate(scs):
+        o = pyoracle.Oracle(b, trace=False)
+        assert o.run(0) == 0
+        assert dig[i]["status"] == 0
+        assert dig[i]["events"] == o.counters()["events"]
+        assert dig[i]["record_bytes"] == len(o.records()) > (1 << 19)
+        assert dig[i]["record_hash"] == E.stream_hash(o.records())
     ens.close()
 
 

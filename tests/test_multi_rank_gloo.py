@@ -70,3 +70,51 @@ def test_two_rank_replicas_gather():
     o = pyoracle.Oracle(sc.to_bytes(), trace=False)
     o.run(20000)
     assert digs[1][2] == E.stream_hash(o.records()) & 0x7FFFFFFFFFFFFFFF
+
+
+def _ens_worker(rank, world, port, out):
+    """bench.py --workload ensemble, host logic: replica i -> rank i mod N, every rank fills its rows of the digest table,
+    one all_reduce leaves the whole table on every rank (oracle instead of the device: no GPU here)"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import argparse
+    import bench
+    from netsim_b200 import engine as E
+    from oracle import pyoracle
+    n_total = 5
+    args = argparse.Namespace(ens_peers=200)
+    tab = torch.zeros(n_total, 4, dtype=torch.int64)
+    for i in range(rank, n_total, world):
+        o = pyoracle.Oracle(bench.ens_script(args, i).to_bytes(), trace=False)
+        assert o.run(0) == 0
+        tab[i] = torch.tensor([o.counters()["events"], o.counters()["solves"], len(o.records()), E.stream_hash(o.records()) & 0x7FFFFFFFFFFFFFFF])
+    dist.all_reduce(tab)
+    if rank == 0:
+        out.put(tab.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ensemble_digest_table():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_ens_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    tab = q.get(timeout=120)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    # the gathered table equals what ONE process computes for all replicas: sharding does not change a digest
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    from netsim_b200 import engine as E
+    from oracle import pyoracle
+    for i, row in enumerate(tab):
+        o = pyoracle.Oracle(bench.ens_script(argparse.Namespace(ens_peers=200), i).to_bytes(), trace=False)
+        o.run(0)
+        assert row == [o.counters()["events"], o.counters()["solves"], len(o.records()), E.stream_hash(o.records()) & 0x7FFFFFFFFFFFFFFF]
+    assert len({r[3] for r in tab}) == len(tab)

@@ -2,6 +2,7 @@
 pinned to the compiled reference by tests/test_oracle_golden.py) and committed as tests/golden/bench_expected.json.
 bench.py compares the device engine's digest after its last window against it (outside the timed region).
     python tools/make_bench_expected.py [ranks] [total_events]
+    python tools/make_bench_expected.py ensemble [peers]        digests of sampled replicas of bench.py --workload ensemble
 """
 import json
 import os
@@ -29,6 +30,34 @@ def one(rank, total_events, peers, hubs, hub_frac):
     o.close()
     return out
 
+
+def ens_one(seed_index, peers):
+    import argparse
+    import bench
+    from netsim_b200 import engine as E
+    from oracle import pyoracle
+    sc = bench.ens_script(argparse.Namespace(ens_peers=peers), seed_index)
+    o = pyoracle.Oracle(sc.to_bytes(), trace=False, records=True)
+    st = o.run(0)
+    c = o.counters()
+    rec = o.records()
+    out = {"seed": seed_index, "status": st, "events": c["events"], "solves": c["solves"], "record_bytes": len(rec), "record_hash": E.stream_hash(rec)}
+    o.close()
+    return out
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ensemble":
+    peers = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
+    seeds = [0, 1, 2, 3, 7, 100, 511, 1023]
+    with ProcessPoolExecutor(max_workers=4) as ex:
+        res = list(ex.map(ens_one, seeds, [peers] * len(seeds)))
+    path = os.path.join(ROOT, "tests", "golden", "bench_expected.json")
+    cur = json.load(open(path))
+    for r in res:
+        cur[f"ensemble,peers={peers},seed={r['seed']}"] = r
+        print(r)
+    json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    sys.exit(0)
 
 if __name__ == "__main__":
     ranks = int(sys.argv[1]) if len(sys.argv) > 1 else 1
