@@ -41,6 +41,8 @@ B_RETIME = 92 + 120   # completion re-time of one flow + the byte-progress updat
 
 
 def workload(args, rank):
+    if args.workload == "churn":
+        return churn_workload(args, rank)
     from netsim_b200 import scenario as S
     return S.swarm_fast(args.peers, args.hubs, n_catalogue=64, seeds_per_peer=8, mean_strips=9.0,
                         hub_frac=args.hub_frac, res_len=600000, seed=12345 + rank, rand_seed=1 + rank)
@@ -156,7 +158,32 @@ def _guard_stdout():
     os.dup2(2, 1)
 
 
+CHURN_METRIC = "simulated events/s (churn: 1M users + 1024 servers, Poisson arrivals/departures, one simulation per GPU)"
+
+
+def churn_workload(args, rank):
+    """BASELINE.json configs[3]: 1M users + 1024 servers; a warm swarm of --churn-init users is connected by
+    the module's init, the others arrive as a Poisson process of 1000/s; every user leaves after an exponential session (its
+    flow is closed); timestamps on a 10 ms grid, so a batch holds ~10 arrivals + ~10 departures and the speed events they trigger"""
+    from netsim_b200 import scenario as S
+    return S.churn_fast(args.churn_users, 1024, rate=1000.0, mean_session=args.churn_session, sim_end=args.churn_end,
+                        init_users=args.churn_init, seed=2024 + rank)
+
+
+def churn_config(args):
+    return {"workload": f"BASELINE.json configs[3]: churn script, {args.churn_users} users + 1024 servers, {args.churn_init} users connected at init, Poisson "
+                        f"arrivals 1000/s, exponential sessions of mean {args.churn_session}s (SURVEY §8d says 600 s from a cold start: a warm start with shorter "
+                        f"sessions reaches the saturated steady state — ~100 flows per server, every arrival/departure a full spread — that "
+                        f"the reference arm can still set up), 10 ms timestamp grid, {args.churn_end} sim-s; records on; step = window of "
+                        f"{args.events_per_step} events; timed range = events [{args.warmup * args.events_per_step}, "
+                        f"{(args.warmup + args.steps) * args.events_per_step}) of the script, the same for both arms",
+            "users": args.churn_users, "servers": 1024, "init_users": args.churn_init, "events_per_step": args.events_per_step,
+            "working_set": "1M-node tables + flows + pending-event ring exceed the 126 MB L2; no explicit L2 flush"}
+
+
 def config_for(args):
+    if args.workload == "churn":
+        return churn_config(args)
     flows_k = args.peers * 10 // 1000
     return {"workload": f"BASELINE.json configs[2]: p2p swarm script, {args.peers} peers + {args.hubs} hubs, ~{flows_k}k flows established at init, "
                         f"records on; step = window of {args.events_per_step} events; timed range = events "
@@ -193,6 +220,8 @@ def expected_digest(args, rank, total_events):
         tab = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_expected.json")))
     except Exception:
         return None
+    if args.workload == "churn":
+        return tab.get(f"churn,users={args.churn_users},init={args.churn_init},session={args.churn_session},end={args.churn_end},rank={rank},events={total_events}")
     return tab.get(f"peers={args.peers},hubs={args.hubs},hub_frac={args.hub_frac},rank={rank},events={total_events}")
 
 
@@ -212,6 +241,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", type=int, default=1024, help="--workload ensemble: replicas per ensemble (all ranks together)")
     ap.add_argument("--ens-peers", type=int, default=10000, help="--workload ensemble: peers per replica")
+    ap.add_argument("--churn-users", type=int, default=1000000)
+    ap.add_argument("--churn-init", type=int, default=100000)
+    ap.add_argument("--churn-session", type=float, default=100.0)
+    ap.add_argument("--churn-end", type=float, default=60.0)
     args = ap.parse_args()
     if args.workload == "ensemble" and "--steps" not in sys.argv:
         args.steps = 1                                       # one ensemble of --replicas replicas IS the config
@@ -219,8 +252,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload != "swarm100k":
+    if WORKLOADS[args.workload] is not None:
         return WORKLOADS[args.workload](args, rank, local_rank, world)
+    metric = CHURN_METRIC if args.workload == "churn" else METRIC
     config = config_for(args)
     eps = args.events_per_step
     total_steps = args.steps + args.warmup
@@ -235,7 +269,7 @@ def main():
             emit({"impl": "reference", "unavailable": (r or {}).get("error", "oracle/_ref not built")})
             return 0
         val = r["events_per_s"]
-        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        line = {"metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
                 "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_proc, "kind": "reference",
@@ -374,7 +408,7 @@ def main():
                    "parallel_fraction": d["par_events"] / max(1, events), "solves_per_s": solves_all / (dev_ms_max / 1e3),
                    "full_spreads": d["full_spreads"], "flow_visits": d["flow_visits"], "record_hash": dig["record_hash"], "parity": parity,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"})
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "ours", "config": config,
             "clocks": sampler.summary(),
@@ -602,7 +636,7 @@ def ensemble_main(args, rank, local_rank, world):
     return 0
 
 
-WORKLOADS = {"swarm100k": None, "ensemble": ensemble_main}
+WORKLOADS = {"swarm100k": None, "churn": None, "ensemble": ensemble_main}
 
 
 if __name__ == "__main__":

@@ -749,6 +749,14 @@ __global__ void __launch_bounds__(256) k_ens_drain(const Sim *sims, EnsAcc *acc,
 		atomicAdd(n_more, 1);
 	}
 }
+// hand-overs between the two replica engines (CTA per replica <-> warp per replica) asked for during the round
+__global__ void k_ens_handover(const Sim *sims, int n, int *n_more){
+	for (int s = blockIdx.x*blockDim.x+threadIdx.x; s < n; s += gridDim.x*blockDim.x) {
+		SimState *st = sims[s].st;
+		if (st->status) continue;
+		if (st->want_sparse || st->want_dense) { st->want_sparse = 0; st->want_dense = 0; atomicAdd(n_more, 1); }
+	}
+}
 __global__ void __launch_bounds__(256) k_ens_digest(const Sim *sims, const EnsAcc *acc, int n, ns_digest *out){
 	const int s = blockIdx.x;
 	if (s >= n) return;
@@ -856,8 +864,17 @@ extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms)
 		CK(cudaMemcpyAsync(&e->sims[i].S.st->max_events, &max_events_each, 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaEventRecord(e->e0, e->stream));
 	for (int round = 0; round < 1 << 20; round++) {
-		{ int rc = e->cta_engine ? ens_launch_run(e->d_sims, e->d_scr, e->d_pars, e->n, e->stream) : seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc; }
 		CK(cudaMemsetAsync(e->d_more, 0, 4, e->stream));
+		if (e->cta_engine) {
+			// dense phases: one CTA per replica; sparse phases (streaks of tiny batches): one warp per replica, so that
+			// every replica of the ensemble is resident at once.  A replica switches engine at most once per round.
+			int rc = ens_launch_run(e->d_sims, e->d_scr, e->d_pars, e->n, e->stream); if (rc) return rc;
+			rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream, 1); if (rc) return rc;
+			k_ens_handover<<<(e->n+127)/128, 128, 0, e->stream>>>(e->d_sims, e->n, e->d_more);
+			e->launches += 2;
+		} else {
+			int rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc;
+		}
 		k_ens_drain<<<e->n, 256, 0, e->stream>>>(e->d_sims, e->d_acc, e->n, e->d_more);
 		CK(cudaGetLastError());
 		e->launches += 2;

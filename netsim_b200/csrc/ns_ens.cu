@@ -3,6 +3,9 @@
 // commit), its barriers are __syncthreads, and a launch covers every replica of the ensemble: the CTAs that
 // do not fit wait on the hardware block scheduler, which is the work queue of the replicas (run
 // times vary several-fold by seed).  Short runs of events go through the one-event-per-lane path of ns_seq.cuh.
+// A replica that enters a sparse phase (a streak of tiny batches: a swarm draining to completion is ten thousands
+// of single-event timestamps) leaves the CTA engine: one SM holds one such CTA but dozens of single warps, so the
+// host loop (ns_ens_run) alternates this kernel with k_run_seq over the replicas that asked for it.
 #define NS_SCOPE_CTA
 #define PAR_MIN_BATCH 33           // up to one warp's worth of events: the one-event-per-lane path; above: the whole CTA
 #include "ns_par_dev.cuh"
@@ -11,7 +14,8 @@
 #define NS_KERNEL_PROLOGUE \
 	CtaScope grid; \
 	if ((int)blockIdx.x >= n_sims) return; \
-	const Sim *sp = sims+blockIdx.x; const SeqScratch *scrp = scrs+blockIdx.x; const ParScratch &P = pars[blockIdx.x];
+	const Sim *sp = sims+blockIdx.x; const SeqScratch *scrp = scrs+blockIdx.x; const ParScratch &P = pars[blockIdx.x]; \
+	if (sp->st->sparse_mode) return;          /* in its sparse phase: stepped by its warp of k_run_seq */
 #include "ns_par_kernel.inc"
 
 int ens_preload(void){

@@ -95,7 +95,7 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 
 // ---- launchers (each defined next to its kernel)
 // ns_seq.cu
-int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream);
+int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream, int ens_phase = 0);   // ens_phase: only the replicas in their sparse phase
 int seq_launch_init_groups(const Sim *d_sims, int n, cudaStream_t stream);
 int seq_launch_exec_ops(const Sim *d_sim, int n_ops, cudaStream_t stream);
 int seq_preload(void);

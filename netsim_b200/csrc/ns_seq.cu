@@ -25,16 +25,16 @@ __global__ void __launch_bounds__(32) k_exec_ops(const Sim *sp, int n_ops){
 }
 
 // one warp per simulation, strictly sequential event handling
-__global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n){
+__global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n, int ens_phase){
 	int s = blockIdx.x;
 	if (s >= n) return;
 	__shared__ WideSmem W;
-	seq_run(&sims[s], scr[s], threadIdx.x, &W);
+	seq_run(&sims[s], scr[s], threadIdx.x, &W, ens_phase);
 }
 
 static int launched(void){ cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : (int)e; }
-int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream){
-	k_run_seq<<<n, 32, 0, stream>>>(d_sims, d_scr, n);
+int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream, int ens_phase){
+	k_run_seq<<<n, 32, 0, stream>>>(d_sims, d_scr, n, ens_phase);
 	return launched();
 }
 int seq_launch_init_groups(const Sim *d_sims, int n, cudaStream_t stream){

@@ -451,9 +451,11 @@ __device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &
 }
 
 #define NS_SPARSE_MAX_HIT_TILES 4
-__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem *W){
+#define NS_ENS_MAX_HIT_TILES 64
+__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem *W, int ens_phase = 0){
 	Ctx c;
 	ctx_load(c, Sp, lane);
+	if (ens_phase && !c.st->sparse_mode) return;                         // ensemble, sparse phase: this replica is with the CTA engine (or done)
 	if (W) wide_init(*W, lane);
 	if (c.st->pending_close >= 0) {                                   // flow_done_cleaner of the event the host just saw
 		int f = c.st->pending_close;
@@ -475,7 +477,8 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem 
 			u64 first = c.head >> NS_TILE_SHIFT, last = c.tail ? (c.tail-1) >> NS_TILE_SHIFT : 0;
 			if (c.tail > c.head) for (u64 a = first+lane; a <= last; a += 32) hits += S.q_tmin[a & tmask] == m;
 			for (int d = 16; d; d >>= 1) hits += __shfl_xor_sync(FULLMASK, hits, d);
-			if (hits > NS_SPARSE_MAX_HIT_TILES) { L0 c.st->want_dense = 1; __syncwarp(); break; }
+			// (an ensemble switches engines in rounds over all replicas: there the warp keeps medium batches — its lanes take 32 events at a time)
+			if (hits > (ens_phase ? NS_ENS_MAX_HIT_TILES : NS_SPARSE_MAX_HIT_TILES)) { L0 { c.st->want_dense = 1; if (ens_phase) c.st->sparse_mode = 0; } __syncwarp(); break; }
 		}
 		int nr = seq_collect_ring(c, m);
 		if (nr < 0) { set_status(c, NS_E_BATCH_FULL); __syncwarp(); break; }

@@ -429,6 +429,79 @@ def churn(n_users: int = 5000, n_servers: int = 16, rate: float = 1000.0, mean_s
     return Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, groups, {}, seed=1)
 
 
+def churn_fast(n_users: int = 1000000, n_servers: int = 1024, rate: float = 1000.0, mean_session: float = 600.0,
+               quantum: float = 0.01, res_len: int = 4000000, seed: int = 2024, sim_end: float | None = None,
+               init_users: int = 0) -> Scenario:
+    """Vectorised `churn()` for SURVEY §8d config 4 at scale (1M users, 1024 servers, Poisson arrivals of `rate`/s,
+    exponential sessions): the same script, built as numpy tables.  Group 0 schedules one USER event per arrival and per
+    departure (in time order, arrivals before departures at equal times, like `churn()`); group k holds the one
+    sim_establish_flow / flow_close of timeline entry k."""
+    rng = np.random.default_rng(seed)
+    n = n_servers + n_users
+    idx = np.arange(n)
+    is_srv = idx < n_servers
+    tz = np.where(is_srv, _tz(idx, n_servers), _tz(idx - n_servers, n_users))
+    mu = np.where(is_srv, 160000.0, 8000.0)
+    md = np.where(is_srv, 160000.0, 40000.0)
+    res = np.zeros(1, dtype=RES_DTYPE)
+    res["owner"] = 0
+    res["len"] = res_len
+    res["bit_rate"] = 2000
+    cp = np.zeros(n_servers - 1, dtype=COPY_DTYPE)
+    cp["node"] = np.arange(1, n_servers)
+    cp["res"] = 0
+    # `init_users` users are already connected when the simulation starts (a warm swarm: their flows are established by the
+    # module's init, like modules/p2p.c's first connections); the others arrive as a Poisson process
+    I = int(init_users)
+    t_arr = np.zeros(n_users)
+    t_arr[I:] = np.floor(np.cumsum(rng.exponential(1.0 / rate, n_users - I)) / quantum) * quantum
+    t_dep = np.floor((t_arr + rng.exponential(mean_session, n_users)) / quantum + 1) * quantum
+    srv = rng.integers(0, n_servers, n_users)
+    ub, dl = _ub_delay(tz[srv], tz[n_servers + np.arange(n_users)])
+    if sim_end is not None:                       # nothing after the end of the simulation needs to be in the script
+        n_a = int((t_arr < sim_end).sum())
+    else:
+        n_a = n_users
+    users = np.arange(n_a)
+    dep_ok = np.ones(n_a, dtype=bool) if sim_end is None else (t_dep[:n_a] < sim_end)
+    arr_u = users[I:]
+    ev_t = np.concatenate([t_arr[I:n_a], t_dep[:n_a][dep_ok]])
+    ev_kind = np.concatenate([np.zeros(n_a - I, dtype=np.int64), np.ones(int(dep_ok.sum()), dtype=np.int64)])
+    ev_u = np.concatenate([arr_u, users[dep_ok]])
+    order = np.lexsort((ev_u, ev_kind, ev_t))     # (time, kind, user): the order of sorted((t, kind, u)) in churn()
+    ev_t, ev_kind, ev_u = ev_t[order], ev_kind[order], ev_u[order]
+    n_ev = len(ev_t)
+    n_end = 1 if sim_end is not None else 0
+    n0 = I + n_ev + n_end
+    ops = np.zeros(n0 + n_ev + n_end, dtype=OP_DTYPE)
+    # group 0: the warm swarm's flows (creation ordinal == user index), then the schedule
+    ops["kind"][:I] = OP_CREATE
+    ops["a"][:I] = srv[:I]
+    ops["b"][:I] = n_servers + np.arange(I)
+    ops["x"][:I] = ub[:I]
+    ops["y"][:I] = dl[:I]
+    ops["kind"][I:I + n_ev] = OP_SCHED
+    ops["a"][I:I + n_ev] = 1 + np.arange(n_ev)
+    ops["x"][I:I + n_ev] = ev_t
+    if n_end:
+        ops[I + n_ev] = (OP_SCHED, n_ev + 1, 0, 0, 0, float(sim_end), 0.0)
+    # groups 1..n_ev: one op each
+    body = ops[n0:n0 + n_ev]
+    is_a = ev_kind == 0
+    body["kind"] = np.where(is_a, OP_CREATE, OP_CLOSE)
+    body["a"] = np.where(is_a, srv[ev_u], ev_u)   # close: flow ordinal == arrival index (arrivals are created in time order)
+    body["b"] = np.where(is_a, n_servers + ev_u, 0)
+    body["x"] = np.where(is_a, ub[ev_u], 0.0)
+    body["y"] = np.where(is_a, dl[ev_u], 0.0)
+    if n_end:
+        ops[n0 + n_ev] = (OP_END, 0, 0, 0, 0, 0.0, 0.0)
+    off = np.concatenate([[0], n0 + np.arange(n_ev + n_end + 1)]).astype("<i4")
+    sc = Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, [], {}, seed=1)
+    sc._ops = ops
+    sc._group_off = off
+    return sc
+
+
 def edge_cases() -> Dict[str, Scenario]:
     """Hand-written corner cases of the module API (sim.c:42-67 error returns, main.c:50-52 exits)."""
     L = 100000

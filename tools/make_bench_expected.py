@@ -3,6 +3,7 @@ pinned to the compiled reference by tests/test_oracle_golden.py) and committed a
 bench.py compares the device engine's digest after its last window against it (outside the timed region).
     python tools/make_bench_expected.py [ranks] [total_events]
     python tools/make_bench_expected.py ensemble [peers]        digests of sampled replicas of bench.py --workload ensemble
+    python tools/make_bench_expected.py churn [total_events]    digest of bench.py --workload churn after its last window
 """
 import json
 import os
@@ -45,6 +46,34 @@ def ens_one(seed_index, peers):
     o.close()
     return out
 
+
+def churn_one(rank, total_events):
+    import argparse
+    import bench
+    from netsim_b200 import engine as E
+    from oracle import pyoracle
+    a = argparse.Namespace(workload="churn", churn_users=1000000, churn_init=100000, churn_session=100.0, churn_end=60.0)
+    sc = bench.churn_workload(a, rank)
+    t0 = time.time()
+    o = pyoracle.Oracle(sc.to_bytes(), trace=False, records=True)
+    st = o.run(total_events)
+    c = o.counters()
+    rec = o.records()
+    out = {"rank": rank, "status": st, "events": c["events"], "solves": c["solves"], "full_spreads": c["full_spreads"], "seq": c["seq"],
+           "record_bytes": len(rec), "record_hash": E.stream_hash(rec), "oracle_seconds": round(time.time() - t0, 1)}
+    o.close()
+    return a, out
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "churn":
+    total = int(sys.argv[2]) if len(sys.argv) > 2 else 13_000_000
+    a, r = churn_one(0, total)
+    path = os.path.join(ROOT, "tests", "golden", "bench_expected.json")
+    cur = json.load(open(path))
+    cur[f"churn,users={a.churn_users},init={a.churn_init},session={a.churn_session},end={a.churn_end},rank=0,events={total}"] = r
+    print(r)
+    json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    sys.exit(0)
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ensemble":
     peers = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
