@@ -24,12 +24,27 @@ enum ns_op_kind {
 	NS_OP_SCHED  = 2, /* event_add(event_new(c ? now+x : x, USER, group a)) */
 	NS_OP_CLOSE  = 3, /* flow_close(flow created by the a-th executed CREATE), if still alive */
 	NS_OP_END    = 4, /* sim_end(): the event loop stops before the next pop (main.c:51-52) */
+	NS_OP_PLAY1  = 5, /* client_new_play1(rid[c], node[a]) (modules/client_behaviour.c:364-387) with fetch metric b
+	                     (0 = distance_metric, 1 = share_metric, p2p_common.h:171-198): server_picker_opt1 over the
+	                     server nodes + qselect, one sim_establish_flow per kept server at strip i*strip with
+	                     distance_based_bw / distance_based_delay, then client_start_play.  Needs NS_SC_F_CLIENTS. */
 };
+
+/* header.flags */
+#define NS_SC_F_CLIENTS 1u  /* a struct ns_sc_client per node follows the on-done table: the nodes run the behaviour
+                               library's client side (modules/client_behaviour.c: water-mark state machine on every
+                               RCV speed change / FLOW_DONE / throttle, its USER events, R_NODE_STATE records) */
+enum ns_client_kind {
+	NS_CK_PLAIN  = 0,   /* no behaviour (user_data == NULL) */
+	NS_CK_CLIENT = 1,   /* p2p client: def_user with lowwm/highwm, state N_IDLE (modules/p2p.c:166-174) */
+	NS_CK_SERVER = 2,   /* p2p_new_server (p2p_common.h:101-115): state N_SERVER, member of the picker's server list */
+};
+struct ns_sc_client { int32_t kind, time_zone, lowwm, highwm; };
 
 struct ns_sc_header {
 	uint32_t magic, version;
 	uint32_t seed;       /* srandom(seed) before anything else; 1 == glibc default state */
-	uint32_t flags;      /* reserved, 0 */
+	uint32_t flags;      /* NS_SC_F_* */
 	int32_t n_nodes, n_resources, n_copies, n_groups, n_ops, n_ondone;
 	int32_t pad[2];
 };                           /* 48 bytes, followed by the arrays below in this order */
@@ -39,5 +54,6 @@ struct ns_sc_copy     { int32_t node;  int32_t res; };                    /* sim
 /* int32_t group_off[n_groups+1];   group g = ops[group_off[g] .. group_off[g+1]); group 0 runs at init */
 struct ns_sc_op { int32_t kind, a, b, c; int64_t start; double x, y; };  /* 40 bytes */
 struct ns_sc_ondone { int32_t flow_ord; int32_t group; };                /* sorted by flow_ord, unique */
+/* struct ns_sc_client client[n_nodes];   only with NS_SC_F_CLIENTS */
 
 #endif

@@ -32,6 +32,8 @@
 
 enum { SND = 0, RCV = 1 };
 enum { EV_FLOW_DRAIN = 0, EV_FLOW_DONE = 1, EV_FLOW_SPEED_THROTTLE = 2, EV_PACKET_DONE = 3, EV_SPEED_CHANGE = 4, EV_USER = 5 };
+enum { NST_OFFLINE = 0, NST_STALE, NST_PLAYING, NST_DONE, NST_IDLE, NST_SERVER, NST_CLOUD, NST_DYING };   // enum node_state, data.h:89-98
+enum { UE_DONE_PLAY = 0, UE_PAUSE_BUFFERING = 1, UE_DONE_BUFFERING = 2 };                                 // enum ue_type, p2p_common.h:41-49
 enum { R_USAGE = 0, R_SPD = 2, R_CONN_CREATE = 4, R_CONN_DST = 5, R_CONN_CLOSE = 6, R_NODE_STATE = 7, R_NODE_CREATE = 8 };
 
 typedef unsigned long long u64;
@@ -86,6 +88,13 @@ struct Sim {
 	double *q_time, *q_speed; int *q_fd; uint32_t *q_gen; double *q_tmin;
 	// long-lived event table
 	double *l_time; u64 *l_seq; double *l_tmin; int *u_group, *u_next_free;
+	// behaviour library, client side (scripts with NS_SC_F_CLIENTS): struct def_user (modules/p2p_common.h:8-29) and
+	// node->state as columns; the client's own USER event d->e lives in L-table slot 2*cap_flows+cap_users+node
+	int has_clients, n_srv;
+	const ns_sc_client *c_cfg; const int *srv_list;   // script table; server nodes, newest first (list_add at head, p2p_common.h:112)
+	int *n_state;                                     // enum node_state, data.h:89-98
+	double *c_bit_rate, *c_last; int *c_buffer_pos, *c_next_state, *c_trigger, *c_ue_type, *c_ue_rng;
+	int *s_brate;                                     // resource->bit_rate (data.h:29)
 	// script
 	const ns_sc_op *ops; const int *group_off; const ns_sc_ondone *ondone; const uint32_t *rids;
 	int *ord2flow;
