@@ -193,13 +193,17 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	const ns_sc_copy *cp = (const ns_sc_copy *)p; p += (size_t)H.n_copies*sizeof *cp;
 	const int32_t *goff = (const int32_t *)p; p += (size_t)(H.n_groups+1)*4;
 	const ns_sc_op *ops = (const ns_sc_op *)p; p += (size_t)H.n_ops*sizeof *ops;
-	const ns_sc_ondone *od = (const ns_sc_ondone *)p;
+	const ns_sc_ondone *od = (const ns_sc_ondone *)p; p += (size_t)H.n_ondone*sizeof *od;
+	const bool has_clients = (H.flags & NS_SC_F_CLIENTS) != 0;
+	const ns_sc_client *cl = (const ns_sc_client *)p;
+	if (has_clients && len < need+(size_t)H.n_nodes*sizeof(ns_sc_client)) return NS_E_BAD_SCENARIO;
+	if (H.flags & ~NS_SC_F_CLIENTS) return NS_E_BAD_SCENARIO;
 	// group g = ops[goff[g] .. goff[g+1]): offsets must be monotone and inside the op table
 	if (goff[0] < 0 || goff[H.n_groups] > H.n_ops) return NS_E_BAD_SCENARIO;
 	for (int g = 0; g < H.n_groups; g++) if (goff[g] > goff[g+1]) return NS_E_BAD_SCENARIO;
 	// the on-done table is binary-searched on the device: sorted, unique
 	for (int i = 1; i < H.n_ondone; i++) if (od[i-1].flow_ord >= od[i].flow_ord) return NS_E_BAD_SCENARIO;
-	int n_create = 0, n_sched = 0;
+	int n_create = 0, n_sched = 0, n_play = 0;
 	for (int i = 0; i < H.n_ops; i++) {
 		if (ops[i].kind == NS_OP_CLOSE && ops[i].a < 0) return NS_E_BAD_SCENARIO;
 		if (ops[i].kind == NS_OP_CREATE) {
@@ -208,8 +212,15 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		} else if (ops[i].kind == NS_OP_SCHED) {
 			n_sched++;
 			if (ops[i].a < 0 || ops[i].a >= H.n_groups) return NS_E_BAD_SCENARIO;
+		} else if (ops[i].kind == NS_OP_PLAY1) {
+			if (!has_clients || ops[i].a < 0 || ops[i].a >= H.n_nodes || ops[i].c < 0 || ops[i].c >= H.n_resources || (ops[i].b != 0 && ops[i].b != 1)) return NS_E_BAD_SCENARIO;
+			if (cl[ops[i].a].kind != NS_CK_CLIENT) return NS_E_BAD_SCENARIO;
+			n_play++;
 		}
 	}
+	std::vector<int> srv_list;                                        // list_add at head: newest server first (p2p_common.h:112)
+	if (has_clients) for (int i = H.n_nodes-1; i >= 0; i--) if (cl[i].kind == NS_CK_SERVER) srv_list.push_back(i);
+	n_create += n_play*std::max(1, (int)srv_list.size()/2);           // a PLAY1 establishes up to nsvr/2 flows
 	for (int i = 0; i < H.n_ondone; i++) if (od[i].group < 0 || od[i].group >= H.n_groups) return NS_E_BAD_SCENARIO;
 	h.seed = H.seed; h.n_creates = n_create;
 
@@ -229,7 +240,8 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	S.n_groups = H.n_groups; S.n_ops = H.n_ops; S.n_ondone = H.n_ondone; S.n_rids = H.n_resources;
 	S.ring_cap = o.ring_cap ? next_pow2(std::max<u64>(o.ring_cap, NS_TILE)) : next_pow2(std::min<u64>(std::max<u64>(1u << 16, 128ull*F), 1ull << 28));
 	S.n_ring_tiles = (int)(S.ring_cap >> NS_TILE_SHIFT);
-	S.n_l = 2*F+S.cap_users;
+	S.has_clients = has_clients; S.n_srv = (int)srv_list.size();
+	S.n_l = 2*F+S.cap_users+(has_clients ? N : 0);                    // + one slot per node for a client's own USER event
 	S.n_l_tiles = (S.n_l+NS_TILE-1)/NS_TILE;
 	S.adj_arena_cap = 16*F+8*N+64;
 	S.batch_cap = (int)std::min<u64>(S.ring_cap/2, 1ull << 30);
@@ -257,7 +269,13 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	DA(S.r_start, R); DA(S.r_total, R); DA(S.r_len, R); DA(S.r_lenc, R); DA(S.r_last, R);
 	DA(S.r_prod, R); DA(S.r_res, R); DA(S.r_next, R); DA(S.r_prev, R); DA(S.r_cons, R); DA(S.r_next_free, R);
 	const int Q = S.cap_res;
-	DA(S.s_id, Q); DA(S.s_len, Q); DA(S.s_node, Q); DA(S.s_first, Q); DA(S.s_nprod, Q); DA(S.s_ncons, Q); DA(S.s_next, Q);
+	DA(S.s_id, Q); DA(S.s_len, Q); DA(S.s_node, Q); DA(S.s_first, Q); DA(S.s_nprod, Q); DA(S.s_ncons, Q); DA(S.s_next, Q); DA(S.s_brate, Q);
+	ns_sc_client *d_cl = nullptr; int *d_srv = nullptr;
+	if (has_clients) {
+		DA(d_cl, N); DA(d_srv, std::max(1, S.n_srv)); DA(S.n_state, N);
+		DA(S.c_bit_rate, N); DA(S.c_last, N); DA(S.c_buffer_pos, N); DA(S.c_next_state, N); DA(S.c_trigger, N); DA(S.c_ue_type, N); DA(S.c_ue_rng, N);
+	}
+	S.c_cfg = d_cl; S.srv_list = d_srv;
 	DA(S.q_time, S.ring_cap); DA(S.q_speed, S.ring_cap); DA(S.q_fd, S.ring_cap); DA(S.q_gen, S.ring_cap); DA(S.q_tmin, S.n_ring_tiles);
 	DA(S.l_time, (size_t)S.n_l_tiles*NS_TILE); DA(S.l_seq, (size_t)S.n_l_tiles*NS_TILE); DA(S.l_tmin, S.n_l_tiles);
 	DA(S.u_group, S.cap_users); DA(S.u_next_free, S.cap_users);
@@ -311,15 +329,17 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		do { id = ns_rand_next_host(&g); draws++; } while (!used.insert(id).second);
 		nid[i] = id;
 		if (o.want_records) host_rec(rec, 0.0, R_NODE_CREATE, id, 1, 0);
+		if (has_clients && cl[i].kind == NS_CK_SERVER && o.want_records)
+			host_rec(rec, 0.0, R_NODE_STATE, id, 1, NST_SERVER);     // p2p_new_server: sim_node_change_state(n, N_SERVER), p2p_common.h:106
 	}
 	std::vector<int> res_head(N, -1);
-	std::vector<uint32_t> s_id; std::vector<long long> s_len; std::vector<int> s_node, s_first, s_next;
+	std::vector<uint32_t> s_id; std::vector<long long> s_len; std::vector<int> s_node, s_first, s_next, s_brate;
 	std::vector<long long> r_start, r_total; std::vector<double> r_len; std::vector<int> r_res;
 	std::vector<uint32_t> rids(H.n_resources);
 	auto store_find = [&](int node, uint32_t rid){ for (int r = res_head[node]; r >= 0; r = s_next[r]) if (s_id[r] == rid) return r; return -1; };
-	auto add_full = [&](int node, uint32_t rid, long long L){
+	auto add_full = [&](int node, uint32_t rid, long long L, int brate){
 		int r = (int)s_id.size();
-		s_id.push_back(rid); s_len.push_back(L); s_node.push_back(node); s_next.push_back(res_head[node]); res_head[node] = r;
+		s_id.push_back(rid); s_len.push_back(L); s_node.push_back(node); s_next.push_back(res_head[node]); res_head[node] = r; s_brate.push_back(brate);
 		s_first.push_back((int)r_start.size());
 		r_start.push_back(0); r_total.push_back(L); r_len.push_back((double)L); r_res.push_back(r);
 		ns_rand_next_host(&g); draws++;                               // resource_new_range -> skip_list_insert
@@ -329,13 +349,13 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		uint32_t rid = ns_rand_next_host(&g); draws++;
 		while (store_find(rs[i].owner, rid) >= 0) { rid = ns_rand_next_host(&g); draws++; }
 		rids[i] = rid;
-		add_full(rs[i].owner, rid, rs[i].len);
+		add_full(rs[i].owner, rid, rs[i].len, rs[i].bit_rate);
 	}
 	for (int i = 0; i < H.n_copies; i++) {
 		if (cp[i].node < 0 || cp[i].node >= N || cp[i].res < 0 || cp[i].res >= H.n_resources) return NS_E_BAD_SCENARIO;
 		uint32_t rid = rids[cp[i].res];
 		if (store_find(cp[i].node, rid) >= 0) continue;
-		add_full(cp[i].node, rid, rs[cp[i].res].len);
+		add_full(cp[i].node, rid, rs[cp[i].res].len, rs[cp[i].res].bit_rate);
 	}
 	const int nres0 = (int)s_id.size(), nrng0 = (int)r_start.size();
 	if (rec.size() > S.rec_cap && o.want_records) return NS_E_RECORDS_LOST;
@@ -358,6 +378,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		CK(cudaMemcpy(S.s_node, s_node.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(S.s_first, s_first.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(S.s_next, s_next.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.s_brate, s_brate.data(), (size_t)nres0*4, cudaMemcpyHostToDevice));
 		CK(cudaMemset(S.s_nprod, 0, (size_t)nres0*4)); CK(cudaMemset(S.s_ncons, 0, (size_t)nres0*4));
 		CK(cudaMemcpy(S.r_start, r_start.data(), (size_t)nrng0*8, cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(S.r_total, r_total.data(), (size_t)nrng0*8, cudaMemcpyHostToDevice));
@@ -365,6 +386,16 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		CK(cudaMemcpy(S.r_res, r_res.data(), (size_t)nrng0*4, cudaMemcpyHostToDevice));
 		if ((rc = fill_f64(S.r_lenc, nrng0, 0)) || (rc = fill_f64(S.r_last, nrng0, 0))) return rc;
 		if ((rc = fill_i32(S.r_prod, nrng0, -1)) || (rc = fill_i32(S.r_next, nrng0, -1)) || (rc = fill_i32(S.r_prev, nrng0, -1)) || (rc = fill_i32(S.r_cons, nrng0, -1))) return rc;
+	}
+	if (has_clients) {
+		CK(cudaMemcpy(d_cl, cl, (size_t)N*sizeof *cl, cudaMemcpyHostToDevice));
+		if (S.n_srv) CK(cudaMemcpy(d_srv, srv_list.data(), (size_t)S.n_srv*4, cudaMemcpyHostToDevice));
+		std::vector<int> st0(N);
+		for (int i = 0; i < N; i++) st0[i] = cl[i].kind == NS_CK_SERVER ? NST_SERVER : cl[i].kind == NS_CK_CLIENT ? NST_IDLE : NST_OFFLINE;   // p2p.c:168, data.h:226-236
+		CK(cudaMemcpy(S.n_state, st0.data(), (size_t)N*4, cudaMemcpyHostToDevice));
+		CK(cudaMemset(S.c_bit_rate, 0, (size_t)N*8)); CK(cudaMemset(S.c_last, 0, (size_t)N*8)); CK(cudaMemset(S.c_buffer_pos, 0, (size_t)N*4));
+		CK(cudaMemcpy(S.c_next_state, st0.data(), (size_t)N*4, cudaMemcpyHostToDevice));
+		if ((rc = fill_i32(S.c_trigger, N, -1)) || (rc = fill_i32(S.c_ue_type, N, 0)) || (rc = fill_i32(S.c_ue_rng, N, -1))) return rc;
 	}
 	CK(cudaMemcpy(d_ops, ops, (size_t)H.n_ops*sizeof *ops, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d_goff, goff, (size_t)(H.n_groups+1)*4, cudaMemcpyHostToDevice));

@@ -735,7 +735,10 @@ __device__ __noinline__ int sim_establish_flow(Ctx &c, uint32_t rid, long long s
 	int sr = store_get(S, src, rid);
 	if (sr < 0) return -1;                                            // :49-53
 	int dr = store_get(S, dst, rid);
-	if (dr < 0) dr = resource_new(c, dst, rid, S.s_len[sr]);          // :54-61
+	if (dr < 0) {                                                     // :54-61
+		dr = resource_new(c, dst, rid, S.s_len[sr]);
+		if (dr >= 0) { L0 S.s_brate[dr] = S.s_brate[sr]; WSYNC(); }
+	}
 	if (dr < 0) return -1;
 	if (range_get(S, dr, (int)start) >= 0) return -1;                 // :62-67
 	int rng = range_get(S, sr, (int)start);                           // :69
@@ -759,6 +762,141 @@ __device__ __noinline__ int sim_establish_flow(Ctx &c, uint32_t rid, long long s
 	if (ph >= 0) range_calc_and_requeue_events(c, S.r_prod[ph]);
 	return f;
 }
+
+
+#ifndef NS_NO_CLIENTS   // (the grid engine of plain simulations is compiled without the behaviour hooks: ns_par.cu / ns_par_cl.cu)
+// ---------------------------------------------------------------- behaviour library, client side
+// modules/client_behaviour.c on the device (scripts with NS_SC_F_CLIENTS): the water-mark state machine a p2p
+// client runs on every RCV speed change, FLOW_DONE and throttle of its flows, and on its own USER event d->e.
+// Everything a handler touches belongs to the client node or to the flow that triggered it, so the hooks are
+// legal wherever the DEFAULT handler of the same event is (one (node,RCV) group).  The C arithmetic of the
+// reference is kept conversion for conversion (size_t/int/double mixes, int truncation of buffer_pos).
+__device__ __forceinline__ int cl_slot(const Sim &S, int n){ return 2*S.cap_flows+S.cap_users+n; }
+// sim_node_change_state, sim.h:25-28
+__device__ __forceinline__ void node_change_state(Ctx &c, int n, int state){
+	const Sim &S = *c.S;
+	L0 S.n_state[n] = state;
+	WSYNC();
+	write_record(c, R_NODE_STATE, S.n_id[n], 1, (uint32_t)state & 0xffu, 0);
+}
+// event_remove(d->e), event.h:13-18
+__device__ __forceinline__ void cl_event_remove(Ctx &c, int n){
+	L0 c.S->l_time[cl_slot(*c.S, n)] = NS_INF;
+	WSYNC();
+}
+// ue->type / ue->data / d->e->time set, then event_add(d->e), event.h:56-74 (an event at +inf burns its draw and never fires)
+__device__ __forceinline__ void cl_event_add(Ctx &c, int n, int type, int rng, double t){
+	const Sim &S = *c.S;
+	if (!ev_time_ok(c, t)) return;
+	u64 seq = seq_reserve(c, 1);
+	if (c.st->status && c.st->status != NS_E_RECORDS_LOST) return;
+	L0 { S.c_ue_type[n] = type; S.c_ue_rng[n] = rng; l_put(c, cl_slot(S, n), seq, t); }
+	WSYNC();
+}
+// client_lowwm_event, client_behaviour.c:17-89
+__device__ __noinline__ void client_lowwm_event(Ctx &c, int rng){
+	const Sim &S = *c.S;
+	const int n = S.s_node[S.r_res[rng]];
+	L0 range_update_1(S, rng, c.now);                                 // :22
+	WSYNC();
+	if (S.n_state[n] != NST_PLAYING) return;                          // :23-24
+	const int pos = S.c_buffer_pos[n];
+	const long long rstart = S.r_start[rng], total = S.r_total[rng];
+	if ((u64)rstart > (u64)(long long)pos) return;                    // :27-29 (size_t > int)
+	cl_event_remove(c, n);                                            // :35
+	const double br = S.c_bit_rate[n];
+	const int prod = S.r_prod[rng];
+	const double sgrow = prod >= 0 ? S.f_speed[1][prod] : 0;          // :40
+	const double rlen = S.r_len[rng];
+	if (S.r_next[rng] < 0) {                                          // :41-55
+		double time2 = (double)((u64)total-(u64)(long long)pos)/br;
+		double time3 = ((double)(u64)(total-rstart)-rlen)/sgrow;
+		double d0 = (double)(u64)total-((double)(u64)rstart+rlen);
+		if (d0 > -NS_EPS && d0 < NS_EPS) time3 = 0;
+		if (time2 > time3) { cl_event_add(c, n, UE_DONE_PLAY, -1, c.now+time2); return; }
+	}
+	if (br < sgrow) return;                                           // :57-61
+	const int limit = S.c_cfg[n].lowwm;
+	const double time = ((((double)(u64)rstart+rlen)-(double)pos)-(double)limit)/(br-sgrow);   // :65
+	// :78-88 (the reference compares the RELATIVE time with the absolute event times)
+	if (prod < 0 || (!is_later_than(time, S.l_time[2*prod]) && !is_later_than(time, S.l_time[2*prod+1])))
+		cl_event_add(c, n, UE_PAUSE_BUFFERING, rng, time+c.now);
+}
+// client_highwm_event, client_behaviour.c:91-139
+__device__ __noinline__ void client_highwm_event(Ctx &c, int rng){
+	const Sim &S = *c.S;
+	L0 range_update_1(S, rng, c.now);                                 // :92
+	WSYNC();
+	const int n = S.s_node[S.r_res[rng]];
+	if (S.n_state[n] != NST_STALE) return;                            // :98-100
+	const int nh = S.r_next[rng];
+	const int pos = S.c_buffer_pos[n];
+	const long long rstart = S.r_start[rng], total = S.r_total[rng];
+	if ((u64)(long long)pos < (u64)rstart) return;                    // :102-105 (int < size_t)
+	cl_event_remove(c, n);                                            // :111
+	const double rlen = S.r_len[rng];
+	const int re = (int)(((double)(u64)rstart+rlen)-(double)pos);     // :113
+	const int prod = S.r_prod[rng];
+	const double sgrow = prod >= 0 ? S.f_speed[1][prod] : 0;
+	const int highwm = S.c_cfg[n].highwm;
+	double time = (double)(highwm-re)/sgrow;                          // :115
+	if (re >= highwm) time = 0;
+	if (nh < 0) {                                                     // :118-125: reaching the end counts as high water
+		double time2 = ((double)(u64)(total-rstart)-rlen)/sgrow;
+		double d0 = (double)(u64)total-((double)(u64)rstart+rlen);
+		if (d0 > -NS_EPS && d0 < NS_EPS) time2 = 0;
+		if (time2 < time) time = time2;
+	}
+	time += c.now;
+	if (prod < 0 || (!is_later_than(time, S.l_time[2*prod]) && !is_later_than(time, S.l_time[2*prod+1])))
+		cl_event_add(c, n, UE_DONE_BUFFERING, rng, time);
+}
+// the part client_speed_change / client_done / client_speed_throttle share (client_behaviour.c:270-317)
+__device__ __forceinline__ void client_touch(Ctx &c, int f){
+	const Sim &S = *c.S;
+	const int n = S.f_peer[1][f];
+	if (S.c_cfg[n].kind != NS_CK_CLIENT) return;
+	L0 {
+		if (S.n_state[n] == NST_PLAYING)                              // d->buffer_pos += d->bit_rate*(s->now-d->last_update)+eps (int += double)
+			S.c_buffer_pos[n] = (int)((double)S.c_buffer_pos[n]+(S.c_bit_rate[n]*(c.now-S.c_last[n])+NS_EPS));
+		S.c_last[n] = c.now;
+	}
+	WSYNC();
+	const int rng = S.f_drng[f];
+	client_lowwm_event(c, rng);
+	client_highwm_event(c, rng);
+}
+// the client's own USER event: client_next_state_from_event + client_handle_next_state (client_behaviour.c:143-196),
+// as modules/p2p.c:59-67 dispatches them (the next NEW_CONNECTION of a client that finished playing is the script's business)
+__device__ __noinline__ void client_user_event(Ctx &c, int n){
+	const Sim &S = *c.S;
+	const int type = S.c_ue_type[n];
+	int next = NST_DONE;
+	if (type != UE_DONE_PLAY) {                                       // :145-151 returns before d->trigger is touched
+		L0 S.c_trigger[n] = S.c_ue_rng[n];
+		next = type == UE_PAUSE_BUFFERING ? NST_STALE : NST_PLAYING;
+	}
+	L0 S.c_next_state[n] = next;
+	WSYNC();
+	const int rng = S.c_trigger[n];
+	const int o_state = S.n_state[n];
+	if (o_state == next) return;                                      // :173-174
+	node_change_state(c, n, next);
+	if (o_state == NST_PLAYING) {                                     // :178-183
+		L0 {
+			S.c_buffer_pos[n] = (int)((double)S.c_buffer_pos[n]+(S.c_bit_rate[n]*(c.now-S.c_last[n])+NS_EPS));
+			S.c_last[n] = c.now;
+		}
+		WSYNC();
+		if (next == NST_STALE) client_highwm_event(c, rng);
+	} else if (o_state == NST_STALE) {                                // :184-190
+		L0 S.c_last[n] = c.now;
+		WSYNC();
+		if (next == NST_PLAYING) client_lowwm_event(c, rng);
+	}
+}
+
+#endif
 
 // ---------------------------------------------------------------- handlers
 // Would this SPEED_CHANGE reach bwspread's full spread (flow.c:126)?  Pure function of the current
@@ -791,7 +929,112 @@ __device__ void handle_speed_change(Ctx &c, int f, int type, double speed){
 		queue_speed_event(c, f, RCV, S.f_speed[0][f]);
 	write_record(c, R_SPD|type, S.f_id[f], -1, 0, speed);             // :383
 	trace_row(c, EV_SPEED_CHANGE|(type << 8), S.f_ord[f], speed, S.f_speed[type][f]);
+#ifndef NS_NO_CLIENTS
+	if (S.has_clients && type == RCV) client_touch(c, f);             // HNDR_USER: client_speed_change, client_behaviour.c:285-299
+#endif
 }
+
+
+__device__ int note_created_flow(Ctx &c, int f);
+#ifndef NS_NO_CLIENTS
+// ---------------------------------------------------------------- client_new_play1 (NS_OP_PLAY1)
+#define NS_PICK_MAX 128
+// is_connected, flow.h:29-35: a flow src -> dst exists (walks dst's receive list, the short one)
+__device__ __forceinline__ bool is_connected(const Sim &S, int src, int dst){
+	const int g = dst*2+RCV, off = S.adj_off[g], len = S.adj_len[g];
+	for (int p = 0; p < len; p++) { int f = S.adj_arena[off+p]; if (f >= 0 && S.f_peer[0][f] == src) return true; }
+	return false;
+}
+// distance_metric / share_metric, modules/p2p_common.h:171-198
+__device__ __forceinline__ int fetch_metric(const Sim &S, int metric, int node, int client){
+	int d = S.c_cfg[node].time_zone-S.c_cfg[client].time_zone;
+	if (d < 0) d = -d;
+	if (metric == 0) return d;
+	const double bw = 4000-100*d;
+	const double total = S.n_total[0][node]+bw, mx = S.n_max[0][node];
+	return total > mx ? (int)(-bw*mx/total) : (int)(-bw);
+}
+// client_recalc_state, client_behaviour.c:228-247
+__device__ __forceinline__ int client_recalc_state(const Sim &S, int n, int res){
+	const int pos = S.c_buffer_pos[n];
+	const int rng = range_get(S, res, pos);
+	if (rng < 0) return NST_STALE;
+	const long long total = S.r_total[rng];
+	if ((u64)(long long)pos == (u64)total) return NST_DONE;
+	const double end = (double)(u64)S.r_start[rng]+S.r_len[rng];
+	if (end == (double)(u64)total) return NST_PLAYING;
+	if (end > (double)(pos+S.c_cfg[n].lowwm)) return NST_PLAYING;
+	return NST_STALE;
+}
+// client_start_play, client_behaviour.c:249-268
+__device__ __noinline__ void client_start_play(Ctx &c, int n, uint32_t rid){
+	const Sim &S = *c.S;
+	const int res = store_get(S, n, rid);
+	if (res < 0) { set_status(c, NS_E_NULL_RANGE); return; }         // the reference dereferences NULL here
+	int rng = range_get(S, res, 0);
+	L0 { S.c_buffer_pos[n] = 0; S.c_last[n] = c.now; S.c_bit_rate[n] = (double)S.s_brate[res]; }
+	WSYNC();
+	node_change_state(c, n, client_recalc_state(S, n, res));
+	L0 S.c_next_state[n] = S.n_state[n];
+	WSYNC();
+	if (rng < 0) rng = S.s_first[res];                                // nothing downloaded yet: the first range
+	if (rng < 0) { set_status(c, NS_E_NULL_RANGE); return; }
+	client_lowwm_event(c, rng);
+	client_highwm_event(c, rng);
+}
+// client_new_play1, client_behaviour.c:364-387, with server_picker_opt1 (client_behaviour.h:68-88) and the
+// reference's quick-select (modules/qselect.h:5-27: Lomuto, last element as pivot, `<=` goes left)
+__device__ __noinline__ void client_new_play1(Ctx &c, int n, uint32_t rid, int metric){
+	const Sim &S = *c.S;
+	if (store_get(S, n, rid) >= 0) { client_start_play(c, n, rid); return; }   // :366-372
+	int cnt = S.n_srv/2;
+	if (cnt <= 0) cnt = 1;
+	int v[NS_PICK_MAX], nd[NS_PICK_MAX];
+	int cc = 0;
+	if (S.n_srv > NS_PICK_MAX) { set_status(c, NS_E_TABLE_FULL); return; }
+	for (int i = 0; i < S.n_srv; i++) {                               // list order: newest server first
+		const int sv = S.srv_list[i];
+		if (is_connected(S, sv, n)) continue;
+		v[cc] = fetch_metric(S, metric, sv, n); nd[cc] = sv; cc++;
+	}
+	if (cc <= cnt) cnt = cc;
+	else {
+		int base = 0, nmemb = cc, kq = cnt;                           // qselect_eval(eval_table, c, *count)
+		while (true) {
+			int st = 0;
+			const int pv = v[base+nmemb-1];
+			for (int i = 0; i < nmemb-1; i++) {
+				const int vi = v[base+i];
+				if ((int)((unsigned)vi-(unsigned)pv) > 0) continue;   // cmp(a,b) = a->val-b->val
+				int tv = v[base+st], tn = nd[base+st];
+				v[base+st] = vi; nd[base+st] = nd[base+i];
+				v[base+i] = tv; nd[base+i] = tn;
+				st++;
+			}
+			int tv = v[base+st], tn = nd[base+st];
+			v[base+st] = v[base+nmemb-1]; nd[base+st] = nd[base+nmemb-1];
+			v[base+nmemb-1] = tv; nd[base+nmemb-1] = tn;
+			if (kq-1 == st) break;
+			if (st > kq-1) nmemb = st;
+			else { base += st; nmemb -= st; kq -= st; }
+		}
+	}
+	if (cnt <= 0) { set_status(c, NS_E_ARG); return; }               // assert(cnt), :380
+	const int r1 = store_get(S, nd[0], rid);
+	if (r1 < 0) { set_status(c, NS_E_NULL_RANGE); return; }
+	const int strip = (int)((u64)S.s_len[r1]/(u64)(long long)cnt);   // :382
+	for (int i = 0; i < cnt; i++) {                                   // client_new_connection, client_behaviour.c:198-226
+		if (c.st->status) return;
+		int d = S.c_cfg[nd[i]].time_zone-S.c_cfg[n].time_zone;
+		if (d < 0) d = -d;
+		const double ub = 4000-100*d, delay = 0.02*d+0.1;             // distance_based_bw / distance_based_delay, p2p_common.h:181-189,214-221
+		const int f = sim_establish_flow(c, rid, (long long)(u64)(long long)(i*strip), nd[i], n, ub, delay);
+		if (note_created_flow(c, f) < 0) return;
+	}
+	client_start_play(c, n, rid);
+}
+
+#endif
 
 __device__ void run_group(Ctx &c, int g);
 
@@ -807,6 +1050,9 @@ __device__ __noinline__ void handle_flow_done(Ctx &c, int f){
 	}
 	int ord = S.f_ord[f];
 	trace_row(c, EV_FLOW_DONE, ord, S.r_len[S.f_drng[f]], S.f_speed[1][f]);
+#ifndef NS_NO_CLIENTS
+	if (S.has_clients) client_touch(c, f);                            // HNDR_USER: client_done, client_behaviour.c:301-317 (via p2p_done)
+#endif
 	if (S.n_ondone) {
 		int lo = 0, hi = S.n_ondone-1, g = -1;
 		while (lo <= hi) {
@@ -841,6 +1087,29 @@ __device__ __noinline__ void handle_throttle(Ctx &c, int f){
 		range_update_consumer_events(c, S.f_drng[f]);
 	}
 	trace_row(c, EV_FLOW_SPEED_THROTTLE, S.f_ord[f], S.f_speed[0][f], S.f_speed[1][f]);
+#ifndef NS_NO_CLIENTS
+	if (S.has_clients) client_touch(c, f);                            // HNDR_USER: client_speed_throttle, client_behaviour.c:270-281
+#endif
+}
+
+// every sim_establish_flow call takes the next creation ordinal, whether it succeeded or not
+__device__ int note_created_flow(Ctx &c, int f){
+	const Sim &S = *c.S;
+	int ord = c.st->n_ord;
+	if (ord >= S.cap_ord) { set_status(c, NS_E_TABLE_FULL); return -1; }
+	WSYNC();
+	L0 {
+		S.ord2flow[ord] = f;
+		c.st->n_ord = ord+1;
+		if (f >= 0) {
+			S.f_ord[f] = ord;
+			c.st->cnt[NS_CNT_CREATES] += 1;
+			u64 live = ++c.st->cnt[NS_CNT_LIVE_FLOWS];
+			if (live > c.st->cnt[NS_CNT_PEAK_FLOWS]) c.st->cnt[NS_CNT_PEAK_FLOWS] = live;
+		}
+	}
+	WSYNC();
+	return ord;
 }
 
 // one group of script operations == what oracle/ref_scenario.c run_group() does through the module API
@@ -853,21 +1122,14 @@ __device__ __noinline__ void run_group(Ctx &c, int g){
 		switch (op.kind) {
 		case NS_OP_CREATE: {
 			int f = sim_establish_flow(c, S.rids[op.c], op.start, op.a, op.b, op.x, op.y);
-			int ord = c.st->n_ord;
-			if (ord >= S.cap_ord) { set_status(c, NS_E_TABLE_FULL); return; }
-			WSYNC();
-			L0 {
-				S.ord2flow[ord] = f;
-				c.st->n_ord = ord+1;
-				if (f >= 0) {
-					S.f_ord[f] = ord;
-					c.st->cnt[NS_CNT_CREATES] += 1;
-					u64 live = ++c.st->cnt[NS_CNT_LIVE_FLOWS];
-					if (live > c.st->cnt[NS_CNT_PEAK_FLOWS]) c.st->cnt[NS_CNT_PEAK_FLOWS] = live;
-				}
-			}
-			WSYNC();
+			if (note_created_flow(c, f) < 0) return;
 			break; }
+#ifndef NS_NO_CLIENTS
+		case NS_OP_PLAY1:
+			if (!S.has_clients || S.c_cfg[op.a].kind != NS_CK_CLIENT) { set_status(c, NS_E_BAD_SCENARIO); return; }
+			client_new_play1(c, op.a, S.rids[op.c], op.b);
+			break;
+#endif
 		case NS_OP_SCHED: {
 			int u = c.st->free_user;
 			if (u >= 0) { WSYNC(); L0 c.st->free_user = S.u_next_free[u]; }

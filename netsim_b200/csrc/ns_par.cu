@@ -1,6 +1,7 @@
 // ns_par.cu — the grid-parallel engine's persistent kernel (k_run_par) and its host loop.
 #include <vector>
 #define NS_NO_WIDE      // one-event-per-lane runs live in k_run_seq / k_run_ens only: k_run_par's code layout is touchy (profiles/README.md r1-f)
+#define NS_NO_CLIENTS   // ... and so do the behaviour-library hooks: simulations with client behaviour run k_run_par_cl (ns_par_cl.cu)
 #include "ns_par_dev.cuh"
 
 #define NS_KERNEL_DECL __global__ void __launch_bounds__(PAR_THREADS, PAR_MIN_BLOCKS) k_run_par(const Sim *sp, const SeqScratch *scrp, ParScratch P)
@@ -18,18 +19,19 @@ int par_grid(const void *kernel, int sm_count, int *grid, size_t dyn_smem){
 	return 0;
 }
 int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches){
+	const void *kernel = S.has_clients ? par_kernel_cl() : (const void *)k_run_par;   // same engine, with / without the behaviour hooks
 	{	// per device: the hub path keeps a node's flows in dynamic shared memory
-		cudaError_t e0 = cudaFuncSetAttribute(k_run_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HubSmem));
+		cudaError_t e0 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HubSmem));
 		if (e0 != cudaSuccess) return (int)e0;
 	}
-	int grid = 0, rc = par_grid((const void *)k_run_par, sm_count, &grid, sizeof(HubSmem));
+	int grid = 0, rc = par_grid(kernel, sm_count, &grid, sizeof(HubSmem));
 	if (rc) return rc;
 	// The grid engine runs until it is done or asks for the single-warp engine (a sparse phase: many
 	// timestamps with a handful of events each, where six grid barriers per timestamp cost more than
 	// the events); that one hands back at the first timestamp that spans many ring tiles.
 	for (int round = 0; round < 1 << 20; round++) {
 		void *args[] = { (void *)&d_sim, (void *)&d_scr, (void *)&p };
-		cudaError_t e = cudaLaunchCooperativeKernel((void *)k_run_par, dim3(grid), dim3(PAR_THREADS), args, sizeof(HubSmem), stream);
+		cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(PAR_THREADS), args, sizeof(HubSmem), stream);
 		if (e != cudaSuccess) return (int)e;
 		(*launches)++;
 		int flags[3];                                                     // sparse_mode, want_sparse, want_dense

@@ -105,6 +105,8 @@ int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count,
 // ns_ens.cu: one CTA per replica (the batch engine at CTA scope)
 int ens_launch_run(const Sim *d_sims, const SeqScratch *d_scr, const ParScratch *d_pars, int n, cudaStream_t stream);
 int ens_preload(void);
+// ns_par_cl.cu: k_run_par with the behaviour-library hooks
+const void *par_kernel_cl(void);
 // ns_par.cu
 int par_run(const Sim &S, const Sim *d_sim, const SeqScratch *d_scr, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
 int par_preload(void);

@@ -175,6 +175,13 @@ __device__ __noinline__ bool seq_handle_l(Ctx &c, double m, u64 seq, int slot){
 		if (!(slot & 1)) { cnt_add(c, NS_CNT_FLOW_DONE, 1); handle_flow_done(c, f); host_report(c, EV_FLOW_DONE, f, 0, 0, -1); }
 		else if (S.f_drain_type[f] == EV_FLOW_SPEED_THROTTLE) { cnt_add(c, NS_CNT_THROTTLE, 1); handle_throttle(c, f); host_report(c, EV_FLOW_SPEED_THROTTLE, f, 0, 0, -1); }
 		else { cnt_add(c, NS_CNT_DRAIN, 1); trace_row(c, EV_FLOW_DRAIN, S.f_ord[f], 0, 0); host_report(c, EV_FLOW_DRAIN, f, 0, 0, -1); }   // no default handler (main.c:44-48)
+#ifndef NS_NO_CLIENTS
+	} else if (slot >= 2*S.cap_flows+S.cap_users) {                      // a client's own USER event (d->e, client_behaviour.c:31-34)
+		const int n = slot-2*S.cap_flows-S.cap_users;
+		cnt_add(c, NS_CNT_USER, 1);
+		trace_row(c, EV_USER, 0x40000000u|(unsigned)n, (double)S.c_ue_type[n], 0);
+		client_user_event(c, n);
+#endif
 	} else {
 		int u = slot-2*S.cap_flows;
 		int g = S.u_group[u];
@@ -220,7 +227,8 @@ __device__ bool seq_handle_ring(Ctx &c, double m, u64 seq){
 #define NS_REC_RESERVE (1u << 20)
 // script operations an L-table event will run (a USER event's group, the on-done group of a FLOW_DONE)
 __device__ __forceinline__ int l_entry_ops(const Sim &S, int slot){
-	if (slot >= 2*S.cap_flows) { int g = S.u_group[slot-2*S.cap_flows]; return g >= 0 ? S.group_off[g+1]-S.group_off[g] : 0; }
+	if (slot >= 2*S.cap_flows+S.cap_users) return 0;                   // a client's own event: one node-state record at most
+	if (slot >= 2*S.cap_flows) { int g = S.u_group[slot-2*S.cap_flows]; return g >= 0 ? (S.group_off[g+1]-S.group_off[g])*(S.has_clients ? S.n_srv/2+2 : 1) : 0; }   // a PLAY1 op is up to nsvr/2 creates
 	if ((slot & 1) || !S.n_ondone) return 0;
 	const int ord = S.f_ord[slot >> 1];
 	int lo = 0, hi = S.n_ondone-1;

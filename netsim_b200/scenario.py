@@ -18,13 +18,16 @@ import numpy as np
 
 MAGIC = 0x4353534E
 VERSION = 1
-OP_CREATE, OP_SCHED, OP_CLOSE, OP_END = 1, 2, 3, 4
+OP_CREATE, OP_SCHED, OP_CLOSE, OP_END, OP_PLAY1 = 1, 2, 3, 4, 5
+F_CLIENTS = 1
+CK_PLAIN, CK_CLIENT, CK_SERVER = 0, 1, 2
 
 OP_DTYPE = np.dtype([("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"),
                      ("start", "<i8"), ("x", "<f8"), ("y", "<f8")])
 RES_DTYPE = np.dtype([("owner", "<i4"), ("bit_rate", "<i4"), ("len", "<i8")])
 COPY_DTYPE = np.dtype([("node", "<i4"), ("res", "<i4")])
 ONDONE_DTYPE = np.dtype([("flow_ord", "<i4"), ("group", "<i4")])
+CLIENT_DTYPE = np.dtype([("kind", "<i4"), ("time_zone", "<i4"), ("lowwm", "<i4"), ("highwm", "<i4")])
 
 
 def create(src: int, dst: int, res: int, start: int, ub: float, delay: float):
@@ -43,6 +46,11 @@ def end():
     return (OP_END, 0, 0, 0, 0, 0.0, 0.0)
 
 
+def play1(client: int, res: int, metric: int = 0):
+    """client_new_play1(rid[res], node[client]) with fetch metric 0 = distance, 1 = share (needs Scenario.clients)"""
+    return (OP_PLAY1, client, metric, res, 0, 0.0, 0.0)
+
+
 @dataclass
 class Scenario:
     max_up: np.ndarray
@@ -52,6 +60,8 @@ class Scenario:
     groups: List[Sequence[tuple]] = field(default_factory=list)   # group 0 = init
     ondone: Dict[int, int] = field(default_factory=dict)          # flow ordinal -> group
     seed: int = 1
+    # behaviour library, client side (NS_SC_F_CLIENTS): one CLIENT_DTYPE row per node, or None
+    clients: np.ndarray | None = None
     # optional pre-packed op table (big generators build numpy directly)
     _ops: np.ndarray | None = None
     _group_off: np.ndarray | None = None
@@ -83,7 +93,8 @@ class Scenario:
         for i, (k, v) in enumerate(sorted(self.ondone.items())):
             od[i] = (k, v)
         n_groups = len(off) - 1
-        hdr = struct.pack("<IIII6i2i", MAGIC, VERSION, self.seed & 0xFFFFFFFF, 0,
+        flags = F_CLIENTS if self.clients is not None else 0
+        hdr = struct.pack("<IIII6i2i", MAGIC, VERSION, self.seed & 0xFFFFFFFF, flags,
                           self.n_nodes, len(self.resources), len(self.copies), n_groups,
                           len(ops), len(od), 0, 0)
         return b"".join([
@@ -95,6 +106,7 @@ class Scenario:
             np.ascontiguousarray(off, dtype="<i4").tobytes(),
             np.ascontiguousarray(ops, dtype=OP_DTYPE).tobytes(),
             od.tobytes(),
+            np.ascontiguousarray(self.clients, dtype=CLIENT_DTYPE).tobytes() if self.clients is not None else b"",
         ])
 
     def write(self, path: str) -> None:
@@ -427,6 +439,47 @@ def churn(n_users: int = 5000, n_servers: int = 16, rate: float = 1000.0, mean_s
         groups.append([end()])
         groups[0].append(sched(len(groups) - 1, sim_end))
     return Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, groups, {}, seed=1)
+
+
+def p2p_clients(n_clients: int = 200, n_servers: int = 4, n_catalogue: int = 6, play_seconds: float = 120.0, bit_rate: int = 2000,
+                arrival_window: float = 30.0, arrival_quantum: float = 0.05, metric: int = 1, lowwm: int = 0, highwm: int = 25000,
+                seed: int = 7, rand_seed: int = 1, end_time: float | None = None) -> Scenario:
+    """The client side of modules/p2p.c as a script (BASELINE.json configs[1] shape: servers + clients in server-only mode,
+    client_new_play = 0): `n_servers` servers (160000/160000 Kbit/s, p2p.c:144-145) hold the whole catalogue, `n_clients`
+    clients (8000 up / 40000 down, water marks 0 / 25000, p2p.c:166-173) each start ONE play at a USER event
+    (NS_OP_PLAY1 = client_new_play1: server_picker_opt1 over the servers with the share or distance metric, nsvr/2 strips,
+    client_start_play), then run the water-mark state machine of client_behaviour.c on every speed change until the
+    resource has been played (DONE_PLAY).  Time zones 24*i/n as p2p.c:146,171."""
+    rng = np.random.default_rng(seed)
+    n = n_servers + n_clients
+    idx = np.arange(n)
+    is_srv = idx < n_servers
+    tz = np.where(is_srv, _tz(idx, n_servers), _tz(idx - n_servers, n_clients))
+    mu = np.where(is_srv, 160000.0, 8000.0)
+    md = np.where(is_srv, 160000.0, 40000.0)
+    res = np.zeros(n_catalogue, dtype=RES_DTYPE)
+    res["owner"] = rng.integers(0, n_servers, n_catalogue)
+    res["len"] = (play_seconds * (0.5 + rng.random(n_catalogue))).astype(np.int64) * bit_rate     # rlen*rbr, resource.c:41
+    res["bit_rate"] = bit_rate
+    cp = np.array([(s_, r) for r in range(n_catalogue) for s_ in range(n_servers) if s_ != res["owner"][r]], dtype=COPY_DTYPE).reshape(-1)
+    cl = np.zeros(n, dtype=CLIENT_DTYPE)
+    cl["kind"] = np.where(is_srv, CK_SERVER, CK_CLIENT)
+    cl["time_zone"] = tz
+    cl["lowwm"] = lowwm
+    cl["highwm"] = highwm
+    if arrival_window > 0:
+        t_arr = np.floor(rng.random(n_clients) * arrival_window / arrival_quantum) * arrival_quantum
+    else:                                         # modules/p2p.c:178: gaussian_noise_nz(900, 3600), i.e. N(3600 s, 900 s) clipped at 0, not quantised
+        t_arr = np.maximum(0.0, rng.normal(3600.0, 900.0, n_clients))
+    want = rng.integers(0, n_catalogue, n_clients)
+    groups: List[List[tuple]] = [[]]
+    for c_ in np.argsort(t_arr, kind="stable"):
+        groups.append([play1(n_servers + int(c_), int(want[c_]), metric)])
+        groups[0].append(sched(len(groups) - 1, float(t_arr[c_])))
+    if end_time is not None:
+        groups.append([end()])
+        groups[0].append(sched(len(groups) - 1, end_time))
+    return Scenario(mu.astype("<f8"), md.astype("<f8"), res, cp, groups, {}, seed=rand_seed, clients=cl)
 
 
 def churn_fast(n_users: int = 1000000, n_servers: int = 1024, rate: float = 1000.0, mean_session: float = 600.0,

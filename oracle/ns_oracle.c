@@ -663,6 +663,7 @@ ns_oracle *ns_oracle_create(const void *scenario, size_t len, int want_trace, in
 	memcpy(&o->H, o->blob, sizeof o->H);
 	struct ns_sc_header *H = &o->H;
 	if (H->magic != NS_SC_MAGIC || H->version != NS_SC_VERSION) { o->status = NS_O_BAD_SCENARIO; return o; }
+	if (H->flags) { o->status = NS_O_BAD_SCENARIO; return o; }   /* scripts with client behaviour (NS_SC_F_CLIENTS) are checked against the compiled reference itself */
 	size_t need = sizeof *H+(size_t)H->n_nodes*16+(size_t)H->n_resources*sizeof(struct ns_sc_resource)+
 		(size_t)H->n_copies*sizeof(struct ns_sc_copy)+(size_t)(H->n_groups+1)*4+
 		(size_t)H->n_ops*sizeof(struct ns_sc_op)+(size_t)H->n_ondone*sizeof(struct ns_sc_ondone);

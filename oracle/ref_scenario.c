@@ -31,6 +31,7 @@
 #include "flow.h"
 #include "record.h"
 #include "uthash.h"
+#include "client_behaviour.h"   /* the reference's behaviour library, client side: modules/client_behaviour.{h,c}, p2p_common.h */
 
 #include "ns_scenario.h"
 
@@ -57,8 +58,16 @@ static struct timespec t_init_done;
 static const char *stats_path;
 static struct sim_state *S;
 
-static double sc_bw(void *a, void *b){ return cur_ub; }
-static double sc_dly(void *a, void *b){ return cur_delay; }
+/* scripts with NS_SC_F_CLIENTS: nodes carry the reference's struct def_user (first member, so that the library's casts work) */
+struct cl_user { struct def_user d; int index; };
+static struct ns_sc_client *clients;
+static int has_clients, in_play;
+
+/* s->bwcalc / s->dlycalc (flow.c:303-309): explicit per-op values for NS_OP_CREATE, the reference's own distance rules
+ * (p2p_common.h:181-189,214-221) for the flows client_new_play1 establishes */
+static double sc_bw(void *a, void *b){ return in_play ? distance_based_bw(a, b) : cur_ub; }
+static double sc_dly(void *a, void *b){ return in_play ? distance_based_delay(a, b) : cur_delay; }
+static int is_client(struct node *n){ return has_clients && n->user_data && ((struct def_user *)n->user_data)->nt == N_IDLE; }
 
 static void *xread(FILE *f, size_t n, size_t sz){
 	void *p = calloc(n ? n : 1, sz);
@@ -84,25 +93,50 @@ static void trace_row(uint32_t type, uint32_t ord, double t, double v0, double v
 	fwrite(&r, sizeof r, 1, trace);
 }
 
+static void note_flow(struct flow *f){
+	if (nflows == cap_flows) {
+		cap_flows = cap_flows ? cap_flows*2 : 1024;
+		flows = realloc(flows, cap_flows*sizeof *flows);
+	}
+	int ord = nflows++;
+	flows[ord] = f;
+	if (f) {
+		struct fl_ent *e = calloc(1, sizeof *e);
+		e->f = f; e->ord = ord;
+		HASH_ADD_PTR(by_ptr, f, e);
+		n_create++;
+	}
+}
+
 static void run_group(int g, struct sim_state *s){
 	for (int i = group_off[g]; i < group_off[g+1]; i++) {
 		struct ns_sc_op *o = &ops[i];
 		switch (o->kind) {
+		case NS_OP_PLAY1: {
+			/* the reference's own client_new_play1 (client_behaviour.c:364-387): server_picker_opt1 + qselect_eval,
+			 * client_new_connection per kept server, client_start_play */
+			struct def_sim *ds = s->user_data;
+			struct node *cl = nodes[o->a];
+			struct list_head *old = cl->conns[1].next;
+			ds->fetch_metric = o->b ? share_metric : distance_metric;
+			in_play = 1;
+			client_new_play1(rids[o->c], cl, s);
+			in_play = 0;
+			/* the flows it established are at the head of the client's receive list, newest first: they take the next
+			 * creation ordinals in creation order */
+			int k = 0;
+			for (struct list_head *h = cl->conns[1].next; h != &cl->conns[1] && h != old; h = h->next) k++;
+			struct flow **nf = calloc(k ? k : 1, sizeof *nf);
+			int j = k;
+			for (struct list_head *h = cl->conns[1].next; h != &cl->conns[1] && h != old; h = h->next)
+				nf[--j] = list_entry(h, struct flow, conns[1]);
+			for (j = 0; j < k; j++) note_flow(nf[j]);
+			free(nf);
+			break; }
 		case NS_OP_CREATE: {
-			if (nflows == cap_flows) {
-				cap_flows = cap_flows ? cap_flows*2 : 1024;
-				flows = realloc(flows, cap_flows*sizeof *flows);
-			}
 			cur_ub = o->x; cur_delay = o->y;
 			struct flow *f = sim_establish_flow(rids[o->c], (size_t)o->start, nodes[o->a], nodes[o->b], s);
-			int ord = nflows++;
-			flows[ord] = f;
-			if (f) {
-				struct fl_ent *e = calloc(1, sizeof *e);
-				e->f = f; e->ord = ord;
-				HASH_ADD_PTR(by_ptr, f, e);
-				n_create++;
-			}
+			note_flow(f);
 			break; }
 		case NS_OP_SCHED: {
 			struct event *e = event_new(o->c ? s->now+o->x : o->x, USER, (void *)(intptr_t)o->a);
@@ -137,6 +171,16 @@ static void count_event(struct event *e, struct sim_state *s){
 }
 
 static void on_user(struct event *e, struct sim_state *s){
+	if (has_clients && (uintptr_t)e->data >= (uintptr_t)H.n_groups+4096) {
+		/* a client's own event d->e (client_behaviour.c:31-34): what modules/p2p.c:59-67 does with it */
+		struct user_event *ue = e->data;
+		struct cl_user *cu = (struct cl_user *)ue->d;
+		trace_row(USER, 0x40000000u|(uint32_t)cu->index, s->now, (double)ue->type, 0);
+		client_next_state_from_event(e, s);
+		client_handle_next_state(cu->d.n, s);
+		count_event(e, s);
+		return;
+	}
 	int g = (int)(intptr_t)e->data;
 	trace_row(USER, g, s->now, 0, 0);
 	run_group(g, s);
@@ -147,6 +191,7 @@ static void on_speed(struct event *e, struct sim_state *s){
 	struct spd_event *se = e->data;
 	if (trace)
 		trace_row(SPEED_CHANGE | (se->type << 8), ord_of(se->f), s->now, se->speed, se->f->speed[se->type]);
+	if (is_client(se->f->peer[1])) client_speed_change(e, s);          /* modules/p2p.c:184 */
 	count_event(e, s);
 }
 
@@ -164,6 +209,7 @@ static void on_done(struct event *e, struct sim_state *s){
 	struct flow *f = e->data;
 	int ord = ord_of(f);
 	trace_row(FLOW_DONE, ord, s->now, f->drng->len, f->speed[1]);
+	if (is_client(f->peer[1])) client_done(e, s);                      /* modules/p2p.c:113-120 */
 	int g = H.n_ondone ? ondone_group(ord) : -1;
 	if (g >= 0)
 		run_group(g, s);
@@ -175,6 +221,7 @@ static void on_done(struct event *e, struct sim_state *s){
 static void on_throttle(struct event *e, struct sim_state *s){
 	struct flow *f = e->data;
 	trace_row(FLOW_SPEED_THROTTLE, ord_of(f), s->now, f->speed[0], f->speed[1]);
+	if (is_client(f->peer[1])) client_speed_throttle(e, s);            /* modules/p2p.c:182 */
 	count_event(e, s);
 }
 
@@ -232,6 +279,8 @@ void scenario_init(struct sim_state *s){
 	group_off = xread(f, H.n_groups+1, sizeof(int32_t));
 	ops = xread(f, H.n_ops, sizeof *ops);
 	ondone = xread(f, H.n_ondone, sizeof *ondone);
+	has_clients = (H.flags & NS_SC_F_CLIENTS) != 0;
+	if (has_clients) clients = xread(f, H.n_nodes, sizeof *clients);
 	fclose(f);
 	if (tr && *tr) trace = fopen(tr, "wb");
 
@@ -244,12 +293,40 @@ void scenario_init(struct sim_state *s){
 	s->bwcalc = sc_bw;
 	s->dlycalc = sc_dly;
 
+	struct def_sim *ds = NULL;
+	if (has_clients) {                                                 /* modules/p2p.c:124-141 */
+		init_sim_size(s, 20, sizeof(struct def_sim)+16);
+		ds = s->user_data;
+		ds->eval_size = H.n_nodes+1;
+		ds->eval_table = realloc(ds->eval_table, ds->eval_size*sizeof(struct nv_pair));
+		ds->fetch_metric = distance_metric; ds->push_metric = distance_metric; ds->new_conn_cb = NULL;
+	}
 	nodes = calloc(H.n_nodes, sizeof *nodes);
 	for (int i = 0; i < H.n_nodes; i++) {
 		nodes[i] = sim_create_node(s);
 		nodes[i]->user_data = NULL;
 		nodes[i]->maximum_bandwidth[0] = max_up[i];
 		nodes[i]->maximum_bandwidth[1] = max_down[i];
+		if (has_clients && clients[i].kind != NS_CK_PLAIN) {
+			struct cl_user *cu = calloc(1, sizeof *cu);
+			cu->index = i;
+			cu->d.n = nodes[i];
+			cu->d.time_zone = clients[i].time_zone;
+			cu->d.lowwm = clients[i].lowwm; cu->d.highwm = clients[i].highwm;
+			nodes[i]->user_data = &cu->d;
+			if (clients[i].kind == NS_CK_SERVER) {                     /* p2p_new_server, p2p_common.h:101-115 */
+				sim_node_change_state(nodes[i], N_SERVER, s);
+				cu->d.next_state = nodes[i]->state;
+				cu->d.nt = N_SERVER;
+				struct server *ss = talloc(1, struct server);
+				ss->n = nodes[i];
+				list_add(&ss->servers, &ds->servers);
+				ds->nsvr++;
+			} else {                                                   /* modules/p2p.c:166-174 */
+				cu->d.nt = N_IDLE;
+				nodes[i]->state = N_IDLE;
+			}
+		}
 	}
 	rids = calloc(H.n_resources ? H.n_resources : 1, sizeof *rids);
 	struct resource **rp = calloc(H.n_resources ? H.n_resources : 1, sizeof *rp);

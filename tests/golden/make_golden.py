@@ -27,6 +27,12 @@ def cases():
     yield "churn150", S.churn(150, 4, rate=100.0, mean_session=1.5, sim_end=4.0), 0
     for name, sc in S.edge_cases().items():
         yield "edge_" + name, sc, 0
+    # behaviour library, client side (NS_SC_F_CLIENTS): the reference's OWN client_new_play1 / water-mark handlers run
+    # inside the replay module (oracle/ref_scenario.c links modules/client_behaviour.c)
+    yield "clients_play40", S.p2p_clients(40, 4, play_seconds=60.0), 0
+    yield "clients_saturated", S.p2p_clients(90, 2, play_seconds=150.0, arrival_window=8.0, metric=1), 0
+    yield "clients_distance", S.p2p_clients(70, 6, play_seconds=80.0, metric=0, arrival_window=3.0, arrival_quantum=0.1), 0
+    yield "clients_cut", S.p2p_clients(120, 4, play_seconds=300.0, arrival_window=6.0, end_time=40.0), 0
 
 
 def main():

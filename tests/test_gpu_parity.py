@@ -367,3 +367,44 @@ def test_engine_bench_scale_matches_oracle(built):
     assert e.flow_state(sc.n_creates()).tobytes() == o.flow_state(sc.n_creates()).tobytes()
     e.close()
     o.close()
+
+
+# ---------------------------------------------------------------- behaviour library, client side, on the device
+CLIENT_CASES = [c for c in CASES if c[0].startswith("clients_")]
+
+
+@pytest.mark.parametrize("mode", [E.MODE_AUTO, E.MODE_SEQ], ids=["cta_per_replica", "warp_per_replica"])
+def test_client_behaviour_in_ensembles_matches_reference_fixtures(built, mode):
+    """the client fixtures (records of the reference running its own modules/client_behaviour.c) as replicas of one ensemble"""
+    scs = [z["scenario"].tobytes() for _, z in CLIENT_CASES]
+    ens = E.Ensemble(scs, mode=mode, record_cap=1 << 16, ring_cap=1 << 16)       # record buffers folded several times
+    ens.run(0)
+    for (name, z), d in zip(CLIENT_CASES, ens.digests()):
+        assert d["status"] == 0, name
+        assert d["events"] == int(z["events"]), name
+        assert d["record_bytes"] == len(z["records"]), name
+        assert d["record_hash"] == E.stream_hash(z["records"].tobytes()), name
+    ens.close()
+
+
+@pytest.mark.parametrize("mname,mode", MODES)
+@pytest.mark.parametrize("cfg", [dict(n_clients=300, n_servers=4, play_seconds=200.0, arrival_window=20.0, metric=1),
+                                 dict(n_clients=200, n_servers=6, play_seconds=100.0, arrival_window=5.0, arrival_quantum=0.1, metric=0),
+                                 dict(n_clients=600, n_servers=8, play_seconds=300.0, arrival_window=10.0, end_time=80.0),
+                                 dict(n_clients=400, n_servers=4, n_catalogue=10, play_seconds=900.0, arrival_window=0, metric=1)],
+                         ids=["saturated_share", "distance_metric", "cut_by_sim_end", "gauss_arrivals_config2_shape"])
+def test_client_behaviour_matches_live_reference(built, cfg, mname, mode):
+    """mid-size p2p client scripts (client_new_play1 + water-mark machine + node-state records on the device) against a LIVE
+    run of the compiled reference, which executes the reference's own client_behaviour.c: records and fp64 trace identical"""
+    if not refrun.available():
+        pytest.skip("oracle/_ref not shipped")
+    b = S.p2p_clients(**cfg).to_bytes()
+    r = refrun.run_reference(b, trace=True, record=True)
+    assert r["returncode"] == 0, r["stderr"]
+    e, st = run_engine(b, mode, trace_cap=len(r["trace"]) + 16, record_cap=len(r["records"]) + (4 << 20))
+    assert st == 0
+    assert e.records() == r["records"]
+    assert e.trace().tobytes() == r["trace"].tobytes()
+    c = e.counters()
+    assert c["events"] == r["stats"]["events"] and c["user"] == r["stats"]["user"] and c["user"] > cfg["n_clients"]
+    e.close()

@@ -8,7 +8,10 @@ from conftest import golden_cases, pick_golden
 from netsim_b200 import scenario as S
 from oracle import pyoracle, refrun
 
-CASES = golden_cases()
+ALL_CASES = golden_cases()
+# scripts with client behaviour are outside the CPU restatement: their oracle is the compiled reference itself
+CASES = [c for c in ALL_CASES if not c[0].startswith("clients_")]
+CLIENT_CASES = [c for c in ALL_CASES if c[0].startswith("clients_")]
 
 
 @pytest.mark.parametrize("name,z", CASES, ids=[c[0] for c in CASES])
@@ -127,3 +130,29 @@ def test_picker_oracle_vs_live_reference(built):
         v1, n1, v2, n2 = val.copy(), node.copy(), val.copy(), node.copy()
         assert R.ref_pick_opt1(v1.ctypes.data, n1.ctypes.data, c, k) == L.ns_oracle_pick_opt1(v2.ctypes.data, n2.ctypes.data, c, k)
         assert (v1 == v2).all() and (n1 == n2).all()
+
+
+@pytest.mark.parametrize("name,z", CLIENT_CASES, ids=[c[0] for c in CLIENT_CASES])
+def test_client_fixtures_are_what_the_reference_does(name, z, built):
+    """the committed client-behaviour fixtures against a LIVE run of the compiled reference (its own
+    modules/client_behaviour.c inside oracle/ref_scenario.c), optimised and assert-enabled builds"""
+    if not refrun.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for debug in (False, True):
+        r = refrun.run_reference(z["scenario"].tobytes(), max_events=int(z["max_events"]), trace=True, debug=debug)
+        assert r["returncode"] == 0, r["stderr"]
+        assert r["records"] == z["records"].tobytes()
+        assert r["trace"].tobytes() == z["trace"].tobytes()
+    # the fixtures do exercise the state machine: node-state records (minor 7) beyond the servers' N_SERVER ones
+    rec = z["records"].tobytes()
+    n_state, p = 0, 0
+    while p < len(rec):
+        minor, nb = rec[p + 1], int.from_bytes(rec[p + 12:p + 13], "big", signed=True)
+        n_state += minor == 7
+        p += 13 + (1 if nb == 1 else 4 if nb == 4 else 6)
+    assert p == len(rec) and n_state > 20
+
+
+def test_oracle_rejects_client_scripts(built):
+    o = pyoracle.Oracle(CLIENT_CASES[0][1]["scenario"].tobytes())
+    assert o.run(0) != 0

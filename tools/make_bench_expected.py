@@ -3,6 +3,7 @@ pinned to the compiled reference by tests/test_oracle_golden.py) and committed a
 bench.py compares the device engine's digest after its last window against it (outside the timed region).
     python tools/make_bench_expected.py [ranks] [total_events]
     python tools/make_bench_expected.py ensemble [peers]        digests of sampled replicas of bench.py --workload ensemble
+    python tools/make_bench_expected.py p2p1k                   digests of sampled replicas of --workload ensemble --ens-kind p2p1k (compiled reference)
     python tools/make_bench_expected.py churn [total_events]    digest of bench.py --workload churn after its last window
 """
 import json
@@ -72,6 +73,31 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "churn":
     cur = json.load(open(path))
     cur[f"churn,users={a.churn_users},init={a.churn_init},session={a.churn_session},end={a.churn_end},rank=0,events={total}"] = r
     print(r)
+    json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    sys.exit(0)
+
+def p2p_one(seed_index):
+    """config-2-shaped replicas run the behaviour library: their digest comes from the COMPILED REFERENCE (oracle/_ref)"""
+    import argparse
+    import bench
+    from netsim_b200 import engine as E
+    from oracle import refrun
+    sc = bench.ens_script(argparse.Namespace(ens_kind="p2p1k", ens_peers=0), seed_index)
+    r = refrun.run_reference(sc.to_bytes(), trace=False, record=True)
+    assert r["returncode"] == 0, r["stderr"]
+    return {"seed": seed_index, "status": 0, "events": r["stats"]["events"], "solves": None, "record_bytes": len(r["records"]),
+            "record_hash": E.stream_hash(r["records"]), "source": "compiled reference (oracle/_ref/netsim + modules/scenario.so)"}
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "p2p1k":
+    seeds = [0, 1, 2, 3, 7, 100, 511, 1023]
+    with ProcessPoolExecutor(max_workers=4) as ex:
+        res = list(ex.map(p2p_one, seeds))
+    path = os.path.join(ROOT, "tests", "golden", "bench_expected.json")
+    cur = json.load(open(path))
+    for r in res:
+        cur[f"ensemble,kind=p2p1k,seed={r['seed']}"] = r
+        print(r)
     json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
     sys.exit(0)
 
