@@ -547,8 +547,11 @@ def ensemble_main(args, rank, local_rank, world):
         t_gen = time.perf_counter() - t0
         t1 = time.perf_counter()
         ens = E.Ensemble(scs, device=local_rank, records=True, ring_cap=1 << (17 if args.ens_kind == "p2p1k" else 20), record_cap=(2 if args.ens_kind == "p2p1k" else 8) << 20, mode=E.MODE_AUTO)
+        if args.ens_kind == "p2p1k":
+            ens.analysis_begin(3600.0)                       # analyzer reductions on the device, from the records while they are produced
         ens.run(0)
         dg = ens.digests()
+        ana = ens.analysis() if args.ens_kind == "p2p1k" else None
         tab = torch.zeros(n_total, 6, dtype=torch.int64)
         for i, d in zip(mine, dg):
             tab[i] = torch.tensor([d["events"], d["solves"], d["record_bytes"], d["record_hash"] & 0x7FFFFFFFFFFFFFFF, d["status"],
@@ -559,7 +562,12 @@ def ensemble_main(args, rank, local_rank, world):
         torch.cuda.synchronize()
         wall = time.perf_counter() - t1
         cs = ens.counters_sum()
-        out = {"device_ms": ens.device_ms, "wall": wall, "gen": t_gen, "launches": ens.launches, "digests": tab.cpu(), "counters": cs,
+        summary = None
+        if ana:                                              # what a sweep would keep per replica instead of its records
+            summary = {"stale_client_seconds": float(sum(a["stale"].sum() for a in ana)), "max_stale_clients_in_a_replica": int(max(a["stale_max"] for a in ana)),
+                       "server_out_Kbit": float(sum(a["usage"][0, 0].sum() for a in ana)), "client_in_Kbit": float(sum(a["usage"][2, 1].sum() for a in ana)),
+                       "state_records": int(sum(a["state_records"] for a in ana)), "usage_records": int(sum(a["usage_records"] for a in ana))}
+        out = {"device_ms": ens.device_ms, "wall": wall, "gen": t_gen, "launches": ens.launches, "digests": tab.cpu(), "counters": cs, "analysis": summary,
                "h2d": sum(len(b) for b in scs), "d2h": 56 * len(mine)}
         ens.close()
         return out
@@ -622,6 +630,7 @@ def ensemble_main(args, rank, local_rank, world):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / world / (dev_ms_max / 1e3) / 1e9          # per GPU: the kernel of the slowest rank against one GPU's HBM
     config.update({"events": int(events_all), "solves_per_s": solves_all / (dev_ms_max / 1e3), "record_bytes_hashed_on_device": int(rec_bytes),
+                   "analysis_rank0": passes[0]["analysis"],
                    "device_ms_per_rank": [round(x, 1) for x in per_rank], "script_generation_s": round(sum(p["gen"] for p in passes), 2),
                    "parity": {"checked": checked > 0, "ok": ok, "replicas_checked": checked,
                               "against": "digests of the compiled reference / the CPU oracle pinned to it (tests/golden/bench_expected.json, tools/make_bench_expected.py)"},

@@ -154,6 +154,21 @@ int  ns_ens_create(ns_ens **out, const void *const *scenarios, const size_t *len
 		   const struct ns_dev_opts *opts);
 int  ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms);
 int  ns_ens_digests(ns_ens *e, struct ns_digest *out, int n);
+/* analyzer reductions on the device, from each replica's record stream while it is produced (analyzer/analyzers.c:80-101 node
+ * classes, :226-297 + :153-180 per-class bandwidth per period, :384-431 stale clients): call ns_ens_analysis_begin before ns_ens_run,
+ * ns_ens_analysis afterwards.  usage[class][dir][k] = integral over period k of the summed R_USAGE of the class's nodes (Kbit;
+ * divide by the period for the analyzer's per-period average), class 0 server / 1 cloud / 2 client, dir 0 out / 1 in;
+ * stale[k] = client-seconds spent in N_STALE in period k.  Sums are order-dependent: ~1e-12 relative to the sequential analyzer. */
+#define NS_ANA_BUCKETS 24
+struct ns_ana_summary {
+	uint64_t off, records, usage_records, state_records;
+	double t_last;
+	double usage[3][2][NS_ANA_BUCKETS];
+	double stale[NS_ANA_BUCKETS];
+	int32_t stale_now, stale_max;
+};
+int  ns_ens_analysis_begin(ns_ens *e, double period);
+int  ns_ens_analysis(ns_ens *e, struct ns_ana_summary *out, int n);
 int  ns_ens_counters_sum(ns_ens *e, uint64_t out[NS_CNT_COUNT]);   /* enum ns_counter, summed over the replicas (max for NS_CNT_MAX_BATCH) */
 uint64_t ns_ens_launches(ns_ens *e);
 void ns_ens_destroy(ns_ens *e);

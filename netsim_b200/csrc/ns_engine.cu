@@ -14,6 +14,7 @@
 
 #include "ns_sim.cuh"
 #include "ns_par_api.cuh"
+#include "ns_ana.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "netsim_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return (int)e_; } } while (0)
 
@@ -817,6 +818,8 @@ __global__ void __launch_bounds__(256) k_ens_digest(const Sim *sims, const EnsAc
 	}
 }
 
+struct ns_ens;
+static bool S_rec_ok(ns_ens *e);
 struct ns_ens {
 	int device = 0, n = 0;
 	std::vector<HostSim> sims;
@@ -825,9 +828,12 @@ struct ns_ens {
 	cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
 	uint64_t launches = 0;
 	char *arena = nullptr;          // every table of every replica
+	// analyzer reductions (ns_ana.cu): per-replica stream state, one arena
+	bool ana_on = false; AnaStream *d_ana = nullptr; ns_ana_summary *d_sum = nullptr; char *ana_arena = nullptr;
 	EnsAcc *d_acc = nullptr; int *d_more = nullptr; ns_digest *d_dig = nullptr;
 };
 
+static bool S_rec_ok(ns_ens *e){ for (auto &h : e->sims) if (!h.S.want_rec) return false; return true; }   // the analysis reads records
 static int ens_init(ns_ens *e, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts &o);
 extern "C" void ns_ens_destroy(ns_ens *e);
 extern "C" int ns_ens_create(ns_ens **out, const void *const *scenarios, const size_t *lens, int n, const ns_dev_opts *opts){
@@ -906,6 +912,7 @@ extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms)
 		} else {
 			int rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc;
 		}
+		if (e->ana_on) { int rc = ana_launch(e->d_ana, e->n, 0, e->stream); if (rc) return rc; e->launches++; }   // before anything is folded away
 		k_ens_drain<<<e->n, 256, 0, e->stream>>>(e->d_sims, e->d_acc, e->n, e->d_more);
 		CK(cudaGetLastError());
 		e->launches += 2;
@@ -929,6 +936,66 @@ extern "C" int ns_ens_digests(ns_ens *e, ns_digest *out, int n){
 	CK(cudaGetLastError());
 	e->launches++;
 	CK(cudaMemcpyAsync(out, e->d_dig, sizeof(ns_digest)*n, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+// ---- analyzer reductions over every replica's record stream (ns_ana.cu)
+extern "C" int ns_ens_analysis_begin(ns_ens *e, double period){
+	if (!e || !(period > 0) || e->ana_on) return NS_E_ARG;
+	CK(cudaSetDevice(e->device));
+	const int n = e->n;
+	auto al = [](size_t b){ return (b+255) & ~(size_t)255; };
+	std::vector<size_t> off(n+1, 0);
+	std::vector<uint32_t> hsz(n);
+	for (int i = 0; i < n; i++) {
+		const size_t N = (size_t)e->sims[i].S.n_nodes;
+		uint32_t h = 16; while (h < 2*N+2) h <<= 1;
+		hsz[i] = h;
+		off[i+1] = off[i]+al(h*4)+al(h*4)+al(N)+4*al(N*8)+al(N)+al(N*8);
+	}
+	CK(cudaMalloc(&e->ana_arena, off[n] ? off[n] : 8));
+	CK(cudaMalloc(&e->d_ana, sizeof(AnaStream)*n)); CK(cudaMalloc(&e->d_sum, sizeof(ns_ana_summary)*n));
+	CK(cudaMemset(e->ana_arena, 0, off[n] ? off[n] : 8));
+	CK(cudaMemset(e->d_sum, 0, sizeof(ns_ana_summary)*n));
+	std::vector<AnaStream> hs(n);
+	for (int i = 0; i < n; i++) {
+		const Sim &S = e->sims[i].S;
+		const size_t N = (size_t)S.n_nodes;
+		char *p = e->ana_arena+off[i];
+		AnaStream &A = hs[i];
+		A.rec = S.rec; A.rec_base = &S.st->rec_base; A.rec_len = &S.st->rec_len;
+		A.st = e->d_sum+i; A.n_nodes = (int)N; A.hmask = hsz[i]-1; A.period = period;
+		uint32_t *hk = (uint32_t *)p; p += al(hsz[i]*4);
+		int *hv = (int *)p; p += al(hsz[i]*4);
+		A.hkey = hk; A.hval = hv;
+		A.ntype = (uint8_t *)p; p += al(N);
+		for (int d = 0; d < 2; d++) { A.u_time[d] = (double *)p; p += al(N*8); A.u_val[d] = (double *)p; p += al(N*8); }
+		A.n_state = (int8_t *)p; p += al(N);
+		A.n_since = (double *)p; p += al(N*8);
+		// node id -> index (the ids were drawn on the host side of build_sim and live in S.n_id)
+		std::vector<uint32_t> ids(N), keys(hsz[i], 0); std::vector<int> vals(hsz[i], -1);
+		if (N) CK(cudaMemcpy(ids.data(), S.n_id, N*4, cudaMemcpyDeviceToHost));
+		for (size_t k = 0; k < N; k++) {
+			uint32_t h = (ids[k]*2654435761u) & A.hmask;
+			while (vals[h] >= 0) h = (h+1) & A.hmask;
+			keys[h] = ids[k]; vals[h] = (int)k;
+		}
+		CK(cudaMemcpy(hk, keys.data(), (size_t)hsz[i]*4, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(hv, vals.data(), (size_t)hsz[i]*4, cudaMemcpyHostToDevice));
+		if (N) { CK(cudaMemset(A.ntype, 2, N)); CK(cudaMemset(A.n_state, 0xff, N)); }     // everything is a client until a state record says otherwise; no state yet
+	}
+	CK(cudaMemcpy(e->d_ana, hs.data(), sizeof(AnaStream)*n, cudaMemcpyHostToDevice));
+	if (!S_rec_ok(e)) return NS_E_ARG;
+	e->ana_on = true;
+	return 0;
+}
+extern "C" int ns_ens_analysis(ns_ens *e, ns_ana_summary *out, int n){
+	if (!e || !out || !e->ana_on) return NS_E_ARG;
+	if (n > e->n) n = e->n;
+	CK(cudaSetDevice(e->device));
+	{ int rc = ana_launch(e->d_ana, e->n, 1, e->stream); if (rc) return rc; }
+	e->launches++;
+	CK(cudaMemcpyAsync(out, e->d_sum, sizeof(ns_ana_summary)*n, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
 }
@@ -963,6 +1030,9 @@ extern "C" void ns_ens_destroy(ns_ens *e){
 	if (e->d_sims) cudaFree(e->d_sims);
 	if (e->d_scr) cudaFree(e->d_scr);
 	if (e->d_pars) cudaFree(e->d_pars);
+	if (e->d_ana) cudaFree(e->d_ana);
+	if (e->d_sum) cudaFree(e->d_sum);
+	if (e->ana_arena) cudaFree(e->ana_arena);
 	if (e->d_acc) cudaFree(e->d_acc);
 	if (e->d_more) cudaFree(e->d_more);
 	if (e->d_dig) cudaFree(e->d_dig);

@@ -472,9 +472,17 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem 
 		WSYNC();
 		flow_close(c, f);
 	}
+#ifdef NS_PROFILE
+	u64 sp_t = 0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(sp_t));
+#define SEQ_MARK(id) do { u64 t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); if (lane == 0) c.st->phase_ns[id] += t_-sp_t; sp_t = t_; } while (0)
+#else
+#define SEQ_MARK(id) do { } while (0)
+#endif
 	while (true) {
 		if (seq_should_stop(c)) break;
+		SEQ_MARK(6);
 		double m = seq_find_tmin(c);
+		SEQ_MARK(0);
 		if (m == NS_INF) break;                                       // queue empty (main.c:50)
 		if (c.st->sparse_mode && !c.st->relay_seen) {
 			// sparse phase of a big simulation: a timestamp spread over many ring tiles is a batch for
@@ -488,9 +496,12 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem 
 			// (an ensemble switches engines in rounds over all replicas: there the warp keeps medium batches — its lanes take 32 events at a time)
 			if (hits > (ens_phase ? NS_ENS_MAX_HIT_TILES : NS_SPARSE_MAX_HIT_TILES)) { L0 { c.st->want_dense = 1; if (ens_phase) c.st->sparse_mode = 0; } __syncwarp(); break; }
 		}
+		SEQ_MARK(1);
 		int nr = seq_collect_ring(c, m);
 		if (nr < 0) { set_status(c, NS_E_BATCH_FULL); __syncwarp(); break; }
+		SEQ_MARK(2);
 		int nl = seq_collect_l(c, m, sc);
+		SEQ_MARK(3);
 		if (nr+nl == 0) continue;                                     // only stale lower bounds surfaced
 		u64 n_ops = 0;
 		for (int k = lane; k < nl; k += 32) n_ops += (u64)l_entry_ops(*c.S, sc.lb_ref[k]);
@@ -505,7 +516,9 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem 
 		cnt_add(c, NS_CNT_BATCHES, 1);
 		L0 { if ((u64)(nr+nl) > c.st->cnt[NS_CNT_MAX_BATCH]) c.st->cnt[NS_CNT_MAX_BATCH] = nr+nl; }
 		int pi = 0, pj = 0;
+		SEQ_MARK(4);
 		seq_process(c, m, pi, nr, pj, nl, sc, W);
+		SEQ_MARK(5);
 		if (pi < nr || pj < nl) seq_restore(c, m, pi, nr, pj, nl, sc);   // max_events / sim_end mid-batch
 		__syncwarp();
 	}

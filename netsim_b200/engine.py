@@ -38,6 +38,15 @@ class Digest(C.Structure):
                 ("status", C.c_int64)]
 
 
+ANA_BUCKETS = 24
+
+
+class AnaSummary(C.Structure):
+    _fields_ = [("off", C.c_uint64), ("records", C.c_uint64), ("usage_records", C.c_uint64), ("state_records", C.c_uint64),
+                ("t_last", C.c_double), ("usage", C.c_double * ANA_BUCKETS * 2 * 3), ("stale", C.c_double * ANA_BUCKETS),
+                ("stale_now", C.c_int32), ("stale_max", C.c_int32)]
+
+
 class RandState(C.Structure):
     _fields_ = [("st", C.c_int32 * 31), ("f", C.c_int32), ("r", C.c_int32)]
 
@@ -79,6 +88,8 @@ def lib():
         L.ns_ens_run.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]
         L.ns_ens_digests.argtypes = [C.c_void_p, C.POINTER(Digest), C.c_int]
         L.ns_ens_counters_sum.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ns_ens_analysis_begin.argtypes = [C.c_void_p, C.c_double]
+        L.ns_ens_analysis.argtypes = [C.c_void_p, C.POINTER(AnaSummary), C.c_int]
         L.ns_ens_launches.restype = C.c_uint64
         L.ns_ens_launches.argtypes = [C.c_void_p]
         L.ns_ens_destroy.argtypes = [C.c_void_p]
@@ -289,6 +300,24 @@ class Ensemble:
         if rc:
             raise NsError(rc, "ns_ens_digests")
         return [{k: getattr(x, k) for k, _ in Digest._fields_} for x in d]
+
+    def analysis_begin(self, period: float) -> None:
+        """analyzer reductions on the device while the replicas run (ns_ana.cu); call before run()"""
+        rc = self.L.ns_ens_analysis_begin(self.h, float(period))
+        if rc:
+            raise NsError(rc, "ns_ens_analysis_begin")
+
+    def analysis(self):
+        a = (AnaSummary * self.n)()
+        rc = self.L.ns_ens_analysis(self.h, a, self.n)
+        if rc:
+            raise NsError(rc, "ns_ens_analysis")
+        out = []
+        for x in a:
+            out.append({"records": int(x.records), "usage_records": int(x.usage_records), "state_records": int(x.state_records),
+                        "t_last": float(x.t_last), "usage": np.ctypeslib.as_array(x.usage).copy(), "stale": np.ctypeslib.as_array(x.stale).copy(),
+                        "stale_now": int(x.stale_now), "stale_max": int(x.stale_max)})
+        return out
 
     def counters_sum(self) -> dict:
         out = (C.c_uint64 * len(COUNTERS))()
