@@ -24,6 +24,8 @@ enum ns_op_kind {
 	NS_OP_SCHED  = 2, /* event_add(event_new(c ? now+x : x, USER, group a)) */
 	NS_OP_CLOSE  = 3, /* flow_close(flow created by the a-th executed CREATE), if still alive */
 	NS_OP_END    = 4, /* sim_end(): the event loop stops before the next pop (main.c:51-52) */
+	NS_OP_CANCEL = 6, /* ns_dev_exec only: event_remove (event.h:13-18) of a module-owned USER event; a = the slot ns_dev_exec
+	                     returned in .b for its NS_OP_SCHED */
 	NS_OP_PLAY1  = 5, /* client_new_play1(rid[c], node[a]) (modules/client_behaviour.c:364-387) with fetch metric b
 	                     (0 = distance_metric, 1 = share_metric, p2p_common.h:171-198): server_picker_opt1 over the
 	                     server nodes + qselect, one sim_establish_flow per kept server at strip i*strip with

@@ -329,7 +329,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		uint32_t id;
 		do { id = ns_rand_next_host(&g); draws++; } while (!used.insert(id).second);
 		nid[i] = id;
-		if (o.want_records) host_rec(rec, 0.0, R_NODE_CREATE, id, 1, 0);
+		if (o.want_records && (S.features & NS_FEAT_INIT_REC)) host_rec(rec, 0.0, R_NODE_CREATE, id, 1, 0);
 		if (has_clients && cl[i].kind == NS_CK_SERVER && o.want_records)
 			host_rec(rec, 0.0, R_NODE_STATE, id, 1, NST_SERVER);     // p2p_new_server: sim_node_change_state(n, N_SERVER), p2p_common.h:106
 	}
@@ -677,6 +677,7 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 		const ns_sc_op &op = ops[i];
 		if (op.kind == NS_OP_CREATE) { if (op.a < 0 || op.a >= d->h.S.n_nodes || op.b < 0 || op.b >= d->h.S.n_nodes || op.c < 0 || op.c >= d->h.S.n_rids) return NS_E_ARG; }
 		else if (op.kind == NS_OP_CLOSE) { if (op.a < 0) return NS_E_ARG; }
+		else if (op.kind == NS_OP_CANCEL) { if (op.a < 0 || op.a >= d->h.S.cap_users) return NS_E_ARG; }
 		else if (op.kind != NS_OP_SCHED && op.kind != NS_OP_END) return NS_E_ARG;
 	}
 	CK(cudaSetDevice(d->device));
@@ -752,7 +753,6 @@ extern "C" void ns_dev_destroy(ns_dev *d){
 // up (the engine's soft stop, host_stop == 2) — a word-aligned prefix is hashed at its stream position, the
 // odd tail bytes move to the front of the buffer — and the simulation goes on.  One CTA per replica, one
 // launch for the whole ensemble, one 4-byte read-back per round (how many replicas still want to run).
-struct EnsAcc { u64 hash; };
 __global__ void __launch_bounds__(256) k_ens_drain(const Sim *sims, EnsAcc *acc, int n, int *n_more){
 	const int s = blockIdx.x;
 	if (s >= n) return;
@@ -905,12 +905,13 @@ extern "C" int ns_ens_run(ns_ens *e, uint64_t max_events_each, float *device_ms)
 		if (e->cta_engine) {
 			// dense phases: one CTA per replica; sparse phases (streaks of tiny batches): one warp per replica, so that
 			// every replica of the ensemble is resident at once.  A replica switches engine at most once per round.
-			int rc = ens_launch_run(e->d_sims, e->d_scr, e->d_pars, e->n, e->stream); if (rc) return rc;
-			rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream, 1); if (rc) return rc;
+			AnaStream *ana = e->ana_on ? e->d_ana : nullptr;
+			int rc = ens_launch_run(e->d_sims, e->d_scr, e->d_pars, e->n, e->stream, e->d_acc, ana); if (rc) return rc;
+			rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream, 1, e->d_acc, ana); if (rc) return rc;
 			k_ens_handover<<<(e->n+127)/128, 128, 0, e->stream>>>(e->d_sims, e->n, e->d_more);
 			e->launches += 2;
 		} else {
-			int rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream); if (rc) return rc;
+			int rc = seq_launch_run(e->d_sims, e->d_scr, e->n, e->stream, 0, e->d_acc, e->ana_on ? e->d_ana : nullptr); if (rc) return rc;
 		}
 		if (e->ana_on) { int rc = ana_launch(e->d_ana, e->n, 0, e->stream); if (rc) return rc; e->launches++; }   // before anything is folded away
 		k_ens_drain<<<e->n, 256, 0, e->stream>>>(e->d_sims, e->d_acc, e->n, e->d_more);

@@ -10,7 +10,7 @@
 #define PAR_MIN_BATCH 33           // up to one warp's worth of events: the one-event-per-lane path; above: the whole CTA
 #include "ns_par_dev.cuh"
 
-#define NS_KERNEL_DECL __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_ens(const Sim *sims, const SeqScratch *scrs, const ParScratch *pars, int n_sims)
+#define NS_KERNEL_DECL __global__ void __launch_bounds__(PAR_THREADS, 1) k_run_ens(const Sim *sims, const SeqScratch *scrs, const ParScratch *pars, int n_sims, EnsAcc *ens_acc, AnaStream *ens_ana)
 #define NS_KERNEL_PROLOGUE \
 	CtaScope grid; \
 	if ((int)blockIdx.x >= n_sims) return; \
@@ -22,8 +22,8 @@ int ens_preload(void){
 	cudaError_t e = cudaFuncSetAttribute(k_run_ens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HubSmem));
 	return e == cudaSuccess ? 0 : (int)e;
 }
-int ens_launch_run(const Sim *d_sims, const SeqScratch *d_scr, const ParScratch *d_pars, int n, cudaStream_t stream){
-	k_run_ens<<<n, PAR_THREADS, sizeof(HubSmem), stream>>>(d_sims, d_scr, d_pars, n);
+int ens_launch_run(const Sim *d_sims, const SeqScratch *d_scr, const ParScratch *d_pars, int n, cudaStream_t stream, EnsAcc *acc, AnaStream *ana){
+	k_run_ens<<<n, PAR_THREADS, sizeof(HubSmem), stream>>>(d_sims, d_scr, d_pars, n, acc, ana);
 	cudaError_t e = cudaGetLastError();
 	return e == cudaSuccess ? 0 : (int)e;
 }

@@ -1196,7 +1196,15 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 			double t = op.c ? c.now+op.x : op.x;
 			if (ev_time_ok(c, t)) {
 				u64 seq = seq_reserve(c, 1);
-				L0 { S.u_group[u] = -(op.a+1); l_put(c, 2*S.cap_flows+u, seq, t); }
+				L0 { S.u_group[u] = -(op.a+1); l_put(c, 2*S.cap_flows+u, seq, t); S.host_ops[i].b = u; }   // result: the slot, for a later NS_OP_CANCEL
+			}
+			WSYNC();
+			break; }
+		case NS_OP_CANCEL: {                                           // event_remove of a module-owned event: the slot is free again
+			const int u = op.a;
+			if (S.l_time[2*S.cap_flows+u] != NS_INF && S.u_group[u] < 0) {
+				WSYNC();
+				L0 { S.l_time[2*S.cap_flows+u] = NS_INF; S.u_next_free[u] = c.st->free_user; c.st->free_user = u; }
 			}
 			WSYNC();
 			break; }

@@ -95,7 +95,7 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 
 // ---- launchers (each defined next to its kernel)
 // ns_seq.cu
-int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream, int ens_phase = 0);   // ens_phase: only the replicas in their sparse phase
+int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream, int ens_phase = 0, EnsAcc *acc = nullptr, AnaStream *ana = nullptr);   // ens_phase: only the replicas in their sparse phase; acc: ensemble replicas fold their records in place
 int seq_launch_init_groups(const Sim *d_sims, int n, cudaStream_t stream);
 int seq_launch_exec_ops(const Sim *d_sim, int n_ops, cudaStream_t stream);
 int seq_preload(void);
@@ -103,7 +103,7 @@ int seq_preload(void);
 int par_plan_init(ParScratch &p, const ns_sc_op *ops, int n0, int n_nodes);
 int par_init_group0(const Sim &S, const Sim *d_sim, ParScratch &p, int sm_count, cudaStream_t stream, uint64_t *launches);
 // ns_ens.cu: one CTA per replica (the batch engine at CTA scope)
-int ens_launch_run(const Sim *d_sims, const SeqScratch *d_scr, const ParScratch *d_pars, int n, cudaStream_t stream);
+int ens_launch_run(const Sim *d_sims, const SeqScratch *d_scr, const ParScratch *d_pars, int n, cudaStream_t stream, EnsAcc *acc, AnaStream *ana);
 int ens_preload(void);
 // ns_par_cl.cu: k_run_par with the behaviour-library hooks
 const void *par_kernel_cl(void);

@@ -25,16 +25,19 @@ __global__ void __launch_bounds__(32) k_exec_ops(const Sim *sp, int n_ops){
 }
 
 // one warp per simulation, strictly sequential event handling
-__global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n, int ens_phase){
+__global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n, int ens_phase, EnsAcc *acc, AnaStream *ana){
 	int s = blockIdx.x;
 	if (s >= n) return;
 	__shared__ WideSmem W;
-	seq_run(&sims[s], scr[s], threadIdx.x, &W, ens_phase);
+	__shared__ FoldSmem Fs;
+	EnsFold F;
+	F.acc = acc ? acc+s : nullptr; F.ana = ana ? ana+s : nullptr;
+	seq_run(&sims[s], scr[s], threadIdx.x, &W, ens_phase, acc ? &F : nullptr, &Fs);
 }
 
 static int launched(void){ cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : (int)e; }
-int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream, int ens_phase){
-	k_run_seq<<<n, 32, 0, stream>>>(d_sims, d_scr, n, ens_phase);
+int seq_launch_run(const Sim *d_sims, const SeqScratch *d_scr, int n, cudaStream_t stream, int ens_phase, EnsAcc *acc, AnaStream *ana){
+	k_run_seq<<<n, 32, 0, stream>>>(d_sims, d_scr, n, ens_phase, acc, ana);
 	return launched();
 }
 int seq_launch_init_groups(const Sim *d_sims, int n, cudaStream_t stream){

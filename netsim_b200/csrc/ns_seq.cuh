@@ -8,6 +8,7 @@
 // the batch is every pending event with time == t, in insertion order (FIFO ties, event.h:27-31).
 #pragma once
 #include "ns_model.cuh"
+#include "ns_ana_dev.cuh"
 
 namespace {   // internal linkage: every engine translation unit carries its own copy of the device code
 
@@ -414,6 +415,28 @@ __device__ __noinline__ void seq_wide_run(Ctx &c, double m, int &i, int end, Wid
 }
 #endif
 
+// fold the record buffer of an ensemble replica in place (one warp; rec_len = the bytes in the buffer): returns the new length
+struct FoldSmem { uint8_t tile[ANA_TILE+32]; int starts[34]; uint8_t tailb[8]; };
+__device__ __noinline__ u64 ens_fold_records(const Sim &S, SimState *st, const EnsFold &F, u64 rec_len, FoldSmem &Fs, int lane){
+	const u64 base = st->rec_base;
+	if (lane == 0) st->rec_len = rec_len;                             // what the analysis reads
+	__syncwarp();
+	__threadfence_block();
+	if (F.ana) ana_process(*F.ana, Fs.tile, Fs.starts, lane, 0);
+	const u64 nw = rec_len >> 3;                                      // whole words (rec_base stays a multiple of 8)
+	u64 a = 0;
+	const u64 *w = (const u64 *)S.rec;
+	for (u64 j = lane; j < nw; j += 32) a += ns_mix64(w[j]+0x9e3779b97f4a7c15ULL*((base >> 3)+j+1));
+	for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(FULLMASK, a, d);
+	const u64 tail = rec_len & 7;
+	if ((u64)lane < tail) Fs.tailb[lane] = S.rec[(nw << 3)+lane];
+	__syncwarp();
+	if ((u64)lane < tail) S.rec[lane] = Fs.tailb[lane];
+	if (lane == 0) { F.acc->hash += a; st->rec_base = base+(nw << 3); st->rec_len = tail; }
+	__syncwarp();
+	return tail;
+}
+
 // put the unprocessed tail of a batch back under the tile minima (max_events / sim_end mid-batch)
 __device__ __noinline__ void seq_restore(Ctx &c, double m, int i, int nr, int j, int nl, const SeqScratch &sc){
 	const Sim &S = *c.S;
@@ -460,7 +483,7 @@ __device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &
 
 #define NS_SPARSE_MAX_HIT_TILES 4
 #define NS_ENS_MAX_HIT_TILES 64
-__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem *W, int ens_phase = 0){
+__device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem *W, int ens_phase = 0, const EnsFold *fold = nullptr, FoldSmem *Fs = nullptr){
 	Ctx c;
 	ctx_load(c, Sp, lane);
 	if (ens_phase && !c.st->sparse_mode) return;                         // ensemble, sparse phase: this replica is with the CTA engine (or done)
@@ -508,6 +531,10 @@ __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem 
 		for (int d = 16; d; d >>= 1) n_ops += __shfl_xor_sync(FULLMASK, n_ops, d);
 		if (rec_room_short(c, nr+nl, n_ops)) {                        // soft stop BEFORE the batch: nothing is lost
 			seq_restore(c, m, 0, nr, 0, nl, sc);
+			if (fold && c.rec_len > 64) {                                 // an ensemble replica folds its records itself and goes on
+				c.rec_len = ens_fold_records(*c.S, c.st, *fold, c.rec_len, *Fs, lane);
+				continue;
+			}
 			L0 c.st->host_stop = 2;
 			__syncwarp();
 			break;

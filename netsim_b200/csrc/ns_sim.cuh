@@ -28,6 +28,7 @@
 #define NS_FEAT_CHAIN2 1u   /* small-node event chains: scalar recurrence pass + lane-parallel emission pass */
 #define NS_FEAT_HUBCTA 2u   /* full spreads of large SND groups by a whole CTA from shared memory */
 #define NS_FEAT_WIDE 4u     // single-warp engine: runs of SPEED_CHANGE events handled one event per lane (ns_seq.cuh)
+#define NS_FEAT_INIT_REC 8u // the R_NODE_CREATE records of the script's nodes are written by ns_dev_create (off: the caller writes them itself, in its own order)
 #define NS_FEAT_ALL 0xffffu
 
 enum { SND = 0, RCV = 1 };
@@ -104,6 +105,13 @@ struct Sim {
 	// outputs
 	uint8_t *rec; ns_trace_row32 *tr;
 };
+
+// Replica ensembles: a replica whose bounded record buffer fills up folds it on the spot — the analyzer reductions take
+// what they need (ns_ana_dev.cuh), a word-aligned prefix goes into the running stream hash at its stream position, the
+// odd tail bytes move to the front — and goes on (ns_ens_*; no records ever leave the device).
+struct EnsAcc { u64 hash; };
+struct AnaStream;
+struct EnsFold { EnsAcc *acc; AnaStream *ana; };   // ana may be null (no analysis requested)
 
 // Staging area of the grid-parallel path: an event handled out of order cannot know its final
 // sequence numbers / record offset, so its event_adds, records and trace row are parked here under

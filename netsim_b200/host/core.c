@@ -93,6 +93,8 @@ struct node *sim_create_node(struct sim_state *s){
 	n->index = c->n_nodes;
 	GROW(c->nodes, c->n_nodes, c->cap_nodes);
 	c->nodes[c->n_nodes++] = n;
+	uint8_t padding = 0;
+	write_record(0, R_NODE_CREATE, n->node_id, 1, &padding, s);        /* sim.c:122-123 */
 	return n;
 }
 
@@ -170,6 +172,7 @@ static int materialize(struct ns_host_core *c){
 	 * sized by the environment (defaults fit a p2p.c run of a few thousand clients) */
 	const char *ev;
 	o.device = c->device; o.mode = NS_MODE_SEQ; o.want_records = c->want_records;
+	o.features_off = 8;                                     /* NS_FEAT_INIT_REC: sim_create_node wrote the R_NODE_CREATE records itself, interleaved with the module's own */
 	o.cap_flows = (ev = getenv("NS_CAP_FLOWS")) ? atoi(ev) : 1 << 17;      /* concurrent flows */
 	o.cap_ord = (ev = getenv("NS_CAP_ORD")) ? atoi(ev) : 1 << 21;          /* flows ever created */
 	o.cap_ranges = 2*o.cap_flows+c->n_rsrc+c->n_copies+16;
@@ -257,6 +260,7 @@ struct flow *sim_establish_flow(id_t rid, size_t start, struct node *src, struct
 	GROW(c->flows, c->n_flows, c->cap_flows);
 	c->flows[c->n_flows++] = f;
 	f->peer[0] = src; f->peer[1] = dst; f->dst_id = dst->node_id;
+	f->out_next = src->outs; src->outs = f;
 	f->bwupbound = op.x; f->delay = op.y; f->resource_id = rid;
 	f->start = start; f->begin_time = s->now;
 	f->drng = talloc(1, struct range);
@@ -277,10 +281,13 @@ void flow_close(struct flow *f, struct sim_state *s){
 	f->closed = true;
 }
 
-bool is_connected(struct node *src, struct node *dst){    /* flow.h:29-35 */
-	struct ns_host_core *c = the_core;
-	for (int i = 0; i < c->n_flows; i++)
-		if (c->flows[i] && !c->flows[i]->closed && c->flows[i]->peer[0] == src && c->flows[i]->peer[1] == dst) return true;
+bool is_connected(struct node *src, struct node *dst){    /* flow.h:29-35: src->outs, keyed by the destination */
+	struct flow **pp = &src->outs;
+	while (*pp) {
+		if ((*pp)->closed) { *pp = (*pp)->out_next; continue; }       /* unlink what has been closed since */
+		if ((*pp)->peer[1] == dst) return true;
+		pp = &(*pp)->out_next;
+	}
 	return false;
 }
 
@@ -297,25 +304,62 @@ void event_add(struct event *e, struct sim_state *s){
 	if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time, e: %lf now: %lf\n", e->time, s->now); abort(); }
 	if (rc == NS_E_NAN_TIME) { log_err("Add event at nan\n"); abort(); }
 	e->active = true;
+	e->dev_slot = op.b;
 }
+/* event_remove, event.h:13-18, of a module-owned event */
 void event_remove(struct event *e){
+	struct ns_host_core *c = the_core;
 	if (!e || !e->active) return;
-	log_err("event_remove of a module-owned event is not forwarded to the device core\n");
+	e->active = false;
+	if (!c || !c->dev || e->dev_slot < 0) return;
+	struct ns_sc_op op;
+	memset(&op, 0, sizeof op);
+	op.kind = NS_OP_CANCEL; op.a = e->dev_slot;
+	ns_dev_exec(c->dev, &op, 1);
+	e->dev_slot = -1;
 }
 
 void sim_send_packet(void *data, int len, struct node *src, struct node *dst, struct sim_state *s){
 	(void)data; (void)len; (void)src; (void)dst; (void)s;   /* dead in the reference too: no PACKET_DONE handler */
 }
-void sim_node_change_state(struct node *n, enum node_state state, struct sim_state *s){
-	(void)s;
-	n->state = state;                                       /* R_NODE_STATE records are module-side, not on the hot path */
+void sim_node_change_state(struct node *n, enum node_state state, struct sim_state *s){   /* sim.h:25-28 */
+	n->state = state;
+	uint8_t v = (uint8_t)state;
+	write_record(0, R_NODE_STATE, n->node_id, 1, &v, s);
 }
 
 void user_speed_change(struct event *e, struct sim_state *s){ (void)e; (void)s; }   /* user.c:7-13 */
 void user_done(struct event *e, struct sim_state *s){ (void)e; (void)s; }
 
+static void rec_reserve(struct ns_host_core *c, size_t more);
+static void pull_records(struct ns_host_core *c);
+/* write_record, record.c:27-117, for records the MODULE side writes (sim_create_node, sim_node_change_state, a module's own):
+ * what the device has produced so far is pulled first, so the merged stream keeps the reference's order */
 void write_record(uint8_t major, uint8_t minor, uint32_t id, int8_t bytes, void *value, struct sim_state *s){
-	(void)major; (void)minor; (void)id; (void)bytes; (void)value; (void)s;              /* core records come from the device */
+	struct ns_host_core *c = core_of(s);
+	if (!c->record_path) return;                            /* record.c:29-32: no file, no record */
+	pull_records(c);
+	rec_reserve(c, 19);
+	uint8_t *b = c->rec+c->rec_len; int n = 0;
+	b[n++] = major; b[n++] = minor;
+	b[n++] = id >> 24; b[n++] = id >> 16; b[n++] = id >> 8; b[n++] = id;
+	uint32_t t = (uint32_t)(int)s->now;                      /* record.c:66-71 */
+	b[n++] = t >> 24; b[n++] = t >> 16; b[n++] = t >> 8; b[n++] = t;
+	uint16_t ut = (uint16_t)(int)((s->now-(double)((int)s->now))*1000);
+	b[n++] = ut >> 8; b[n++] = ut;
+	b[n++] = (uint8_t)bytes;
+	if (bytes == 1) b[n++] = *(uint8_t *)value;
+	else if (bytes == 2) { uint16_t v = *(uint16_t *)value; b[n++] = v >> 8; b[n++] = v; }
+	else if (bytes == 4) { uint32_t v = *(uint32_t *)value; b[n++] = v >> 24; b[n++] = v >> 16; b[n++] = v >> 8; b[n++] = v; }
+	else {                                                  /* -1: a double as integer part + milli part, record.c:98-106 */
+		double tmp = *(double *)value;
+		uint32_t ip = (uint32_t)(int)tmp;
+		b[n++] = ip >> 24; b[n++] = ip >> 16; b[n++] = ip >> 8; b[n++] = ip;
+		tmp = tmp-(double)((int)tmp);
+		uint16_t fp = (uint16_t)(int)(tmp*1000);
+		b[n++] = fp >> 8; b[n++] = fp;
+	}
+	c->rec_len += (size_t)n;
 }
 /* open_record, record.c:119-153: remember the file; the device's record stream is saved there */
 void open_record(const char *filename, int create, struct sim_state *s){

@@ -55,6 +55,7 @@ struct flow {
 	struct range *drng, *srng;
 	int ord;                      /* creation ordinal == device handle */
 	bool closed;
+	struct flow *out_next;        /* the sender's outgoing flows (node->outs there): is_connected */
 };
 
 enum node_state { N_OFFLINE = 0, N_STALE, N_PLAYING, N_DONE, N_IDLE, N_SERVER, N_CLOUD, N_DYING };
@@ -68,6 +69,7 @@ struct node {
 	id_t node_id;
 	enum node_state state;
 	int index;                    /* device handle */
+	struct flow *outs;            /* outgoing flows, newest first */
 };
 
 enum event_type { FLOW_DRAIN, FLOW_DONE, FLOW_SPEED_THROTTLE, PACKET_DONE, SPEED_CHANGE, USER, LAST_EVENT };
@@ -83,6 +85,7 @@ struct event {
 	void *data;
 	bool auto_free;
 	int token;                    /* host-owned USER events: handle on the device */
+	int dev_slot;                 /* ... and the device slot of its pending instance (event_remove) */
 };
 
 #define SND 0
@@ -102,7 +105,7 @@ struct sim_state {
 static inline struct event *event_new(double time, enum event_type t, void *d){
 	struct event *e = talloc(1, struct event);
 	e->time = time; e->type = t; e->data = d;
-	e->token = -1;
+	e->token = -1; e->dev_slot = -1;
 	return e;
 }
 static inline void event_free(struct event *e){ free(e); }

@@ -65,6 +65,20 @@ def stderr_goldens():
             open(os.path.join(OUT, t + ".stderr.txt"), "wb").write(p.stderr)
 
 
+def modx_golden():
+    """tests/modules/modx.c compiled against the REFERENCE's headers and run by the reference core: its stderr and record file"""
+    import subprocess
+    import tempfile
+    src = os.path.join(ROOT, "tests", "modules", "modx.c")
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.run(["gcc", "-O2", "-g", "-DNDEBUG", "-ffp-contract=off", "-w", "-fPIC", "-shared", "-I/root/reference", src,
+                        "-o", os.path.join(d, "modx.so")], check=True)
+        p = subprocess.run([os.path.join(refrun.REF, "netsim"), os.path.join(d, "modx")], cwd=d, capture_output=True)
+        assert p.returncode == 0
+        open(os.path.join(OUT, "modx.stderr.txt"), "wb").write(p.stderr)
+        open(os.path.join(OUT, "modx.rec"), "wb").write(refrun.record_payload(os.path.join(d, "RX")))
+
+
 def pick_goldens():
     """Candidate tables through the reference's own qselect_eval (client_behaviour.h:63-65 over qselect.h:5-27)
     and fetch metrics (p2p_common.h:171-198), via oracle/ref_pick.c -> oracle/_ref/libref_pick.so."""
@@ -110,4 +124,5 @@ if __name__ == "__main__":
         sys.exit(0)
     main()
     stderr_goldens()
+    modx_golden()
     pick_goldens()
