@@ -113,7 +113,7 @@ __global__ void k_pick_metric(const Sim *sp, int metric, int n_req, const int32_
 	}
 }
 int ns_pick_launch(int mode, int n_req, const int32_t *d_off, const int32_t *d_val, const int32_t *d_node, const int32_t *d_k,
-		   int32_t *d_ov, int32_t *d_on, int32_t *d_oc, cudaStream_t stream);
+		   int32_t *d_ov, int32_t *d_on, int32_t *d_oc, cudaStream_t stream, int max_c);
 
 // ---------------------------------------------------------------- host-side simulation object
 struct HostSim {
@@ -638,7 +638,9 @@ extern "C" int ns_dev_pick_live(ns_dev *d, int mode, int metric, int n_req, cons
 	CK(cudaEventRecord(d->e0, d->stream));
 	k_pick_metric<<<std::min(n_req, 1184), 128, 0, d->stream>>>(d->d_sim, metric, n_req, d_off, d_node, d_tz, d_ctz, d_us, d_val);
 	CK(cudaGetLastError());
-	int rc = ns_pick_launch(mode, n_req, d_off, d_val, d_node, d_k, d_ov, d_on, d_oc, d->stream);
+	int max_c = 0;
+	for (int q = 0; q < n_req; q++) max_c = std::max(max_c, off[q+1]-off[q]);
+	int rc = ns_pick_launch(mode, n_req, d_off, d_val, d_node, d_k, d_ov, d_on, d_oc, d->stream, max_c);
 	d->launches += 2;
 	CK(cudaEventRecord(d->e1, d->stream));
 	if (rc) return rc;

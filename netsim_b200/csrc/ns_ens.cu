@@ -7,6 +7,7 @@
 // of single-event timestamps) leaves the CTA engine: one SM holds one such CTA but dozens of single warps, so the
 // host loop (ns_ens_run) alternates this kernel with k_run_seq over the replicas that asked for it.
 #define NS_SCOPE_CTA
+#define NS_PREFETCH      // one CTA per simulation: request an event's lines up front (ns_model.cuh)
 #define PAR_MIN_BATCH 33           // up to one warp's worth of events: the one-event-per-lane path; above: the whole CTA
 #include "ns_par_dev.cuh"
 

@@ -916,9 +916,36 @@ __device__ __forceinline__ bool sc_needs_full_spread(const Sim &S, int f, int ty
 	return true;
 }
 
+#ifdef NS_PREFETCH
+// One simulation stepped by one warp / one CTA pays the latency of every dependent table walk of an event in full
+// (there is nothing else to switch to), and the structure-of-arrays layout puts every field of a flow, node or
+// range into a different line.  So the lines an event will touch are requested up front, in the three waves
+// their addresses become known: the flow's columns; its node's and its two ranges' columns; the source range's
+// producer and the next range.  Prefetches only: no value is used from here.  (Engines that keep thousands of
+// events in flight — the grid kernel — do not need this and are compiled without it.)
+__device__ __forceinline__ void pf(const void *p){ asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_event(const Sim &S, int f, int dir){
+	pf(&S.f_speed[0][f]); pf(&S.f_speed[1][f]); pf(&S.f_ub[f]); pf(&S.f_delay[f]); pf(&S.f_id[f]); pf(&S.f_ord[f]);
+	pf(&S.l_time[2*f]);
+	const int n = S.f_peer[dir][f], sr = S.f_srng[f], dr = S.f_drng[f];
+	pf(&S.n_total[dir][n]); pf(&S.n_max[dir][n]); pf(&S.n_usage[dir][n]); pf(&S.n_id[n]);
+	if (dir == RCV && sr >= 0 && dr >= 0) {
+		pf(&S.r_last[sr]); pf(&S.r_len[sr]); pf(&S.r_lenc[sr]); pf(&S.r_start[sr]);
+		pf(&S.r_last[dr]); pf(&S.r_len[dr]); pf(&S.r_lenc[dr]); pf(&S.r_start[dr]); pf(&S.r_total[dr]); pf(&S.r_cons[dr]);
+		if (S.has_clients) { pf(&S.c_cfg[n]); pf(&S.n_state[n]); pf(&S.c_buffer_pos[n]); pf(&S.c_bit_rate[n]); pf(&S.c_last[n]); pf(&S.r_res[dr]); }
+		const int prod = S.r_prod[sr], nx = S.r_next[dr];
+		if (prod >= 0) { pf(&S.f_speed[1][prod]); pf(&S.l_time[2*prod]); }
+		if (nx >= 0) pf(&S.r_start[nx]);
+	}
+}
+#endif
+
 // handle_speed_change (flow.c:341-384) + speed_change_free (flow.c:386-389)
 __device__ void handle_speed_change(Ctx &c, int f, int type, double speed){
 	const Sim &S = *c.S;
+#ifdef NS_PREFETCH
+	if (c.scalar || c.lane == 0) prefetch_event(S, f, type);
+#endif
 	if (type == RCV) flow_range_update(c, f);                         // :355-357
 	double delta = speed-S.f_speed[type][f];                          // :359
 	bwspread(c, f, delta, type, 0);                                   // :361

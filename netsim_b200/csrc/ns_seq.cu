@@ -1,6 +1,7 @@
 // ns_seq.cu — kernels of the single-warp engine (ns_seq.cuh) and their launchers: one warp per
 // simulation, strictly sequential event handling.  Used for replica ensembles, module inits that are
 // not pure flow creation, the host-callback mode and the sparse phases of the grid engine.
+#define NS_PREFETCH      // one warp per simulation: request an event's lines up front (ns_model.cuh)
 #include "ns_seq.cuh"
 #include "ns_par_api.cuh"
 

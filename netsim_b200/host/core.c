@@ -8,9 +8,13 @@
  * on the host between the device's DEFAULT and CLEANER work for that event (ns_dev_run_host), with the
  * mirror structs it may read refreshed first.
  *
+ * Module-side records (sim_create_node, sim_node_change_state, a module's own write_record) are merged into the
+ * device's record stream in call order; event_remove of a module-owned event cancels it on the device.
+ *
  * Limits (documented in INTEGRATION.md): nodes and resources must be created before the first flow;
- * event_remove of module-owned events and sim_send_packet are not forwarded; the behaviour library
- * (client_behaviour.c ...) needs per-event access to ranges' consumer lists and is not covered.
+ * sim_send_packet is not forwarded (dead in the reference too); the mirrors carry no list.h / uthash.h /
+ * skip-list containers, so modules that walk those (p2p.c's behaviour library) do not compile against
+ * them — their client side runs on the device through the script form (NS_SC_F_CLIENTS).
  */
 #define _GNU_SOURCE
 #include <stdarg.h>

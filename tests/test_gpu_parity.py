@@ -408,3 +408,26 @@ def test_client_behaviour_matches_live_reference(built, cfg, mname, mode):
     c = e.counters()
     assert c["events"] == r["stats"]["events"] and c["user"] == r["stats"]["user"] and c["user"] > cfg["n_clients"]
     e.close()
+
+
+def test_pick_small_tables_one_request_per_thread(built):
+    """the reference's real table sizes (c <= 64): k_pick_small, one quick-select per THREAD, against the same goldens"""
+    z = pick_golden()
+    off = z["off"]
+    keep = [q for q in range(len(off) - 1) if off[q + 1] - off[q] <= 64]
+    assert len(keep) > 300
+    sel = np.concatenate([np.arange(off[q], off[q + 1]) for q in keep]).astype(np.int64)
+    noff = np.concatenate([[0], np.cumsum([off[q + 1] - off[q] for q in keep])]).astype(np.int32)
+    ov, on, oc, ms = E.pick_batch(1, noff, z["val"][sel], z["node"][sel], z["k"][keep])
+    assert (oc == z["out_cnt"][keep]).all()
+    assert (ov == z["out_val"][sel]).all() and (on == z["out_node"][sel]).all()
+    # mode 2 (first strict minimum) on the same tables against the definition
+    ov2, on2, oc2, _ = E.pick_batch(2, noff, z["val"][sel], z["node"][sel])
+    v, nd = z["val"][sel], z["node"][sel]
+    for i, q in enumerate(keep):
+        lo, hi = noff[i], noff[i + 1]
+        if hi == lo:
+            assert oc2[i] == 0
+            continue
+        j = int(np.argmin(v[lo:hi]))
+        assert oc2[i] == 1 and on2[lo] == nd[lo + j] and ov2[lo] == v[lo + j]
