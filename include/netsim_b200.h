@@ -143,6 +143,11 @@ int  ns_dev_resource_id(ns_dev *d, int res, uint32_t *id);
 /* leader-thread nanoseconds per engine phase of the grid-parallel path:
  * {argmin, extract, sequential, group, solve, commit} — a profiling aid */
 int  ns_dev_phase_ns(ns_dev *d, uint64_t out[16]);
+/* memory-safety aid (compute-sanitizer is not available on every pool): with the environment variable NS_REDZONE=1 every
+ * device table is allocated between two 256-byte red zones; *violations = red-zone bytes that were overwritten (0 = clean,
+ * -1 = red zones not enabled) */
+int  ns_dev_check(ns_dev *d, int *violations);
+int  ns_ens_check(ns_ens *e, int *violations);
 uint64_t ns_dev_launches(ns_dev *d);
 void ns_dev_destroy(ns_dev *d);
 

@@ -128,20 +128,61 @@ struct HostSim {
 	// the real pass (arena_mode 2) carves them out of [arena, arena+arena_size)
 	int arena_mode = 0;
 	char *arena = nullptr; size_t arena_size = 0, arena_used = 0;
+	std::vector<std::pair<char *, size_t>> zones;   // NS_REDZONE=1: (allocation base, payload bytes) of every table
 };
 
+// Red zones (compute-sanitizer is closed on the GPU pool): with NS_REDZONE=1 every table gets NS_RZ bytes of a fixed pattern
+// in front of it and behind it (behind: right after its last byte, then padding); ns_dev_check / ns_ens_check compare them
+// after a run, so a store that runs off either end of a table shows up as a violation instead of as silent corruption.
+#define NS_RZ 256
+#define NS_RZ_BYTE 0xA5
+static bool redzones_on(void){ static int on = -1; if (on < 0) { const char *e = getenv("NS_REDZONE"); on = e && *e && *e != '0'; } return on != 0; }
 static int dev_alloc(HostSim &h, void **p, size_t bytes){
 	if (bytes == 0) bytes = 8;
+	const bool rz = redzones_on();
+	const size_t total = rz ? bytes+2*NS_RZ : bytes;
+	char *base = nullptr;
 	if (h.arena_mode) {
-		const size_t b = (bytes+255) & ~(size_t)255;
+		const size_t b = (total+255) & ~(size_t)255;
 		if (h.arena_mode == 1) { *p = (void *)(uintptr_t)256; h.arena_used += b; return 0; }
 		if (h.arena_used+b > h.arena_size) return NS_E_INTERNAL;
-		*p = h.arena+h.arena_used; h.arena_used += b; h.bytes += b;
-		return 0;
+		base = h.arena+h.arena_used; h.arena_used += b; h.bytes += b;
+	} else {
+		CK(cudaMalloc((void **)&base, total));
+		h.allocs.push_back(base);
+		h.bytes += total;
 	}
-	CK(cudaMalloc(p, bytes));
-	h.allocs.push_back(*p);
-	h.bytes += bytes;
+	if (rz) {
+		CK(cudaMemset(base, NS_RZ_BYTE, NS_RZ)); CK(cudaMemset(base+NS_RZ+bytes, NS_RZ_BYTE, NS_RZ));
+		h.zones.push_back({ base, bytes });
+		*p = base+NS_RZ;
+	} else *p = base;
+	return 0;
+}
+__global__ void k_check_zones(const char *const *base, const size_t *bytes, int n, int *bad){
+	for (int z = blockIdx.x; z < n; z += gridDim.x) {
+		const unsigned char *a = (const unsigned char *)base[z], *b = a+NS_RZ+bytes[z];
+		int v = 0;
+		for (int i = threadIdx.x; i < NS_RZ; i += blockDim.x) v += (a[i] != NS_RZ_BYTE)+(b[i] != NS_RZ_BYTE);
+		if (v) atomicAdd(bad, v);
+	}
+}
+// number of red-zone bytes that no longer hold the pattern (0 = clean; -1: red zones were not enabled)
+static int check_zones(const std::vector<std::pair<char *, size_t>> &zones, cudaStream_t stream, int *out){
+	if (!redzones_on()) { *out = -1; return 0; }
+	const int n = (int)zones.size();
+	*out = 0;
+	if (!n) return 0;
+	std::vector<const char *> hb(n); std::vector<size_t> hs(n);
+	for (int i = 0; i < n; i++) { hb[i] = zones[i].first; hs[i] = zones[i].second; }
+	const char **db; size_t *ds; int *dbad;
+	CK(cudaMalloc(&db, sizeof(char *)*n)); CK(cudaMalloc(&ds, sizeof(size_t)*n)); CK(cudaMalloc(&dbad, 4));
+	CK(cudaMemcpy(db, hb.data(), sizeof(char *)*n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(ds, hs.data(), sizeof(size_t)*n, cudaMemcpyHostToDevice));
+	CK(cudaMemset(dbad, 0, 4));
+	k_check_zones<<<std::min(n, 1024), 64, 0, stream>>>(db, ds, n, dbad);
+	CK(cudaMemcpyAsync(out, dbad, 4, cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	cudaFree(db); cudaFree(ds); cudaFree(dbad);
 	return 0;
 }
 // short-lived device buffers of one call
@@ -727,6 +768,11 @@ extern "C" int ns_dev_resource_id(ns_dev *d, int res, uint32_t *id){
 	return 0;
 }
 
+extern "C" int ns_dev_check(ns_dev *d, int *violations){
+	if (!d || !violations) return NS_E_ARG;
+	CK(cudaSetDevice(d->device));
+	return check_zones(d->h.zones, d->stream, violations);
+}
 extern "C" int ns_dev_phase_ns(ns_dev *d, uint64_t out[16]){
 	if (!d || !out) return NS_E_ARG;
 	SimState st; int rc = read_state(d, &st); if (rc) return rc;
@@ -1023,6 +1069,13 @@ extern "C" int ns_ens_counters_sum(ns_ens *e, uint64_t out[NS_CNT_COUNT]){
 	CK(cudaMemcpyAsync(out, d_out, sizeof(u64)*NS_CNT_COUNT, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
+}
+extern "C" int ns_ens_check(ns_ens *e, int *violations){
+	if (!e || !violations) return NS_E_ARG;
+	CK(cudaSetDevice(e->device));
+	std::vector<std::pair<char *, size_t>> all;
+	for (auto &h : e->sims) all.insert(all.end(), h.zones.begin(), h.zones.end());
+	return check_zones(all, e->stream, violations);
 }
 extern "C" uint64_t ns_ens_launches(ns_ens *e){ return e ? e->launches : 0; }
 extern "C" void ns_ens_destroy(ns_ens *e){

@@ -81,6 +81,8 @@ def lib():
         L.ns_dev_flow_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_node_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_phase_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ns_dev_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.ns_ens_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ns_dev_launches.restype = C.c_uint64
         L.ns_dev_launches.argtypes = [C.c_void_p]
         L.ns_dev_destroy.argtypes = [C.c_void_p]
@@ -220,6 +222,14 @@ class Engine:
             raise NsError(rc, "ns_dev_node_state")
         return out[:n.value]
 
+    def check(self) -> int:
+        """red-zone violations (NS_REDZONE=1): 0 = clean, -1 = not enabled"""
+        v = C.c_int()
+        rc = self.L.ns_dev_check(self.h, C.byref(v))
+        if rc:
+            raise NsError(rc, "ns_dev_check")
+        return int(v.value)
+
     def phase_ms(self) -> dict:
         a = (C.c_uint64 * 16)()
         self.L.ns_dev_phase_ns(self.h, a)
@@ -318,6 +328,13 @@ class Ensemble:
                         "t_last": float(x.t_last), "usage": np.ctypeslib.as_array(x.usage).copy(), "stale": np.ctypeslib.as_array(x.stale).copy(),
                         "stale_now": int(x.stale_now), "stale_max": int(x.stale_max)})
         return out
+
+    def check(self) -> int:
+        v = C.c_int()
+        rc = self.L.ns_ens_check(self.h, C.byref(v))
+        if rc:
+            raise NsError(rc, "ns_ens_check")
+        return int(v.value)
 
     def counters_sum(self) -> dict:
         out = (C.c_uint64 * len(COUNTERS))()
