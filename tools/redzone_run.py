@@ -41,7 +41,7 @@ one("clients", S.p2p_clients(400, 4, n_catalogue=10, play_seconds=900.0, arrival
 scs = [S.swarm(300 + 40 * i, 3, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0, res_len=30000, seed=50 + i).to_bytes() for i in range(6)]
 scs += [S.p2p_clients(150, 4, play_seconds=200.0, arrival_window=10.0, seed=70 + i).to_bytes() for i in range(6)]
 for mode in (E.MODE_AUTO, E.MODE_SEQ):
-    ens = E.Ensemble(scs, mode=mode, record_cap=1 << 17, ring_cap=1 << 18)
+    ens = E.Ensemble(scs, mode=mode, record_cap=1 << 19, ring_cap=1 << 18)   # (a replica's module init must fit: 500 peers x 3 creates)
     ens.analysis_begin(30.0)
     ens.run(0)
     dg = ens.digests(); ens.analysis()
