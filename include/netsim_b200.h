@@ -85,7 +85,7 @@ struct ns_dev_opts {
 	int cap_ord;           /* flows ever created (creation ordinals), 0 = auto (2x the script's CREATE ops, >= 2x cap_flows) */
 	int cap_ranges;        /* ranges, 0 = auto */
 	int cap_users;         /* pending USER events, 0 = auto (2x the script's SCHED ops) */
-	int reserved[1];
+	int cap_nodes;         /* nodes, 0 = the script's (a host core that creates nodes later through NS_OP_NEWNODE reserves room here) */
 };
 
 struct ns_trace_row32 { uint32_t type, ord; double time, v0, v1; };
@@ -132,6 +132,17 @@ struct ns_host_event { int32_t type, flow_ord, dir, token; double time, speed, n
 struct ns_flow_info { int32_t alive, src, dst; uint32_t flow_id, resource_id; int32_t pad; double ub, delay, speed[2]; int64_t drng_start; double drng_len; };
 struct ns_range_info { int64_t start, total_len; double len; int32_t producer_ord, pad; };
 struct ns_sc_op;
+struct ns_rand_state;
+/* the whole mutable state a module handler may read, for the host core's mirrors (netsim_b200/host/core.c): every live flow and
+ * every range, as the device has them now.  done_t / drain_t = +inf when the event is not pending (event.h:76-88 is_active). */
+struct ns_view_flow  { int32_t ord, slot, src, dst, srng, drng, drain_type, pad; uint32_t flow_id, pad2; double speed[2], done_t, drain_t; };
+struct ns_view_range { int32_t slot, res, producer_ord, next, prev, pad; int64_t start, total_len; double len, lenc, last_update; };
+/* fills at most max_flows / max_ranges entries (unordered) and reports how many there are */
+int  ns_dev_host_view(ns_dev *d, struct ns_view_flow *flows, int max_flows, int *n_flows, struct ns_view_range *ranges, int max_ranges, int *n_ranges);
+/* the simulation's random() stream (sim.c:117,132, flow.c:327, skiplist.h:34-40 share ONE generator with the module's own
+ * random() calls): get applies the pending burns and returns the state, set installs a state (after the host drew from it) */
+int  ns_dev_rng_get(ns_dev *d, struct ns_rand_state *g);
+int  ns_dev_rng_set(ns_dev *d, const struct ns_rand_state *g);
 int  ns_dev_set_host_mask(ns_dev *d, uint32_t mask);
 int  ns_dev_run_host(ns_dev *d, struct ns_host_event *ev);
 int  ns_dev_exec(ns_dev *d, struct ns_sc_op *ops, int n);

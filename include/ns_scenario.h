@@ -30,6 +30,17 @@ enum ns_op_kind {
 	                     (0 = distance_metric, 1 = share_metric, p2p_common.h:171-198): server_picker_opt1 over the
 	                     server nodes + qselect, one sim_establish_flow per kept server at strip i*strip with
 	                     distance_based_bw / distance_based_delay, then client_start_play.  Needs NS_SC_F_CLIENTS. */
+	/* ---- ns_dev_exec only: what the host core (netsim_b200/host) needs to mirror a module that is code, not data ---- */
+	NS_OP_NEWNODE    = 7,  /* sim_create_node (sim.c:113-125) with the id the host drew: a = node index (== the current node
+	                          count, < ns_dev_opts.cap_nodes), c = node id, x / y = maximum_bandwidth[0 / 1] */
+	NS_OP_NEWRES     = 8,  /* sim_node_new_resource / sim_node_add_resource (sim.c:129-154): a complete copy of resource id c,
+	                          `start` Kbit long, bit rate b, on node a; on return .b = its slot in the resource table, .c = the
+	                          slot of its range [0, len) */
+	NS_OP_CREATE_RID = 9,  /* NS_OP_CREATE with the resource given by its id (c) instead of a script index; on return .a = creation
+	                          ordinal or -1, .b = the destination's resource slot, .c = the new destination range's slot,
+	                          .start = the source range's slot */
+	NS_OP_RANGE_SET  = 10, /* a module handler advanced a range itself (_range_update, range.h:91-118, from is_resource_usable /
+	                          client_lowwm_event ...): a = range slot, x = len, y = lenc, start = the bits of last_update */
 };
 
 /* header.flags */

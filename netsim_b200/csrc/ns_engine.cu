@@ -129,6 +129,7 @@ struct HostSim {
 	int arena_mode = 0;
 	char *arena = nullptr; size_t arena_size = 0, arena_used = 0;
 	std::vector<std::pair<char *, size_t>> zones;   // NS_REDZONE=1: (allocation base, payload bytes) of every table
+	int cap_nodes = 0;                              // rows of the node tables (>= S.n_nodes: NS_OP_NEWNODE appends)
 };
 
 // Red zones (compute-sanitizer is closed on the GPU pool): with NS_REDZONE=1 every table gets NS_RZ bytes of a fixed pattern
@@ -268,8 +269,9 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 
 	Sim &S = h.S;
 	memset(&S, 0, sizeof S);
-	const int N = H.n_nodes;
-	S.n_nodes = N;
+	const int N = (H.flags & NS_SC_F_CLIENTS) ? H.n_nodes : std::max(H.n_nodes, o.cap_nodes);   // node tables: room for NS_OP_NEWNODE (host core)
+	h.cap_nodes = N;
+	S.n_nodes = H.n_nodes;
 	S.cap_flows = o.cap_flows > 0 ? o.cap_flows : std::max(16, n_create);
 	const int F = S.cap_flows;
 	// a caller that creates flows beyond the script (the host core: the module IS the script) sizes the tables
@@ -366,7 +368,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	std::vector<uint32_t> nid(N);
 	std::unordered_set<uint32_t> used;
 	used.reserve((size_t)N*2+16);
-	for (int i = 0; i < N; i++) {
+	for (int i = 0; i < H.n_nodes; i++) {
 		uint32_t id;
 		do { id = ns_rand_next_host(&g); draws++; } while (!used.insert(id).second);
 		nid[i] = id;
@@ -387,14 +389,14 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		ns_rand_next_host(&g); draws++;                               // resource_new_range -> skip_list_insert
 	};
 	for (int i = 0; i < H.n_resources; i++) {
-		if (rs[i].owner < 0 || rs[i].owner >= N) return NS_E_BAD_SCENARIO;
+		if (rs[i].owner < 0 || rs[i].owner >= H.n_nodes) return NS_E_BAD_SCENARIO;
 		uint32_t rid = ns_rand_next_host(&g); draws++;
 		while (store_find(rs[i].owner, rid) >= 0) { rid = ns_rand_next_host(&g); draws++; }
 		rids[i] = rid;
 		add_full(rs[i].owner, rid, rs[i].len, rs[i].bit_rate);
 	}
 	for (int i = 0; i < H.n_copies; i++) {
-		if (cp[i].node < 0 || cp[i].node >= N || cp[i].res < 0 || cp[i].res >= H.n_resources) return NS_E_BAD_SCENARIO;
+		if (cp[i].node < 0 || cp[i].node >= H.n_nodes || cp[i].res < 0 || cp[i].res >= H.n_resources) return NS_E_BAD_SCENARIO;
 		uint32_t rid = rids[cp[i].res];
 		if (store_find(cp[i].node, rid) >= 0) continue;
 		add_full(cp[i].node, rid, rs[cp[i].res].len, rs[cp[i].res].bit_rate);
@@ -404,8 +406,10 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 
 	// ---- fill and upload
 	for (int d = 0; d < 2; d++) { if ((rc = fill_f64(S.n_usage[d], N, 0))) return rc; if ((rc = fill_f64(S.n_total[d], N, 0))) return rc; }
-	CK(cudaMemcpy(S.n_max[0], max_up, (size_t)N*8, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(S.n_max[1], max_down, (size_t)N*8, cudaMemcpyHostToDevice));
+	if (H.n_nodes) {
+		CK(cudaMemcpy(S.n_max[0], max_up, (size_t)H.n_nodes*8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(S.n_max[1], max_down, (size_t)H.n_nodes*8, cudaMemcpyHostToDevice));
+	}
 	CK(cudaMemcpy(S.n_id, nid.data(), (size_t)N*4, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(S.n_res_head, res_head.data(), (size_t)N*4, cudaMemcpyHostToDevice));
 	if ((rc = fill_i32(S.adj_off, 2*N, 0)) || (rc = fill_i32(S.adj_cap, 2*N, 0)) || (rc = fill_i32(S.adj_len, 2*N, 0)) || (rc = fill_i32(S.adj_live, 2*N, 0))) return rc;
@@ -468,6 +472,7 @@ struct ns_dev {
 	size_t rec_total_host = 0;      // record bytes in the buffer when the last run returned
 	size_t rec_base_host = 0;       // ... and the stream offset of the buffer's first byte
 	u64 *d_hash = nullptr;
+	void *view_buf = nullptr; size_t view_cap = 0;   // ns_dev_host_view
 };
 
 extern "C" int ns_dev_count(void){
@@ -716,11 +721,16 @@ extern "C" int ns_dev_run_host(ns_dev *d, ns_host_event *ev){
 extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 	if (!d || !ops || n < 0 || n > d->h.S.host_ops_cap) return NS_E_ARG;
 	if (n == 0) return 0;
+	int new_nodes = 0;
 	for (int i = 0; i < n; i++) {                                        // the device indexes its tables with these
 		const ns_sc_op &op = ops[i];
 		if (op.kind == NS_OP_CREATE) { if (op.a < 0 || op.a >= d->h.S.n_nodes || op.b < 0 || op.b >= d->h.S.n_nodes || op.c < 0 || op.c >= d->h.S.n_rids) return NS_E_ARG; }
 		else if (op.kind == NS_OP_CLOSE) { if (op.a < 0) return NS_E_ARG; }
 		else if (op.kind == NS_OP_CANCEL) { if (op.a < 0 || op.a >= d->h.S.cap_users) return NS_E_ARG; }
+		else if (op.kind == NS_OP_NEWNODE) { if (op.a != d->h.S.n_nodes+new_nodes || op.a >= d->h.cap_nodes) return op.a >= d->h.cap_nodes ? NS_E_TABLE_FULL : NS_E_ARG; new_nodes++; }
+		else if (op.kind == NS_OP_NEWRES) { if (op.a < 0 || op.a >= d->h.S.n_nodes+new_nodes || op.start < 0) return NS_E_ARG; }
+		else if (op.kind == NS_OP_CREATE_RID) { if (op.a < 0 || op.a >= d->h.S.n_nodes+new_nodes || op.b < 0 || op.b >= d->h.S.n_nodes+new_nodes) return NS_E_ARG; }
+		else if (op.kind == NS_OP_RANGE_SET) { if (op.a < 0 || op.a >= d->h.S.cap_ranges) return NS_E_ARG; }
 		else if (op.kind != NS_OP_SCHED && op.kind != NS_OP_END) return NS_E_ARG;
 	}
 	CK(cudaSetDevice(d->device));
@@ -728,8 +738,85 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 	{ int rc = seq_launch_exec_ops(d->d_sim, n, d->stream); if (rc) return rc; }
 	d->launches++;
 	CK(cudaMemcpyAsync(ops, d->h.S.host_ops, (size_t)n*sizeof *ops, cudaMemcpyDeviceToHost, d->stream));
+	if (new_nodes) {                                                     // the node count is part of the device's Sim
+		d->h.S.n_nodes += new_nodes;
+		CK(cudaMemcpyAsync(&d->d_sim->n_nodes, &d->h.S.n_nodes, sizeof(int), cudaMemcpyHostToDevice, d->stream));
+	}
 	CK(cudaStreamSynchronize(d->stream));
 	return ns_dev_status(d);
+}
+
+// ---- the host core's view of the mutable state (every live flow, every range) and the shared random() stream ----
+__global__ void k_host_view(const Sim *sp, ns_view_flow *fl, int max_f, ns_view_range *rg, int max_r, int *cnt){
+	const Sim &S = *sp;
+	const int hf = S.st->hi_flow, hr = S.st->hi_range;
+	const int gt = blockIdx.x*blockDim.x+threadIdx.x, gn = gridDim.x*blockDim.x;
+	for (int f = gt; f < hf; f += gn) {
+		if (!S.f_alive[f]) continue;
+		const int k = atomicAdd(&cnt[0], 1);
+		if (k >= max_f) continue;
+		ns_view_flow v;
+		v.ord = S.f_ord[f]; v.slot = f; v.src = S.f_peer[0][f]; v.dst = S.f_peer[1][f]; v.srng = S.f_srng[f]; v.drng = S.f_drng[f];
+		v.drain_type = S.f_drain_type[f]; v.pad = 0; v.flow_id = S.f_id[f]; v.pad2 = 0;
+		v.speed[0] = S.f_speed[0][f]; v.speed[1] = S.f_speed[1][f]; v.done_t = S.l_time[2*f]; v.drain_t = S.l_time[2*f+1];
+		fl[k] = v;
+	}
+	for (int r = gt; r < hr; r += gn) {
+		if (S.r_res[r] < 0) continue;                                    // a free slot (range_merge_with_next)
+		const int k = atomicAdd(&cnt[1], 1);
+		if (k >= max_r) continue;
+		ns_view_range v;
+		v.slot = r; v.res = S.r_res[r]; v.producer_ord = S.r_prod[r] >= 0 ? S.f_ord[S.r_prod[r]] : -1; v.next = S.r_next[r]; v.prev = S.r_prev[r]; v.pad = 0;
+		v.start = S.r_start[r]; v.total_len = S.r_total[r]; v.len = S.r_len[r]; v.lenc = S.r_lenc[r]; v.last_update = S.r_last[r];
+		rg[k] = v;
+	}
+}
+extern "C" int ns_dev_host_view(ns_dev *d, ns_view_flow *flows, int max_flows, int *n_flows, ns_view_range *ranges, int max_ranges, int *n_ranges){
+	if (!d || !flows || !ranges || !n_flows || !n_ranges || max_flows < 0 || max_ranges < 0) return NS_E_ARG;
+	CK(cudaSetDevice(d->device));
+	// called once per event in host-callback mode: the device buffers stay with the handle
+	const size_t need = 16+sizeof(ns_view_flow)*(size_t)std::max(1, max_flows)+sizeof(ns_view_range)*(size_t)std::max(1, max_ranges);
+	if (need > d->view_cap) {
+		if (d->view_buf) cudaFree(d->view_buf);
+		d->view_buf = nullptr; d->view_cap = 0;
+		CK(cudaMalloc(&d->view_buf, need));
+		d->view_cap = need;
+	}
+	int *dc = (int *)d->view_buf;
+	ns_view_flow *df = (ns_view_flow *)((char *)d->view_buf+16);
+	ns_view_range *dr = (ns_view_range *)((char *)df+sizeof(ns_view_flow)*(size_t)std::max(1, max_flows));
+	CK(cudaMemsetAsync(dc, 0, 8, d->stream));
+	k_host_view<<<64, 256, 0, d->stream>>>(d->d_sim, df, max_flows, dr, max_ranges, dc); d->launches++;
+	int hc[2];
+	CK(cudaMemcpyAsync(hc, dc, 8, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	*n_flows = hc[0]; *n_ranges = hc[1];
+	const int cf = std::min(hc[0], max_flows), cr = std::min(hc[1], max_ranges);
+	if (cf) CK(cudaMemcpyAsync(flows, df, sizeof(ns_view_flow)*(size_t)cf, cudaMemcpyDeviceToHost, d->stream));
+	if (cr) CK(cudaMemcpyAsync(ranges, dr, sizeof(ns_view_range)*(size_t)cr, cudaMemcpyDeviceToHost, d->stream));
+	CK(cudaStreamSynchronize(d->stream));
+	return 0;
+}
+extern "C" int ns_dev_rng_get(ns_dev *d, ns_rand_state *g){
+	if (!d || !g) return NS_E_ARG;
+	SimState st; int rc = read_state(d, &st); if (rc) return rc;
+	if (st.burns) {                                                      // burned draws are applied lazily (ns_rand_jump)
+		ns_rand_jump(st.rnd, st.rf, st.rr, st.burns);
+		st.cnt[NS_CNT_DRAWS] += st.burns; st.burns = 0;
+		CK(cudaMemcpy(&d->h.S.st->burns, &st.burns, sizeof st.burns, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(&d->h.S.st->rnd, st.rnd, sizeof st.rnd+2*sizeof(int32_t), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(&d->h.S.st->cnt[NS_CNT_DRAWS], &st.cnt[NS_CNT_DRAWS], 8, cudaMemcpyHostToDevice));
+	}
+	memcpy(g->st, st.rnd, sizeof st.rnd); g->f = st.rf; g->r = st.rr;
+	return 0;
+}
+extern "C" int ns_dev_rng_set(ns_dev *d, const ns_rand_state *g){
+	if (!d || !g) return NS_E_ARG;
+	CK(cudaSetDevice(d->device));
+	int32_t w[33];
+	memcpy(w, g->st, sizeof g->st); w[31] = g->f; w[32] = g->r;
+	CK(cudaMemcpy(&d->h.S.st->rnd, w, sizeof w, cudaMemcpyHostToDevice));   // rnd[31], rf, rr are laid out together (ns_sim.cuh)
+	return 0;
 }
 extern "C" int ns_dev_flow_info(ns_dev *d, int ord, ns_flow_info *out){
 	if (!d || !out) return NS_E_ARG;
@@ -784,6 +871,7 @@ extern "C" void ns_dev_destroy(ns_dev *d){
 	if (!d) return;
 	cudaSetDevice(d->device);
 	free_sim(d->h);
+	if (d->view_buf) cudaFree(d->view_buf);
 	if (d->d_sim) cudaFree(d->d_sim);
 	if (d->d_scr) cudaFree(d->d_scr);
 	if (d->d_hash) cudaFree(d->d_hash);

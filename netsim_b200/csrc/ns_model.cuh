@@ -642,6 +642,7 @@ __device__ __noinline__ void range_merge_with_next(Ctx &c, int r){
 		S.r_next[r] = nn;
 		if (nn >= 0) S.r_prev[nn] = r;
 		S.r_next_free[nr] = c.st->free_range; c.st->free_range = nr;
+		S.r_res[nr] = -1;                                             // (a free slot: the host view skips it)
 		range_update_1(S, r, c.now);                                  // :113
 	}
 	WSYNC();
@@ -1147,8 +1148,9 @@ __device__ __noinline__ void run_group(Ctx &c, int g){
 		if (c.st->status) return;
 		ns_sc_op op = S.ops[i];
 		switch (op.kind) {
-		case NS_OP_CREATE: {
-			int f = sim_establish_flow(c, S.rids[op.c], op.start, op.a, op.b, op.x, op.y);
+		case NS_OP_CREATE:
+		case NS_OP_CREATE_RID: {
+			int f = sim_establish_flow(c, op.kind == NS_OP_CREATE ? S.rids[op.c] : (uint32_t)op.c, op.start, op.a, op.b, op.x, op.y);
 			if (note_created_flow(c, f) < 0) return;
 			break; }
 #ifndef NS_NO_CLIENTS
@@ -1193,8 +1195,9 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 		if (c.st->status) return;
 		ns_sc_op op = S.host_ops[i];
 		switch (op.kind) {
-		case NS_OP_CREATE: {
-			int f = sim_establish_flow(c, S.rids[op.c], op.start, op.a, op.b, op.x, op.y);
+		case NS_OP_CREATE:
+		case NS_OP_CREATE_RID: {
+			int f = sim_establish_flow(c, op.kind == NS_OP_CREATE ? S.rids[op.c] : (uint32_t)op.c, op.start, op.a, op.b, op.x, op.y);
 			int ord = c.st->n_ord;
 			if (ord >= S.cap_ord) { set_status(c, NS_E_TABLE_FULL); return; }
 			WSYNC();
@@ -1202,6 +1205,10 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 				S.ord2flow[ord] = f;
 				c.st->n_ord = ord+1;
 				S.host_ops[i].a = f >= 0 ? ord : -1;                  // result: creation ordinal or -1
+				if (f >= 0 && op.kind == NS_OP_CREATE_RID) {          // ... and where the host core finds the flow's ranges
+					const int dg = S.f_drng[f];
+					S.host_ops[i].b = dg >= 0 ? S.r_res[dg] : -1; S.host_ops[i].c = dg; S.host_ops[i].start = S.f_srng[f];
+				}
 				if (f >= 0) {
 					S.f_ord[f] = ord;
 					c.st->cnt[NS_CNT_CREATES] += 1;
@@ -1243,6 +1250,35 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 			L0 c.st->exit_flag = 1;
 			WSYNC();
 			break;
+		case NS_OP_NEWNODE: {                                          // sim_create_node, sim.c:113-125 (id drawn and recorded by the host core)
+			const int n = op.a;
+			L0 {
+				S.n_max[0][n] = op.x; S.n_max[1][n] = op.y; S.n_usage[0][n] = 0; S.n_usage[1][n] = 0; S.n_total[0][n] = 0; S.n_total[1][n] = 0;
+				S.n_id[n] = (uint32_t)op.c; S.n_res_head[n] = -1;
+				S.adj_off[2*n] = 0; S.adj_cap[2*n] = 0; S.adj_len[2*n] = 0; S.adj_live[2*n] = 0;
+				S.adj_off[2*n+1] = 0; S.adj_cap[2*n+1] = 0; S.adj_len[2*n+1] = 0; S.adj_live[2*n+1] = 0;
+			}
+			WSYNC();
+			break; }
+		case NS_OP_NEWRES: {                                           // sim_node_new_resource / sim_node_add_resource, sim.c:129-154
+			int r = store_get(S, op.a, (uint32_t)op.c);
+			int g = -1;
+			if (r < 0) {
+				r = resource_new(c, op.a, (uint32_t)op.c, op.start);
+				if (r >= 0) {
+					L0 S.s_brate[r] = op.b;
+					WSYNC();
+					g = resource_new_range(c, r, 0, (double)op.start, 0.0);   // range_new: calloc'ed, last_update = 0 (data.h:202-209)
+					c.burns -= 1;                                     // the host core took the skip-list draw itself, in call order
+				}
+			} else r = -1;                                             // sim.c:144-146: already there
+			L0 { S.host_ops[i].b = r; S.host_ops[i].c = g; }
+			WSYNC();
+			break; }
+		case NS_OP_RANGE_SET: {
+			L0 { S.r_len[op.a] = op.x; S.r_lenc[op.a] = op.y; S.r_last[op.a] = __longlong_as_double(op.start); }
+			WSYNC();
+			break; }
 		}
 	}
 }

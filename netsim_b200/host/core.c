@@ -2,19 +2,27 @@
  *
  * This is the host side of the drop-in boundary: the reference's sim.c / user.c / record.c / main.c
  * API (sim.h:14-53, record.h:19-22, event.h:13-74, flow.h:13-41) with the same names, argument meaning
- * and error behaviour, so that UNMODIFIED module sources (modules/test00.c ... test05.c) compile
- * against netsim_b200/host/include and run with every rate solve, byte-progress update, completion
- * re-time and event pop on the GPU.  A module handler registered with sim_register_handler is called
- * on the host between the device's DEFAULT and CLEANER work for that event (ns_dev_run_host), with the
- * mirror structs it may read refreshed first.
+ * and error behaviour, so that UNMODIFIED module sources (modules/test00.c ... test05.c, test_client1-3.c with
+ * client_behaviour.c / resource.c / gaussian.c, p2p.c with cloud_behaviour.c) compile against
+ * netsim_b200/host/include and run with every rate solve, byte-progress update, completion re-time and event pop
+ * on the GPU.  A module handler registered with sim_register_handler is called on the host between the device's
+ * DEFAULT and CLEANER work for that event (ns_dev_run_host).
+ *
+ * What modules read directly are MIRRORS (host/include/data.h): the same structs, lists, hashes and per-resource range
+ * skip lists as the reference's, whose structure this file keeps (a flow is linked when it is established, unlinked when
+ * it closes, a merged range leaves its list) and whose numbers — speeds, usage, range progress, completion times — are
+ * refreshed from the device (ns_dev_host_view) before every handler and after every call that changes them.  Three
+ * things flow the other way: the module's API calls (ns_dev_exec operations), a range a handler advanced itself
+ * (_range_update from is_resource_usable / client_lowwm_event ...: NS_OP_RANGE_SET, the same fp64 state the device would
+ * have produced), and random(): the module and the core share ONE glibc random() stream (node / resource / flow ids, one
+ * draw per skip-list insert, the module's own gaussian draws), so random() / srandom() are defined here and draw from
+ * the simulation's generator — on the host until the device tables exist, from the device's state afterwards.
  *
  * Module-side records (sim_create_node, sim_node_change_state, a module's own write_record) are merged into the
  * device's record stream in call order; event_remove of a module-owned event cancels it on the device.
  *
- * Limits (documented in INTEGRATION.md): nodes and resources must be created before the first flow;
- * sim_send_packet is not forwarded (dead in the reference too); the mirrors carry no list.h / uthash.h /
- * skip-list containers, so modules that walk those (p2p.c's behaviour library) do not compile against
- * them — their client side runs on the device through the script form (NS_SC_F_CLIENTS).
+ * Limits (documented in INTEGRATION.md): sim_send_packet is not forwarded (dead in the reference too);
+ * node_del_resource (p2p.c only when more than max_rsrc resources have been created) is not supported.
  */
 #define _GNU_SOURCE
 #include <stdarg.h>
@@ -40,26 +48,26 @@
 
 const double eps = 1e-4;            /* sim.c:11 */
 
-struct handler { event_handler_func f; int pri; struct handler *next; };
-
 struct ns_host_core {
 	ns_dev *dev;
-	struct ns_rand_state rng;
-	struct node **nodes; int n_nodes, cap_nodes;
-	struct resource **rsrc; int n_rsrc, cap_rsrc;          /* catalogue (sim_node_new_resource order) */
-	struct { int node, res; } *copies; int n_copies, cap_copies;
+	struct ns_rand_state rng;                              /* the random() stream until the device tables exist */
+	struct node **nodes; int n_nodes, cap_nodes, nodes_pushed;
+	struct resource **rsrc; int n_rsrc, cap_rsrc, rsrc_pushed;   /* every resource copy, in creation order */
 	struct flow **flows; int n_flows, cap_flows;           /* by creation ordinal */
+	struct range **rng_by_slot; int cap_rng;               /* device range slot -> mirror */
+	struct resource **res_by_slot; int cap_res;            /* device resource slot -> mirror */
 	struct event **uev; int n_uev, cap_uev;                /* module-owned USER events by token */
-	struct handler *handlers[LAST_EVENT];
 	char *record_path; int want_records;
 	uint8_t *rec; size_t rec_len, rec_cap;                 /* record stream pulled from the device so far (+ module records) */
 	size_t dev_off;                                        /* device stream offset already pulled */
+	struct ns_view_flow *vf; struct ns_view_range *vr; int vf_cap, vr_cap;
+	unsigned epoch;
 	struct sim_state *s;
-	int device, mode;
+	int device;
 };
 
 static struct ns_host_core *core_of(struct sim_state *s){ return s->core; }
-static struct ns_host_core *the_core;     /* sim_node_new_resource() has no sim_state argument */
+static struct ns_host_core *the_core;     /* sim_node_new_resource(), event_remove() and random() have no sim_state argument */
 
 void ns_host_log(int level, const char *domain, const char *fmt, ...){
 	if (level > global_log_level) return;
@@ -69,31 +77,229 @@ void ns_host_log(int level, const char *domain, const char *fmt, ...){
 	vfprintf(stderr, fmt, ap);
 	va_end(ap);
 }
+static void die(int rc, const char *what){ log_err("device core: %s: %s\n", what, ns_strerror(rc)); exit(3); }
 
-#define GROW(arr, n, cap) do { if ((n) == (cap)) { (cap) = (cap) ? (cap)*2 : 16; (arr) = realloc((arr), (size_t)(cap)*sizeof *(arr)); } } while (0)
+#define GROW(arr, n, cap) do { if ((n) >= (cap)) { int c_ = (cap) ? (cap) : 16; while (c_ <= (n)) c_ *= 2; \
+	(arr) = realloc((arr), (size_t)c_*sizeof *(arr)); memset((arr)+(cap), 0, (size_t)(c_-(cap))*sizeof *(arr)); (cap) = c_; } } while (0)
+
+/* ---------------------------------------------------------------- the shared random() stream */
+static uint32_t core_random(struct ns_host_core *c){
+	if (!c->dev) return ns_rand_next_host(&c->rng);
+	struct ns_rand_state g;
+	int rc = ns_dev_rng_get(c->dev, &g);
+	if (rc) die(rc, "random");
+	uint32_t v = ns_rand_next_host(&g);
+	if ((rc = ns_dev_rng_set(c->dev, &g))) die(rc, "random");
+	return v;
+}
+/* modules (and the containers of host/include: one draw per skip_list_insert) call these by name: they resolve to the
+ * executable's definitions, i.e. to the simulation's generator, before libc's */
+long random(void){
+	if (!the_core) { static struct ns_rand_state g; static int seeded; if (!seeded) { ns_rand_seed_host(&g, 1); seeded = 1; } return (long)ns_rand_next_host(&g); }
+	return (long)core_random(the_core);
+}
+void srandom(unsigned seed){
+	if (!the_core) return;
+	if (the_core->dev) { struct ns_rand_state g; ns_rand_seed_host(&g, seed); ns_dev_rng_set(the_core->dev, &g); }
+	else ns_rand_seed_host(&the_core->rng, seed);
+}
 
 struct sim_state *ns_host_state_new(int device){
 	struct sim_state *s = talloc(1, struct sim_state);
 	struct ns_host_core *c = talloc(1, struct ns_host_core);
 	s->core = c; c->s = s; c->device = device;
+	for (int i = 0; i < LAST_EVENT; i++) INIT_LIST_HEAD(&s->handlers[i]);
 	ns_rand_seed_host(&c->rng, 1);            /* glibc default state == srandom(1) */
 	the_core = c;
 	return s;
 }
 
+/* ---------------------------------------------------------------- device calls */
+static void dev_exec(struct ns_host_core *c, struct ns_sc_op *ops, int n, const char *what){
+	int rc = ns_dev_exec(c->dev, ops, n);
+	if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time\n"); abort(); }
+	if (rc == NS_E_NAN_TIME) { log_err("Add event at nan\n"); abort(); }
+	if (rc) die(rc, what);
+}
+/* nodes and resources the module has created since the last call, in creation order.  Pushed lazily: a module sets
+ * maximum_bandwidth / bit_rate on the struct AFTER sim_create_node / sim_node_new_resource returned (p2p.c:144-170). */
+static void flush_pending(struct ns_host_core *c){
+	if (!c->dev) return;
+	struct ns_sc_op ops[64]; int n = 0;
+	while (c->nodes_pushed < c->n_nodes) {
+		struct node *nd = c->nodes[c->nodes_pushed++];
+		struct ns_sc_op *op = &ops[n++];
+		memset(op, 0, sizeof *op);
+		op->kind = NS_OP_NEWNODE; op->a = nd->index; op->c = (int32_t)nd->node_id; op->x = nd->maximum_bandwidth[0]; op->y = nd->maximum_bandwidth[1];
+		nd->on_device = true;
+		if (n == 64) { dev_exec(c, ops, n, "sim_create_node"); n = 0; }
+	}
+	if (n) { dev_exec(c, ops, n, "sim_create_node"); n = 0; }
+	while (c->rsrc_pushed < c->n_rsrc) {
+		int first = c->rsrc_pushed;
+		while (c->rsrc_pushed < c->n_rsrc && n < 64) {
+			struct resource *r = c->rsrc[c->rsrc_pushed++];
+			struct ns_sc_op *op = &ops[n++];
+			memset(op, 0, sizeof *op);
+			op->kind = NS_OP_NEWRES; op->a = r->owner->index; op->b = r->bit_rate; op->c = (int32_t)r->resource_id; op->start = (int64_t)r->len;
+		}
+		dev_exec(c, ops, n, "sim_node_new_resource");
+		for (int i = 0; i < n; i++) {
+			struct resource *r = c->rsrc[first+i];
+			if (ops[i].b < 0) continue;
+			r->dev_slot = ops[i].b;
+			GROW(c->res_by_slot, r->dev_slot, c->cap_res); c->res_by_slot[r->dev_slot] = r;
+			struct range *g = r->ranges.next[0] ? skip_list_entry(r->ranges.next[0], struct range, ranges) : NULL;
+			if (g && ops[i].c >= 0) { g->dev_slot = ops[i].c; GROW(c->rng_by_slot, g->dev_slot, c->cap_rng); c->rng_by_slot[g->dev_slot] = g; }
+		}
+		n = 0;
+	}
+}
+
+/* the device tables are laid out when the first flow (or the event loop) needs them */
+static void materialize(struct ns_host_core *c){
+	if (c->dev) return;
+	struct ns_sc_header H;
+	memset(&H, 0, sizeof H);
+	H.magic = NS_SC_MAGIC; H.version = NS_SC_VERSION; H.seed = 1; H.n_groups = 1;
+	char buf[sizeof H+8];
+	memset(buf, 0, sizeof buf);
+	memcpy(buf, &H, sizeof H);                              /* no nodes, no resources, group_off = {0, 0}: the module itself is the script */
+	struct ns_dev_opts o;
+	memset(&o, 0, sizeof o);
+	/* nothing is known about how many nodes / flows the module will create: the tables are sized by the environment
+	 * (the defaults fit a p2p.c run of a few thousand clients) */
+	const char *ev;
+	o.device = c->device; o.mode = NS_MODE_SEQ; o.want_records = c->want_records;
+	o.features_off = 8;                                     /* NS_FEAT_INIT_REC: sim_create_node writes the R_NODE_CREATE records itself */
+	o.cap_nodes = (ev = getenv("NS_CAP_NODES")) ? atoi(ev) : (c->n_nodes*2 > 1 << 14 ? c->n_nodes*2 : 1 << 14);
+	o.cap_flows = (ev = getenv("NS_CAP_FLOWS")) ? atoi(ev) : 1 << 16;      /* concurrent flows */
+	o.cap_ord = (ev = getenv("NS_CAP_ORD")) ? atoi(ev) : 1 << 21;          /* flows ever created */
+	o.cap_ranges = 2*o.cap_flows+4*o.cap_nodes+16;
+	o.cap_users = (ev = getenv("NS_CAP_USERS")) ? atoi(ev) : 1 << 16;      /* pending module-owned events */
+	o.ring_cap = 1u << 22; o.record_cap = 64u << 20;
+	int rc = ns_dev_create(&c->dev, buf, sizeof buf, &o);
+	if (rc) { c->dev = NULL; die(rc, "ns_dev_create"); }
+	flush_pending(c);
+	if ((rc = ns_dev_rng_set(c->dev, &c->rng))) die(rc, "ns_dev_rng_set");   /* the stream goes on where the host left it */
+}
+
+/* ---------------------------------------------------------------- mirrors */
+static void flow_unlink(struct ns_host_core *c, struct flow *f){
+	if (f->closed) return;
+	f->closed = true;
+	list_del(&f->conns[0]); list_del(&f->conns[1]);
+	HASH_DELETE(hh2, f->peer[0]->outs, f);
+	if (f->hh.tbl) HASH_DEL(c->s->flows, f);
+	if (f->srng) { list_del(&f->consumers); f->srng->owner->nconsumer--; }
+	if (f->drng) { if (f->drng->producer == f) f->drng->producer = NULL; f->drng->owner->nproducer--; }
+	f->done->active = false; f->drain->active = false;
+}
+static struct range *range_mirror_new(struct ns_host_core *c, struct resource *r, int slot, size_t start, double len){
+	struct range *g = range_new(start, 0);
+	g->len = len; g->total_len = r->len; g->owner = r; g->dev_slot = slot;
+	int key = (int)start;
+	struct skip_list_head *after = skip_list_find_le(&r->ranges, &key, range_start_cmp);   /* sorted by start; no random() draw: the device burns it */
+	ns_skip_link_after(&g->ranges, after ? after : &r->ranges);
+	if (slot >= 0) { GROW(c->rng_by_slot, slot, c->cap_rng); c->rng_by_slot[slot] = g; }
+	return g;
+}
+/* every number a handler may read, as the device has it now */
+static void refresh(struct ns_host_core *c){
+	if (!c->dev) return;
+	struct sim_state *s = c->s;
+	{
+		static double *st; static int st_cap;
+		if (st_cap < c->n_nodes) { st_cap = c->n_nodes*2; st = realloc(st, (size_t)st_cap*32); }
+		size_t k = 0;
+		if (!ns_dev_node_state(c->dev, st, (size_t)c->nodes_pushed, &k))
+			for (size_t i = 0; i < k; i++) {
+				c->nodes[i]->bandwidth_usage[0] = st[4*i]; c->nodes[i]->bandwidth_usage[1] = st[4*i+1];
+				c->nodes[i]->total_bwupbound[0] = st[4*i+2]; c->nodes[i]->total_bwupbound[1] = st[4*i+3];
+			}
+	}
+	int nf = 0, nr = 0;
+	for (;;) {
+		if (!c->vf_cap) { c->vf_cap = 256; c->vr_cap = 512; c->vf = malloc(sizeof *c->vf*(size_t)c->vf_cap); c->vr = malloc(sizeof *c->vr*(size_t)c->vr_cap); }
+		int rc = ns_dev_host_view(c->dev, c->vf, c->vf_cap, &nf, c->vr, c->vr_cap, &nr);
+		if (rc) die(rc, "ns_dev_host_view");
+		if (nf <= c->vf_cap && nr <= c->vr_cap) break;
+		while (c->vf_cap < nf) c->vf_cap *= 2;
+		while (c->vr_cap < nr) c->vr_cap *= 2;
+		c->vf = realloc(c->vf, sizeof *c->vf*(size_t)c->vf_cap); c->vr = realloc(c->vr, sizeof *c->vr*(size_t)c->vr_cap);
+	}
+	const unsigned ep = ++c->epoch;
+	for (int i = 0; i < nr; i++) {
+		const struct ns_view_range *v = &c->vr[i];
+		struct resource *r = v->res < c->cap_res ? c->res_by_slot[v->res] : NULL;
+		if (!r) continue;                                   /* a resource the host never saw cannot exist: every resource is created here */
+		struct range *g = v->slot < c->cap_rng ? c->rng_by_slot[v->slot] : NULL;
+		if (!g || g->owner != r || g->start != (size_t)v->start) g = range_mirror_new(c, r, v->slot, (size_t)v->start, v->len);
+		g->total_len = (size_t)v->total_len;
+		g->len = g->dev_len = v->len; g->lenc = g->dev_lenc = v->lenc; g->last_update = g->dev_last = v->last_update;
+		g->producer = (v->producer_ord >= 0 && v->producer_ord < c->n_flows) ? c->flows[v->producer_ord] : NULL;
+		g->seen = ep;
+	}
+	for (int k = 0; k < c->cap_rng; k++) {                  /* merged into its predecessor (range_merge_with_next, range.c:83-124): out of the list */
+		struct range *g = c->rng_by_slot[k];
+		if (!g || g->seen == ep) continue;
+		struct flow *f;
+		while (!list_empty(&g->consumers)) { f = list_entry(g->consumers.next, struct flow, consumers); list_del(&f->consumers); INIT_LIST_HEAD(&f->consumers); f->srng = NULL; }
+		if (g->ranges.next) skip_list_delete(&g->ranges);
+		c->rng_by_slot[k] = NULL;
+	}
+	for (int i = 0; i < nf; i++) {
+		const struct ns_view_flow *v = &c->vf[i];
+		struct flow *f = (v->ord >= 0 && v->ord < c->n_flows) ? c->flows[v->ord] : NULL;
+		if (!f || f->closed) continue;
+		f->seen = ep;
+		f->speed[0] = v->speed[0]; f->speed[1] = v->speed[1];
+		if (!f->hh.tbl) { f->flow_id = v->flow_id; HASH_ADD_INT(s->flows, flow_id, f); }
+		f->done->active = !isinf(v->done_t); if (f->done->active) f->done->time = v->done_t;
+		f->drain->active = !isinf(v->drain_t); if (f->drain->active) f->drain->time = v->drain_t;
+		f->drain->type = v->drain_type == FLOW_SPEED_THROTTLE ? FLOW_SPEED_THROTTLE : FLOW_DRAIN;
+		struct range *dr = (v->drng >= 0 && v->drng < c->cap_rng) ? c->rng_by_slot[v->drng] : NULL;
+		struct range *sr = (v->srng >= 0 && v->srng < c->cap_rng) ? c->rng_by_slot[v->srng] : NULL;
+		if (dr) f->drng = dr;
+		if (sr && sr != f->srng) {                          /* its source range was merged into the one before it */
+			if (f->srng) list_del(&f->consumers);
+			f->srng = sr; list_add(&f->consumers, &sr->consumers);
+		}
+	}
+	for (int k = 0; k < c->n_flows; k++) {                  /* closed by the device (flow_done_cleaner, flow.c:403-406) */
+		struct flow *f = c->flows[k];
+		if (f && !f->closed && f->seen != ep) flow_unlink(c, f);
+	}
+}
+/* a handler advanced a range itself (_range_update): the device takes the new state over */
+static void push_range_updates(struct ns_host_core *c){
+	if (!c->dev) return;
+	struct ns_sc_op ops[64]; int n = 0;
+	for (int k = 0; k < c->cap_rng; k++) {
+		struct range *g = c->rng_by_slot[k];
+		if (!g || (g->len == g->dev_len && g->lenc == g->dev_lenc && g->last_update == g->dev_last)) continue;
+		struct ns_sc_op *op = &ops[n++];
+		memset(op, 0, sizeof *op);
+		op->kind = NS_OP_RANGE_SET; op->a = k; op->x = g->len; op->y = g->lenc; memcpy(&op->start, &g->last_update, 8);
+		g->dev_len = g->len; g->dev_lenc = g->lenc; g->dev_last = g->last_update;
+		if (n == 64) { dev_exec(c, ops, n, "range update"); n = 0; }
+	}
+	if (n) dev_exec(c, ops, n, "range update");
+}
+
+/* ---------------------------------------------------------------- the module API */
 /* sim_create_node, sim.c:113-125: id = random() until unused */
 struct node *sim_create_node(struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
-	if (c->dev) { log_err("sim_create_node after the first flow is not supported by the device core\n"); return NULL; }
-	struct node *n = talloc(1, struct node);
+	struct node *n = talloc(1, struct node), *on;
 	n->state = N_OFFLINE;
-	n->store = talloc(1, struct store);
-	for (;;) {
-		n->node_id = ns_rand_next_host(&c->rng);
-		int dup = 0;
-		for (int i = 0; i < c->n_nodes; i++) if (c->nodes[i]->node_id == n->node_id) dup = 1;
-		if (!dup) break;
-	}
+	n->store = store_new();
+	INIT_LIST_HEAD(&n->conns[0]); INIT_LIST_HEAD(&n->conns[1]);
+	do {
+		n->node_id = core_random(c);
+		HASH_FIND_INT(s->nodes, &n->node_id, on);
+	} while (on);
+	HASH_ADD_INT(s->nodes, node_id, n);
 	n->index = c->n_nodes;
 	GROW(c->nodes, c->n_nodes, c->cap_nodes);
 	c->nodes[c->n_nodes++] = n;
@@ -102,175 +308,94 @@ struct node *sim_create_node(struct sim_state *s){
 	return n;
 }
 
-static struct resource *store_add(struct node *n, id_t rid, size_t len, int script_index){
-	struct resource *r = talloc(1, struct resource);
-	r->resource_id = rid; r->len = len; r->owner = n; r->script_index = script_index;
-	r->next_in_store = n->store->head; n->store->head = r;
-	n->store->total_size += len;
-	return r;
+/* a complete copy of a resource on a node: one range [0, len), whose skip-list insert takes one random() draw */
+static void resource_attach(struct ns_host_core *c, struct node *n, struct resource *r){
+	r->owner = n;
+	struct range *g = range_new(0, r->len);
+	g->total_len = r->len; g->owner = r;
+	ns_skip_link_after(&g->ranges, &r->ranges);
+	core_random(c);                                         /* resource_new_range -> skip_list_insert (range.h:71-82, skiplist.h:34-40) */
+	GROW(c->rsrc, c->n_rsrc, c->cap_rsrc);
+	c->rsrc[c->n_rsrc++] = r;
 }
-
 /* sim_node_new_resource, sim.c:129-140 */
 struct resource *sim_node_new_resource(struct node *n, size_t len){
 	struct ns_host_core *c = the_core;
-	if (c->dev) { log_err("sim_node_new_resource after the first flow is not supported by the device core\n"); return NULL; }
-	id_t rid = ns_rand_next_host(&c->rng);
-	while (store_get(n->store, rid)) rid = ns_rand_next_host(&c->rng);
-	struct resource *r = store_add(n, rid, len, c->n_rsrc);
-	ns_rand_next_host(&c->rng);               /* resource_new_range -> skip_list_insert burns one draw */
-	GROW(c->rsrc, c->n_rsrc, c->cap_rsrc);
-	c->rsrc[c->n_rsrc++] = r;
+	struct resource *r = resource_new(core_random(c), len);
+	r->owner = n;
+	while (store_set(n->store, r) == -1) r->resource_id = core_random(c);
+	resource_attach(c, n, r);
 	return r;
 }
-
 /* sim_node_add_resource, sim.c:141-154 */
 struct resource *sim_node_add_resource(struct node *n, struct resource *r){
 	struct ns_host_core *c = the_core;
-	if (c->dev) { log_err("sim_node_add_resource after the first flow is not supported by the device core\n"); return NULL; }
 	if (store_get(n->store, r->resource_id)) return NULL;
-	int idx = -1;
-	for (int i = 0; i < c->n_rsrc; i++) if (c->rsrc[i]->resource_id == r->resource_id) { idx = i; break; }
-	if (idx < 0) return NULL;
-	struct resource *nr = store_add(n, r->resource_id, r->len, idx);
+	struct resource *nr = resource_new(r->resource_id, r->len);
 	nr->bit_rate = r->bit_rate;
-	ns_rand_next_host(&c->rng);
-	GROW(c->copies, c->n_copies, c->cap_copies);
-	c->copies[c->n_copies].node = n->index; c->copies[c->n_copies].res = idx; c->n_copies++;
+	nr->owner = n;
+	store_set(n->store, nr);
+	resource_attach(c, n, nr);
 	return nr;
+}
+void node_del_resource(struct resource *r){
+	(void)r;
+	log_err("node_del_resource is not supported by the device core (raise max_rsrc)\n");
+	abort();
 }
 
 /* sim_register_handler, sim.c:96-111: sorted by priority, equal priority in registration order */
 void sim_register_handler(int type, int priority, event_handler_func f, struct sim_state *s){
-	struct ns_host_core *c = core_of(s);
-	struct handler *h = talloc(1, struct handler), **pp = &c->handlers[type];
-	h->f = f; h->pri = priority;
-	while (*pp && (*pp)->pri <= priority) pp = &(*pp)->next;
-	h->next = *pp; *pp = h;
-}
-
-/* the device tables are laid out when the first flow (or the event loop) needs them */
-static int materialize(struct ns_host_core *c){
-	if (c->dev) return 0;
-	struct ns_sc_header H;
-	memset(&H, 0, sizeof H);
-	H.magic = NS_SC_MAGIC; H.version = NS_SC_VERSION; H.seed = 1;
-	H.n_nodes = c->n_nodes; H.n_resources = c->n_rsrc; H.n_copies = c->n_copies; H.n_groups = 1;
-	size_t len = sizeof H+(size_t)c->n_nodes*16+(size_t)c->n_rsrc*sizeof(struct ns_sc_resource)+
-		(size_t)c->n_copies*sizeof(struct ns_sc_copy)+8;
-	char *buf = calloc(1, len), *p = buf;
-	memcpy(p, &H, sizeof H); p += sizeof H;
-	for (int i = 0; i < c->n_nodes; i++) { memcpy(p, &c->nodes[i]->maximum_bandwidth[0], 8); p += 8; }
-	for (int i = 0; i < c->n_nodes; i++) { memcpy(p, &c->nodes[i]->maximum_bandwidth[1], 8); p += 8; }
-	for (int i = 0; i < c->n_rsrc; i++) {
-		struct ns_sc_resource r = { c->rsrc[i]->owner->index, c->rsrc[i]->bit_rate, (int64_t)c->rsrc[i]->len };
-		memcpy(p, &r, sizeof r); p += sizeof r;
-	}
-	for (int i = 0; i < c->n_copies; i++) {
-		struct ns_sc_copy cp = { c->copies[i].node, c->copies[i].res };
-		memcpy(p, &cp, sizeof cp); p += sizeof cp;
-	}
-	/* group_off = {0, 0}: the module itself is the script */
-	struct ns_dev_opts o;
-	memset(&o, 0, sizeof o);
-	/* the module is the script: nothing is known about how many flows it will establish, so the tables are
-	 * sized by the environment (defaults fit a p2p.c run of a few thousand clients) */
-	const char *ev;
-	o.device = c->device; o.mode = NS_MODE_SEQ; o.want_records = c->want_records;
-	o.features_off = 8;                                     /* NS_FEAT_INIT_REC: sim_create_node wrote the R_NODE_CREATE records itself, interleaved with the module's own */
-	o.cap_flows = (ev = getenv("NS_CAP_FLOWS")) ? atoi(ev) : 1 << 17;      /* concurrent flows */
-	o.cap_ord = (ev = getenv("NS_CAP_ORD")) ? atoi(ev) : 1 << 21;          /* flows ever created */
-	o.cap_ranges = 2*o.cap_flows+c->n_rsrc+c->n_copies+16;
-	o.cap_users = (ev = getenv("NS_CAP_USERS")) ? atoi(ev) : 1 << 17;      /* pending module-owned events */
-	o.ring_cap = 1u << 22; o.record_cap = 64u << 20;
-	int rc = ns_dev_create(&c->dev, buf, len, &o);
-	free(buf);
-	if (rc) { log_err("device core: %s\n", ns_strerror(rc)); exit(3); }
-	for (int i = 0; i < c->n_nodes; i++) {              /* the device drew the same ids in the same order */
-		uint32_t id; ns_dev_node_id(c->dev, i, &id);
-		if (id != c->nodes[i]->node_id) { log_err("node id stream diverged\n"); exit(3); }
-	}
-	for (int i = 0; i < c->n_rsrc; i++) {
-		uint32_t id; ns_dev_resource_id(c->dev, i, &id);
-		if (id != c->rsrc[i]->resource_id) { log_err("resource id stream diverged\n"); exit(3); }
-	}
-	return 0;
-}
-
-static void refresh_flow(struct ns_host_core *c, struct flow *f){
-	struct ns_flow_info fi;
-	if (ns_dev_flow_info(c->dev, f->ord, &fi) || !fi.alive) return;
-	f->speed[0] = fi.speed[0]; f->speed[1] = fi.speed[1];
-	f->flow_id = fi.flow_id;
-	if (f->drng) { f->drng->start = (size_t)fi.drng_start; f->drng->len = fi.drng_len; f->drng->last_update = c->s->now; }
-}
-static void refresh_nodes(struct ns_host_core *c){
-	double *st = malloc((size_t)c->n_nodes*32); size_t k = 0;
-	if (!ns_dev_node_state(c->dev, st, c->n_nodes, &k))
-		for (size_t i = 0; i < k; i++) {
-			c->nodes[i]->bandwidth_usage[0] = st[4*i]; c->nodes[i]->bandwidth_usage[1] = st[4*i+1];
-			c->nodes[i]->total_bwupbound[0] = st[4*i+2]; c->nodes[i]->total_bwupbound[1] = st[4*i+3];
-		}
-	free(st);
-}
-
-void ns_host_refresh_ranges(struct resource *r){
-	struct ns_host_core *c = the_core;
-	if (!c || !c->dev) return;
-	int cap = 64, n = 0;
-	struct ns_range_info *ri = malloc((size_t)cap*sizeof *ri);
-	for (;;) {                                              /* as many ranges as the resource has */
-		if (ns_dev_node_ranges(c->dev, r->owner->index, r->resource_id, ri, cap, &n)) { free(ri); return; }
-		if (n < cap) break;
-		cap *= 2;
-		ri = realloc(ri, (size_t)cap*sizeof *ri);
-	}
-	for (struct range *g = r->first, *nx; g; g = nx) { nx = g->next; free(g); }
-	r->first = NULL;
-	struct range **pp = &r->first;
-	for (int i = 0; i < n; i++) {
-		struct range *g = talloc(1, struct range);
-		g->start = (size_t)ri[i].start; g->total_len = (size_t)ri[i].total_len; g->len = ri[i].len;
-		g->owner = r; g->last_update = c->s->now;
-		g->producer = (ri[i].producer_ord >= 0 && ri[i].producer_ord < c->n_flows) ? c->flows[ri[i].producer_ord] : NULL;
-		*pp = g; pp = &g->next;
-	}
-	free(ri);
+	struct event_handler *neh = talloc(1, struct event_handler), *eh;
+	neh->f = f; neh->pri = priority;
+	struct list_head *pos = &s->handlers[type];
+	list_for_each_entry(eh, &s->handlers[type], handlers) if ((int)eh->pri > priority) { pos = &eh->handlers; break; }
+	list_add_tail(&neh->handlers, pos);                     /* before the first handler of a higher priority */
 }
 
 /* sim_establish_flow, sim.c:42-94 */
 struct flow *sim_establish_flow(id_t rid, size_t start, struct node *src, struct node *dst, struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
-	materialize(c);
 	struct resource *sr = store_get(src->store, rid);
 	if (!sr) { log_err("The resource %d doesn't exist on source node %d\n", rid, src->node_id); return NULL; }
 	struct resource *dr = store_get(dst->store, rid);
-	if (!dr) { dr = store_add(dst, rid, sr->len, sr->script_index); dr->bit_rate = sr->bit_rate; }
+	if (dr && range_get(dr, start)) { log_err("Trying to create a flow to a existing range.\n"); return NULL; }   /* sim.c:62-67 */
+	materialize(c);
+	flush_pending(c);
+	push_range_updates(c);
 	struct ns_sc_op op;
 	memset(&op, 0, sizeof op);
-	op.kind = NS_OP_CREATE; op.a = src->index; op.b = dst->index; op.c = sr->script_index; op.start = (int64_t)start;
+	op.kind = NS_OP_CREATE_RID; op.a = src->index; op.b = dst->index; op.c = (int32_t)rid; op.start = (int64_t)start;
 	op.x = s->bwcalc(src->user_data, dst->user_data);      /* flow.c:303-304 */
 	op.y = s->dlycalc(src->user_data, dst->user_data);     /* flow.c:309 */
-	int rc = ns_dev_exec(c->dev, &op, 1);
-	if (rc) { log_err("device core: %s\n", ns_strerror(rc)); exit(3); }
-	GROW(c->flows, c->n_flows, c->cap_flows);
-	if (op.a < 0) {                                        /* sim.c:62-67 */
-		log_err("Trying to create a flow to a existing range.\n");
-		c->flows[c->n_flows++] = NULL;
-		return NULL;
+	dev_exec(c, &op, 1, "sim_establish_flow");
+	if (op.a < 0) die(NS_E_INTERNAL, "sim_establish_flow refused by the device");
+	if (!dr) {                                              /* sim.c:54-61: the destination learns of the resource */
+		dr = resource_new(sr->resource_id, sr->len);
+		dr->bit_rate = sr->bit_rate; dr->owner = dst;
+		store_set(dst->store, dr);
+		dr->dev_slot = op.b;
+		GROW(c->res_by_slot, dr->dev_slot, c->cap_res); c->res_by_slot[dr->dev_slot] = dr;
 	}
 	struct flow *f = talloc(1, struct flow);
 	f->ord = op.a;
-	while (c->n_flows < f->ord) { GROW(c->flows, c->n_flows, c->cap_flows); c->flows[c->n_flows++] = NULL; }
-	GROW(c->flows, c->n_flows, c->cap_flows);
-	c->flows[c->n_flows++] = f;
+	GROW(c->flows, f->ord, c->cap_flows);
+	if (c->n_flows <= f->ord) c->n_flows = f->ord+1;
+	c->flows[f->ord] = f;
 	f->peer[0] = src; f->peer[1] = dst; f->dst_id = dst->node_id;
-	f->out_next = src->outs; src->outs = f;
 	f->bwupbound = op.x; f->delay = op.y; f->resource_id = rid;
 	f->start = start; f->begin_time = s->now;
-	f->drng = talloc(1, struct range);
-	f->drng->owner = dr; f->drng->total_len = dr->len; f->drng->producer = f; f->drng->start = start;
+	INIT_LIST_HEAD(&f->spd_evs);
+	list_add(&f->conns[0], &src->conns[0]);                 /* flow.c:311-312: newest first */
+	list_add(&f->conns[1], &dst->conns[1]);
+	HASH_ADD(hh2, src->outs, dst_id, sizeof(f->dst_id), f);
+	f->done = event_new(0, FLOW_DONE, f); f->drain = event_new(0, FLOW_DRAIN, f);
+	f->drng = range_mirror_new(c, dr, (int)op.c, start, 0);
+	f->drng->producer = f; f->drng->last_update = s->now;
+	f->srng = ((int)op.start >= 0 && (int)op.start < c->cap_rng) ? c->rng_by_slot[(int)op.start] : NULL;
+	if (f->srng) list_add(&f->consumers, &f->srng->consumers); else INIT_LIST_HEAD(&f->consumers);
 	sr->nconsumer++; dr->nproducer++;
-	refresh_flow(c, f);
+	refresh(c);
 	return f;
 }
 
@@ -278,35 +403,30 @@ struct flow *sim_establish_flow(id_t rid, size_t start, struct node *src, struct
 void flow_close(struct flow *f, struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
 	if (!f || f->closed) return;
+	push_range_updates(c);
 	struct ns_sc_op op;
 	memset(&op, 0, sizeof op);
 	op.kind = NS_OP_CLOSE; op.a = f->ord;
-	ns_dev_exec(c->dev, &op, 1);
-	f->closed = true;
-}
-
-bool is_connected(struct node *src, struct node *dst){    /* flow.h:29-35: src->outs, keyed by the destination */
-	struct flow **pp = &src->outs;
-	while (*pp) {
-		if ((*pp)->closed) { *pp = (*pp)->out_next; continue; }       /* unlink what has been closed since */
-		if ((*pp)->peer[1] == dst) return true;
-		pp = &(*pp)->out_next;
-	}
-	return false;
+	dev_exec(c, &op, 1, "flow_close");
+	flow_unlink(c, f);
+	refresh(c);
 }
 
 /* event_add, event.h:56-74, for module-owned events */
 void event_add(struct event *e, struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
 	if (!e || e->active) return;
+	if (e->time < s->now) {                                 /* event.h:58-65 */
+		if (e->time < s->now-eps) { log_err("Add event back in time, e: %lf now: %lf\n", e->time, s->now); abort(); }
+		e->time = s->now;
+	}
+	if (isnan(e->time)) { log_err("Add event at nan\n"); abort(); }
 	materialize(c);
 	if (e->token < 0) { GROW(c->uev, c->n_uev, c->cap_uev); e->token = c->n_uev; c->uev[c->n_uev++] = e; }
 	struct ns_sc_op op;
 	memset(&op, 0, sizeof op);
 	op.kind = NS_OP_SCHED; op.a = e->token; op.c = 0; op.x = e->time;
-	int rc = ns_dev_exec(c->dev, &op, 1);
-	if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time, e: %lf now: %lf\n", e->time, s->now); abort(); }
-	if (rc == NS_E_NAN_TIME) { log_err("Add event at nan\n"); abort(); }
+	dev_exec(c, &op, 1, "event_add");
 	e->active = true;
 	e->dev_slot = op.b;
 }
@@ -319,24 +439,37 @@ void event_remove(struct event *e){
 	struct ns_sc_op op;
 	memset(&op, 0, sizeof op);
 	op.kind = NS_OP_CANCEL; op.a = e->dev_slot;
-	ns_dev_exec(c->dev, &op, 1);
+	dev_exec(c, &op, 1, "event_remove");
 	e->dev_slot = -1;
 }
 
 void sim_send_packet(void *data, int len, struct node *src, struct node *dst, struct sim_state *s){
 	(void)data; (void)len; (void)src; (void)dst; (void)s;   /* dead in the reference too: no PACKET_DONE handler */
 }
-void sim_node_change_state(struct node *n, enum node_state state, struct sim_state *s){   /* sim.h:25-28 */
-	n->state = state;
-	uint8_t v = (uint8_t)state;
-	write_record(0, R_NODE_STATE, n->node_id, 1, &v, s);
-}
+void ns_host_refresh(struct sim_state *s){ refresh(core_of(s)); }
 
 void user_speed_change(struct event *e, struct sim_state *s){ (void)e; (void)s; }   /* user.c:7-13 */
 void user_done(struct event *e, struct sim_state *s){ (void)e; (void)s; }
 
-static void rec_reserve(struct ns_host_core *c, size_t more);
-static void pull_records(struct ns_host_core *c);
+/* ---------------------------------------------------------------- records */
+static void rec_reserve(struct ns_host_core *c, size_t more){
+	if (c->rec_len+more <= c->rec_cap) return;
+	while (c->rec_len+more > c->rec_cap) c->rec_cap = c->rec_cap ? c->rec_cap*2 : 1 << 20;
+	c->rec = realloc(c->rec, c->rec_cap);
+}
+/* append what the device has produced since the last pull to the host copy of the record stream */
+static void pull_records(struct ns_host_core *c){
+	if (!c->want_records || !c->dev) return;
+	for (;;) {
+		size_t got = 0, total = 0;
+		ns_dev_records(c->dev, NULL, 0, c->dev_off, &got, &total);
+		if (total <= c->dev_off) return;
+		rec_reserve(c, total-c->dev_off);
+		ns_dev_records(c->dev, c->rec+c->rec_len, total-c->dev_off, c->dev_off, &got, &total);
+		if (!got) return;
+		c->rec_len += got; c->dev_off += got;
+	}
+}
 /* write_record, record.c:27-117, for records the MODULE side writes (sim_create_node, sim_node_change_state, a module's own):
  * what the device has produced so far is pulled first, so the merged stream keeps the reference's order */
 void write_record(uint8_t major, uint8_t minor, uint32_t id, int8_t bytes, void *value, struct sim_state *s){
@@ -365,7 +498,7 @@ void write_record(uint8_t major, uint8_t minor, uint32_t id, int8_t bytes, void 
 	}
 	c->rec_len += (size_t)n;
 }
-/* open_record, record.c:119-153: remember the file; the device's record stream is saved there */
+/* open_record, record.c:119-153: remember the file; the record stream is saved there */
 void open_record(const char *filename, int create, struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
 	(void)create;
@@ -373,27 +506,8 @@ void open_record(const char *filename, int create, struct sim_state *s){
 	c->record_path = strdup(filename);
 	c->want_records = 1;
 }
-
-/* append what the device has produced since the last pull to the host copy of the record stream */
-static void rec_reserve(struct ns_host_core *c, size_t more){
-	if (c->rec_len+more <= c->rec_cap) return;
-	while (c->rec_len+more > c->rec_cap) c->rec_cap = c->rec_cap ? c->rec_cap*2 : 1 << 20;
-	c->rec = realloc(c->rec, c->rec_cap);
-}
-static void pull_records(struct ns_host_core *c){
-	if (!c->want_records || !c->dev) return;
-	for (;;) {
-		size_t got = 0, total = 0;
-		ns_dev_records(c->dev, NULL, 0, c->dev_off, &got, &total);
-		if (total <= c->dev_off) return;
-		rec_reserve(c, total-c->dev_off);
-		ns_dev_records(c->dev, c->rec+c->rec_len, total-c->dev_off, c->dev_off, &got, &total);
-		if (!got) return;
-		c->rec_len += got; c->dev_off += got;
-	}
-}
 static void save_records(struct ns_host_core *c){
-	if (!c->record_path || !c->dev) return;
+	if (!c->record_path) return;
 	pull_records(c);
 	size_t total = c->rec_len;
 	uint8_t *buf = malloc(total+4);
@@ -410,12 +524,14 @@ static void save_records(struct ns_host_core *c){
 	free(buf);
 }
 
-/* the event loop, main.c:50-67, with the default handlers (main.c:44-48) on the device */
+/* ---------------------------------------------------------------- the event loop, main.c:50-67, with the default handlers (main.c:44-48) on the device */
 int ns_host_run(struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
 	materialize(c);
+	flush_pending(c);
+	push_range_updates(c);
 	uint32_t mask = 1u << USER;
-	for (int t = 0; t < LAST_EVENT; t++) if (c->handlers[t]) mask |= 1u << t;
+	for (int t = 0; t < LAST_EVENT; t++) if (!list_empty(&s->handlers[t])) mask |= 1u << t;
 	ns_dev_set_host_mask(c->dev, mask);
 	int rc = 0;
 	while (!s->exit) {
@@ -441,10 +557,10 @@ int ns_host_run(struct sim_state *s){
 		memset(&tmp, 0, sizeof tmp);
 		tmp.type = ev.type; tmp.time = ev.time; tmp.token = -1;
 		bool need_free = false;
-		refresh_nodes(c);
-		if (f) refresh_flow(c, f);
+		refresh(c);
 		switch (ev.type) {
 		case SPEED_CHANGE:
+			memset(&se, 0, sizeof se);
 			se.e = e; se.f = f; se.speed = ev.speed; se.type = ev.dir;
 			tmp.data = &se;
 			break;
@@ -452,14 +568,23 @@ int ns_host_run(struct sim_state *s){
 			e = (ev.token >= 0 && ev.token < c->n_uev) ? c->uev[ev.token] : NULL;
 			if (!e) continue;
 			e->active = false;                              /* event_pop, event.h:20-25 */
+			e->dev_slot = -1;
 			need_free = e->auto_free;
 			break;
+		case FLOW_DONE:
+			if (f) { e = f->done; e->active = false; }
+			tmp.data = f;
+			break;
 		default:
+			if (f) { e = f->drain; e->active = false; }
 			tmp.data = f;
 		}
-		for (struct handler *h = c->handlers[ev.type]; h; h = h->next) h->f(e, s);
-		if (ev.type == FLOW_DONE && f) f->closed = true;    /* flow_done_cleaner runs on the device next */
+		struct event_handler *eh;
+		list_for_each_entry(eh, &s->handlers[ev.type], handlers) eh->f(e, s);
+		if (ev.type == FLOW_DONE && f) flow_unlink(c, f);   /* flow_done_cleaner (flow.c:403-406) runs on the device next */
 		if (need_free) { c->uev[ev.token] = NULL; free(e); }   /* main.c:65-66 */
+		flush_pending(c);
+		push_range_updates(c);
 		if (s->exit) {
 			struct ns_sc_op op;
 			memset(&op, 0, sizeof op);
@@ -467,7 +592,6 @@ int ns_host_run(struct sim_state *s){
 			ns_dev_exec(c->dev, &op, 1);
 		}
 	}
-	/* let a pending flow_done_cleaner finish so the record stream is complete */
 	save_records(c);
 	return rc;
 }

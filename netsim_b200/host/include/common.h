@@ -7,5 +7,7 @@
 
 #define talloc(nmemb, type) ((type *)calloc((nmemb), sizeof(type)))
 #define fequ(a, b) ((a)-(b) > -eps && (a)-(b) < eps)
+/* the struct that embeds `member` at address ptr */
+#define container_of(ptr, type, member) ((type *)((char *)(ptr)-offsetof(type, member)))
 
 extern const double eps;   /* 1e-4, sim.c:11 */

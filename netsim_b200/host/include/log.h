@@ -7,7 +7,7 @@
 #include <stdlib.h>
 
 #ifndef LOG_DOMAIN
-# define LOG_DOMAIN "netsim"
+# define LOG_DOMAIN "(missing log domain, file: " __BASE_FILE__ ") "     /* the same default as the reference, log.h:3-5 */
 #endif
 
 #define LOG_EMERG 0
