@@ -54,6 +54,7 @@ struct ns_host_core {
 	struct node **nodes; int n_nodes, cap_nodes, nodes_pushed;
 	struct resource **rsrc; int n_rsrc, cap_rsrc, rsrc_pushed;   /* every resource copy, in creation order */
 	struct flow **flows; int n_flows, cap_flows;           /* by creation ordinal */
+	struct flow **live; int n_live, cap_live;              /* the flows that are still open */
 	struct range **rng_by_slot; int cap_rng;               /* device range slot -> mirror */
 	struct resource **res_by_slot; int cap_res;            /* device resource slot -> mirror */
 	struct event **uev; int n_uev, cap_uev;                /* module-owned USER events by token */
@@ -188,6 +189,7 @@ static void materialize(struct ns_host_core *c){
 static void flow_unlink(struct ns_host_core *c, struct flow *f){
 	if (f->closed) return;
 	f->closed = true;
+	c->live[f->live_idx] = c->live[--c->n_live]; c->live[f->live_idx]->live_idx = f->live_idx;
 	list_del(&f->conns[0]); list_del(&f->conns[1]);
 	HASH_DELETE(hh2, f->peer[0]->outs, f);
 	if (f->hh.tbl) HASH_DEL(c->s->flows, f);
@@ -266,9 +268,9 @@ static void refresh(struct ns_host_core *c){
 			f->srng = sr; list_add(&f->consumers, &sr->consumers);
 		}
 	}
-	for (int k = 0; k < c->n_flows; k++) {                  /* closed by the device (flow_done_cleaner, flow.c:403-406) */
-		struct flow *f = c->flows[k];
-		if (f && !f->closed && f->seen != ep) flow_unlink(c, f);
+	for (int k = c->n_live-1; k >= 0; k--) {                /* closed by the device (flow_done_cleaner, flow.c:403-406) */
+		struct flow *f = c->live[k];
+		if (f->seen != ep) flow_unlink(c, f);
 	}
 }
 /* a handler advanced a range itself (_range_update): the device takes the new state over */
@@ -382,6 +384,8 @@ struct flow *sim_establish_flow(id_t rid, size_t start, struct node *src, struct
 	GROW(c->flows, f->ord, c->cap_flows);
 	if (c->n_flows <= f->ord) c->n_flows = f->ord+1;
 	c->flows[f->ord] = f;
+	GROW(c->live, c->n_live, c->cap_live);
+	f->live_idx = c->n_live; c->live[c->n_live++] = f;
 	f->peer[0] = src; f->peer[1] = dst; f->dst_id = dst->node_id;
 	f->bwupbound = op.x; f->delay = op.y; f->resource_id = rid;
 	f->start = start; f->begin_time = s->now;

@@ -73,6 +73,7 @@ struct flow {
 	struct list_head consumers;
 	/* host core */
 	int ord;                      /* creation ordinal == device handle */
+	int live_idx;
 	bool closed;
 	unsigned seen;
 };

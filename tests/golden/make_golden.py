@@ -118,11 +118,67 @@ def pick_goldens():
     print("pick", len(ks), "tables,", len(val), "candidates,", len(mq), "metric points")
 
 
+# the behaviour library's own test modules and p2p itself, on the unmodified reference core: what the host core
+# (netsim_b200/host) must reproduce byte for byte when the SAME sources are compiled against its headers
+P2P_CFGS = {   # name: (seed for the time() shim, p2p.cfg fields in file order)
+    #            max_rsrc nrh cnp smart nch use_client metric nsvr ncld nclnt end
+    "small50":       (1, (20, 0, 0, 0, 0, 0, 0, 4, 1, 50, 6000)),
+    "base200":       (2, (20, 0, 0, 0, 0, 0, 0, 4, 1, 200, 9000)),
+    "push1":         (5, (20, 0, 0, 0, 1, 0, 1, 8, 8, 300, 8000)),
+    "play2b":        (7, (20, 0, 1, 0, 0, 1, 0, 4, 4, 150, 5000)),      # client_new_play2 with clients as sources: relays, throttles
+    "play2c":        (8, (20, 0, 1, 0, 0, 0, 0, 4, 4, 150, 5000)),
+    "cloudb":        (4, (20, 1, 0, 1, 0, 0, 1, 4, 8, 200, 7000)),      # smart cloud, HOUR_PASS
+    "cloudc":        (9, (20, 1, 0, 0, 1, 0, 0, 4, 8, 200, 7000)),
+    "push2":         (6, (20, 0, 0, 0, 2, 0, 1, 8, 8, 200, 6000)),
+    "config2_seed1": (1, (20, 0, 0, 0, 0, 0, 0, 4, 1, 1000, 36000)),    # SURVEY section 8d, config 2 as specified (slow on the host core)
+}
+P2P_KEYS = ("max_rsrc", "new_resource_handler", "client_new_play", "smart_cloud", "new_connection_handler", "use_client", "metric",
+            "nsvr", "ncld", "nclnt", "end_simulation")
+
+
+def client_goldens():
+    import hashlib, json, subprocess, tempfile
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    src = "/root/reference/modules"
+    lib = [os.path.join(src, f) for f in ("client_behaviour.c", "resource.c", "gaussian.c")]
+    with tempfile.TemporaryDirectory() as d:
+        for k in (2, 3):   # test_client1.c dereferences s->user_data == NULL on the reference itself (client_new_connection): no golden
+            so = os.path.join(d, f"tc{k}.so")
+            subprocess.run(["gcc", "-O2", "-DNDEBUG", "-ffp-contract=off", "-w", "-fPIC", "-shared", "-I/root/reference", "-I" + src,
+                            os.path.join(src, f"test_client{k}.c")] + lib + ["-lm", "-o", so], check=True)
+            p = subprocess.run([os.path.join(ref, "netsim"), so[:-3]], cwd=d, capture_output=True, check=True)
+            open(os.path.join(OUT, f"tc{k}.stderr.txt"), "wb").write(p.stderr)
+    exp = {}
+    for name, (seed, vals) in P2P_CFGS.items():
+        cd = os.path.join(OUT, "p2p", name)
+        os.makedirs(cd, exist_ok=True)
+        open(os.path.join(cd, "p2p.cfg"), "w").write("".join(f"{k}={v}\n" for k, v in zip(P2P_KEYS, vals)))
+        with tempfile.TemporaryDirectory() as d:
+            import shutil
+            shutil.copy(os.path.join(cd, "p2p.cfg"), d)
+            env = dict(os.environ, NS_FAKE_TIME=str(seed), LD_PRELOAD=os.path.join(ref, "timeshim.so"))
+            p = subprocess.run([os.path.join(ref, "netsim"), os.path.join(ref, "modules", "p2p")], cwd=d, capture_output=True, check=True, env=env)
+            data = open(os.path.join(d, "p2p_record"), "rb").read()
+            n = int.from_bytes(data[:4], "big")
+            exp[name] = {"seed": seed, "record_bytes": n, "record_sha256": hashlib.sha256(data[4:4 + n]).hexdigest(),
+                         "stderr_sha256": hashlib.sha256(p.stderr).hexdigest()}
+            if len(p.stderr) < (1 << 20):
+                open(os.path.join(cd, "stderr.txt"), "wb").write(p.stderr)
+            else:
+                exp[name]["slow"] = True
+            print("p2p", name, n, "record bytes,", p.stderr.count(b"\n"), "log lines")
+    json.dump(exp, open(os.path.join(OUT, "p2p", "expected.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pick":
         pick_goldens()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "clients":
+        client_goldens()
         sys.exit(0)
     main()
     stderr_goldens()
     modx_golden()
     pick_goldens()
+    client_goldens()

@@ -79,3 +79,16 @@ def test_swarm_generator_is_valid_script():
     assert len(pairs) == len(cr)       # never two flows between the same pair (flow.c:300)
     assert ((cr["x"] >= 1700) & (cr["x"] <= 4000)).all()
     assert ((cr["y"] >= 0.1 - 1e-12) & (cr["y"] <= 0.56 + 1e-12)).all()
+
+
+def test_host_core_containers():
+    """CPU: the list / hash / skip-list headers modules compile against (netsim_b200/host/include) keep the reference's semantics
+    modules rely on: insertion-order iteration, deletion inside HASH_ITER, sorted skip lists, newest-first lists."""
+    import subprocess, tempfile
+    inc = os.path.join(ROOT, "netsim_b200", "host", "include")
+    with tempfile.TemporaryDirectory(prefix="nscont") as d:
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-O2", "-Wall", "-I" + inc, os.path.join(ROOT, "tests", "modules", "t_containers.c"), "-o", exe], check=True)
+        p = subprocess.run([exe], capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout
+        assert "iter in order 1, left 500" in p.stdout and "skip sorted 1 n 200 ge 18 le 17" in p.stdout and "list 31 13 empty 0" in p.stdout
