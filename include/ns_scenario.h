@@ -39,6 +39,9 @@ enum ns_op_kind {
 	NS_OP_CREATE_RID = 9,  /* NS_OP_CREATE with the resource given by its id (c) instead of a script index; on return .a = creation
 	                          ordinal or -1, .b = the destination's resource slot, .c = the new destination range's slot,
 	                          .start = the source range's slot */
+	NS_OP_DELRES     = 11, /* node_del_resource (sim.h:47-53): a = resource slot; its ranges are freed, the node forgets it */
+	NS_OP_AUTODEL    = 12, /* the module set resource->auto_delete (resource.c:63): a = resource slot; flow_close deletes the resource
+	                          when its last consumer / producer has gone (flow.c:279-281) */
 	NS_OP_RANGE_SET  = 10, /* a module handler advanced a range itself (_range_update, range.h:91-118, from is_resource_usable /
 	                          client_lowwm_event ...): a = range slot, x = len, y = lenc, start = the bits of last_update */
 };

@@ -313,6 +313,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	DA(S.r_start, R); DA(S.r_total, R); DA(S.r_len, R); DA(S.r_lenc, R); DA(S.r_last, R);
 	DA(S.r_prod, R); DA(S.r_res, R); DA(S.r_next, R); DA(S.r_prev, R); DA(S.r_cons, R); DA(S.r_next_free, R);
 	const int Q = S.cap_res;
+	if (o.cap_nodes > 0 && !(H.flags & NS_SC_F_CLIENTS)) DA(S.s_autodel, Q);   // a host core is driving (NS_OP_NEWNODE ...)
 	DA(S.s_id, Q); DA(S.s_len, Q); DA(S.s_node, Q); DA(S.s_first, Q); DA(S.s_nprod, Q); DA(S.s_ncons, Q); DA(S.s_next, Q); DA(S.s_brate, Q);
 	ns_sc_client *d_cl = nullptr; int *d_srv = nullptr;
 	if (has_clients) {
@@ -413,6 +414,7 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	CK(cudaMemcpy(S.n_id, nid.data(), (size_t)N*4, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(S.n_res_head, res_head.data(), (size_t)N*4, cudaMemcpyHostToDevice));
 	if ((rc = fill_i32(S.adj_off, 2*N, 0)) || (rc = fill_i32(S.adj_cap, 2*N, 0)) || (rc = fill_i32(S.adj_len, 2*N, 0)) || (rc = fill_i32(S.adj_live, 2*N, 0))) return rc;
+	if (S.s_autodel) CK(cudaMemset(S.s_autodel, 0, (size_t)S.cap_res));
 	CK(cudaMemset(S.f_gen, 0, (size_t)F*4));
 	CK(cudaMemset(S.f_alive, 0, F));
 	if ((rc = fill_f64(S.q_time, S.ring_cap, INFINITY)) || (rc = fill_f64(S.q_tmin, S.n_ring_tiles, INFINITY))) return rc;
@@ -730,6 +732,7 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 		else if (op.kind == NS_OP_NEWNODE) { if (op.a != d->h.S.n_nodes+new_nodes || op.a >= d->h.cap_nodes) return op.a >= d->h.cap_nodes ? NS_E_TABLE_FULL : NS_E_ARG; new_nodes++; }
 		else if (op.kind == NS_OP_NEWRES) { if (op.a < 0 || op.a >= d->h.S.n_nodes+new_nodes || op.start < 0) return NS_E_ARG; }
 		else if (op.kind == NS_OP_CREATE_RID) { if (op.a < 0 || op.a >= d->h.S.n_nodes+new_nodes || op.b < 0 || op.b >= d->h.S.n_nodes+new_nodes) return NS_E_ARG; }
+		else if (op.kind == NS_OP_DELRES || op.kind == NS_OP_AUTODEL) { if (op.a < 0 || op.a >= d->h.S.cap_res || !d->h.S.s_autodel) return NS_E_ARG; }
 		else if (op.kind == NS_OP_RANGE_SET) { if (op.a < 0 || op.a >= d->h.S.cap_ranges) return NS_E_ARG; }
 		else if (op.kind != NS_OP_SCHED && op.kind != NS_OP_END) return NS_E_ARG;
 	}

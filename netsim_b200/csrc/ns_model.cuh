@@ -659,6 +659,28 @@ __device__ __noinline__ void range_merge_with_next(Ctx &c, int r){
 	}
 }
 
+#ifdef NS_HOST_CORE_OPS
+// node_del_resource, sim.h:47-53: range_clear + store_delete (only reached through the host core: p2p.c evicts resources)
+__device__ __noinline__ void res_delete(Ctx &c, int res){
+	const Sim &S = *c.S;
+	WSYNC();
+	L0 {
+		const int node = S.s_node[res];
+		int prev = -1, cur = S.n_res_head[node];
+		while (cur >= 0 && cur != res) { prev = cur; cur = S.s_next[cur]; }
+		if (cur == res) { if (prev >= 0) S.s_next[prev] = S.s_next[res]; else S.n_res_head[node] = S.s_next[res]; }
+		for (int g = S.s_first[res]; g >= 0; ) {
+			const int nx = S.r_next[g];
+			S.r_res[g] = -1; S.r_next_free[g] = c.st->free_range; c.st->free_range = g;
+			g = nx;
+		}
+		S.s_first[res] = -1;
+		if (S.s_autodel) S.s_autodel[res] = 0;
+	}
+	WSYNC();
+}
+#endif
+
 // ---------------------------------------------------------------- flows
 // flow_create, flow.c:296-337
 __device__ __noinline__ int flow_create(Ctx &c, int src, int dst, double ub, double delay){
@@ -726,6 +748,12 @@ __device__ __noinline__ void flow_close(Ctx &c, int f){
 		S.f_next_free[f] = c.st->free_flow; c.st->free_flow = f;
 		c.st->cnt[NS_CNT_CLOSES] += 1; c.st->cnt[NS_CNT_LIVE_FLOWS] -= 1;
 	}
+#ifdef NS_HOST_CORE_OPS
+	if (S.s_autodel) {                                                // :278-281
+		const int sres = S.r_res[sr];
+		if (S.s_autodel[sres] && S.s_ncons[sres] == 0 && S.s_nprod[sres] == 0) res_delete(c, sres);
+	}
+#endif
 	write_record(c, R_CONN_CLOSE, S.f_id[f], 1, 0, 0);                // :289-290
 	WSYNC();
 }
@@ -1275,6 +1303,14 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 			L0 { S.host_ops[i].b = r; S.host_ops[i].c = g; }
 			WSYNC();
 			break; }
+#ifdef NS_HOST_CORE_OPS
+		case NS_OP_DELRES:
+			if (op.a >= 0 && op.a < c.st->hi_res) res_delete(c, op.a);
+			break;
+		case NS_OP_AUTODEL:
+			if (S.s_autodel && op.a >= 0 && op.a < c.st->hi_res) { L0 S.s_autodel[op.a] = 1; WSYNC(); }
+			break;
+#endif
 		case NS_OP_RANGE_SET: {
 			L0 { S.r_len[op.a] = op.x; S.r_lenc[op.a] = op.y; S.r_last[op.a] = __longlong_as_double(op.start); }
 			WSYNC();

@@ -2,6 +2,7 @@
 // simulation, strictly sequential event handling.  Used for replica ensembles, module inits that are
 // not pure flow creation, the host-callback mode and the sparse phases of the grid engine.
 #define NS_PREFETCH      // one warp per simulation: request an event's lines up front (ns_model.cuh)
+#define NS_HOST_CORE_OPS // k_exec_ops / k_run_seq serve the host core: resource deletion (node_del_resource, auto_delete in flow_close)
 #include "ns_seq.cuh"
 #include "ns_par_api.cuh"
 

@@ -104,6 +104,8 @@ struct Sim {
 	u64 *b_seq; int *b_ref;       // ring entries: ref = -1; L entries: ref = slot
 	// outputs
 	uint8_t *rec; ns_trace_row32 *tr;
+	// host core only (k_exec_ops / k_run_seq in host-callback mode): resource->auto_delete (data.h:34), null otherwise
+	uint8_t *s_autodel;
 };
 
 // Replica ensembles: a replica whose bounded record buffer fills up folds it on the spot — the analyzer reductions take

@@ -21,8 +21,7 @@
  * Module-side records (sim_create_node, sim_node_change_state, a module's own write_record) are merged into the
  * device's record stream in call order; event_remove of a module-owned event cancels it on the device.
  *
- * Limits (documented in INTEGRATION.md): sim_send_packet is not forwarded (dead in the reference too);
- * node_del_resource (p2p.c only when more than max_rsrc resources have been created) is not supported.
+ * Limits (documented in INTEGRATION.md): sim_send_packet is not forwarded (dead in the reference too).
  */
 #define _GNU_SOURCE
 #include <stdarg.h>
@@ -136,17 +135,29 @@ static void flush_pending(struct ns_host_core *c){
 		if (n == 64) { dev_exec(c, ops, n, "sim_create_node"); n = 0; }
 	}
 	if (n) { dev_exec(c, ops, n, "sim_create_node"); n = 0; }
+	for (int k = 0; k < c->n_rsrc; k++) {                   /* resource->auto_delete is set by the module on the struct (resource.c:63) */
+		struct resource *r = c->rsrc[k];
+		if (!r || !r->auto_delete || r->autodel_pushed || r->dev_slot < 0) continue;
+		struct ns_sc_op op;
+		memset(&op, 0, sizeof op);
+		op.kind = NS_OP_AUTODEL; op.a = r->dev_slot;
+		dev_exec(c, &op, 1, "auto_delete");
+		r->autodel_pushed = true;
+	}
 	while (c->rsrc_pushed < c->n_rsrc) {
-		int first = c->rsrc_pushed;
+		struct resource *who[64];
 		while (c->rsrc_pushed < c->n_rsrc && n < 64) {
 			struct resource *r = c->rsrc[c->rsrc_pushed++];
-			struct ns_sc_op *op = &ops[n++];
+			if (!r) continue;                               /* deleted again before it reached the device */
+			struct ns_sc_op *op = &ops[n];
+			who[n++] = r;
 			memset(op, 0, sizeof *op);
 			op->kind = NS_OP_NEWRES; op->a = r->owner->index; op->b = r->bit_rate; op->c = (int32_t)r->resource_id; op->start = (int64_t)r->len;
 		}
+		if (!n) break;
 		dev_exec(c, ops, n, "sim_node_new_resource");
 		for (int i = 0; i < n; i++) {
-			struct resource *r = c->rsrc[first+i];
+			struct resource *r = who[i];
 			if (ops[i].b < 0) continue;
 			r->dev_slot = ops[i].b;
 			GROW(c->res_by_slot, r->dev_slot, c->cap_res); c->res_by_slot[r->dev_slot] = r;
@@ -186,6 +197,7 @@ static void materialize(struct ns_host_core *c){
 }
 
 /* ---------------------------------------------------------------- mirrors */
+static void resource_forget(struct ns_host_core *c, struct resource *r);
 static void flow_unlink(struct ns_host_core *c, struct flow *f){
 	if (f->closed) return;
 	f->closed = true;
@@ -193,9 +205,11 @@ static void flow_unlink(struct ns_host_core *c, struct flow *f){
 	list_del(&f->conns[0]); list_del(&f->conns[1]);
 	HASH_DELETE(hh2, f->peer[0]->outs, f);
 	if (f->hh.tbl) HASH_DEL(c->s->flows, f);
-	if (f->srng) { list_del(&f->consumers); f->srng->owner->nconsumer--; }
+	struct resource *sr = f->srng ? f->srng->owner : NULL;
+	if (f->srng) { list_del(&f->consumers); sr->nconsumer--; }
 	if (f->drng) { if (f->drng->producer == f) f->drng->producer = NULL; f->drng->owner->nproducer--; }
 	f->done->active = false; f->drain->active = false;
+	if (sr && sr->nconsumer == 0 && sr->nproducer == 0 && sr->auto_delete) resource_forget(c, sr);   /* flow.c:278-281; the device's flow_close does the same */
 }
 static struct range *range_mirror_new(struct ns_host_core *c, struct resource *r, int slot, size_t start, double len){
 	struct range *g = range_new(start, 0);
@@ -318,6 +332,7 @@ static void resource_attach(struct ns_host_core *c, struct node *n, struct resou
 	ns_skip_link_after(&g->ranges, &r->ranges);
 	core_random(c);                                         /* resource_new_range -> skip_list_insert (range.h:71-82, skiplist.h:34-40) */
 	GROW(c->rsrc, c->n_rsrc, c->cap_rsrc);
+	r->all_idx = c->n_rsrc;
 	c->rsrc[c->n_rsrc++] = r;
 }
 /* sim_node_new_resource, sim.c:129-140 */
@@ -340,10 +355,29 @@ struct resource *sim_node_add_resource(struct node *n, struct resource *r){
 	resource_attach(c, n, nr);
 	return nr;
 }
+/* range_clear + store_delete of the mirror (sim.h:47-53); the structs stay allocated: a module may still hold a pointer */
+static void resource_forget(struct ns_host_core *c, struct resource *r){
+	for (struct skip_list_head *h = r->ranges.next ? r->ranges.next[0] : NULL, *nx; h; h = nx) {
+		nx = h->next[0];
+		struct range *g = skip_list_entry(h, struct range, ranges);
+		if (g->dev_slot >= 0 && g->dev_slot < c->cap_rng && c->rng_by_slot[g->dev_slot] == g) c->rng_by_slot[g->dev_slot] = NULL;
+		skip_list_deinit_node(&g->ranges);
+	}
+	skip_list_deinit_head(&r->ranges);
+	store_delete(r->owner->store, r);
+	if (r->dev_slot >= 0 && r->dev_slot < c->cap_res) c->res_by_slot[r->dev_slot] = NULL;
+	c->rsrc[r->all_idx] = NULL;
+}
 void node_del_resource(struct resource *r){
-	(void)r;
-	log_err("node_del_resource is not supported by the device core (raise max_rsrc)\n");
-	abort();
+	struct ns_host_core *c = the_core;
+	if (c->dev) {
+		flush_pending(c);                                   /* (it may have been created a moment ago) */
+		struct ns_sc_op op;
+		memset(&op, 0, sizeof op);
+		op.kind = NS_OP_DELRES; op.a = r->dev_slot;
+		dev_exec(c, &op, 1, "node_del_resource");
+	}                                                       /* (not on the device yet: resource_forget empties its slot in the pending list) */
+	resource_forget(c, r);
 }
 
 /* sim_register_handler, sim.c:96-111: sorted by priority, equal priority in registration order */
@@ -378,6 +412,8 @@ struct flow *sim_establish_flow(id_t rid, size_t start, struct node *src, struct
 		store_set(dst->store, dr);
 		dr->dev_slot = op.b;
 		GROW(c->res_by_slot, dr->dev_slot, c->cap_res); c->res_by_slot[dr->dev_slot] = dr;
+		GROW(c->rsrc, c->n_rsrc, c->cap_rsrc);              /* (already on the device: flush_pending is up to date before every create) */
+		dr->all_idx = c->n_rsrc; c->rsrc[c->n_rsrc++] = dr; c->rsrc_pushed = c->n_rsrc;
 	}
 	struct flow *f = talloc(1, struct flow);
 	f->ord = op.a;

@@ -44,7 +44,8 @@ struct resource {
 	bool auto_delete;
 	/* host core */
 	int dev_slot;                 /* slot in the device's resource table, -1 while it only exists on the host */
-	struct resource *next_all;
+	int all_idx;                  /* position in the host core's list of resource copies */
+	bool autodel_pushed;          /* the device knows about auto_delete */
 };
 
 struct store {

@@ -130,6 +130,8 @@ P2P_CFGS = {   # name: (seed for the time() shim, p2p.cfg fields in file order)
     "cloudb":        (4, (20, 1, 0, 1, 0, 0, 1, 4, 8, 200, 7000)),      # smart cloud, HOUR_PASS
     "cloudc":        (9, (20, 1, 0, 0, 1, 0, 0, 4, 8, 200, 7000)),
     "push2":         (6, (20, 0, 0, 0, 2, 0, 1, 8, 8, 200, 6000)),
+    "evict3":        (11, (3, 0, 0, 0, 0, 0, 0, 4, 1, 150, 9000)),     # max_rsrc exceeded: node_del_resource + auto_delete (resource.c:49-66, flow.c:278-281)
+    "evict4":        (13, (4, 0, 0, 0, 1, 0, 1, 4, 4, 200, 12000)),
     "config2_seed1": (1, (20, 0, 0, 0, 0, 0, 0, 4, 1, 1000, 36000)),    # SURVEY section 8d, config 2 as specified (slow on the host core)
 }
 P2P_KEYS = ("max_rsrc", "new_resource_handler", "client_new_play", "smart_cloud", "new_connection_handler", "use_client", "metric",
