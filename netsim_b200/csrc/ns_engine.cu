@@ -295,6 +295,10 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 		const char *env = getenv("NS_FEATURES_OFF");
 		if (env) off |= (unsigned)strtoul(env, nullptr, 0);
 		S.features = (int)(NS_FEAT_ALL & ~off);
+		const char *e1 = getenv("NS_E1_MAX");
+		S.e1_max = e1 ? atoi(e1) : 8;
+		const char *hm = getenv("NS_HUB_MIN_DEG");
+		S.hub_min_deg = hm ? atoi(hm) : 160;
 	}
 	S.rec_cap = o.want_records ? (o.record_cap ? o.record_cap : std::max<u64>(64u << 20, 64ull*N+4096ull*F)) : 0;
 	S.tr_cap = o.want_trace ? (o.trace_cap ? o.trace_cap : (1u << 20)) : 0;

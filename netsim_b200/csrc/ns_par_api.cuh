@@ -47,7 +47,7 @@ struct ParScratch {
 		int n_hub, hub_work;                       // groups handed to whole CTAs (hub_chain_cta); stored from the END of `deferred`
 		int piece, last, pos, li, l_lo, l_hi;      // the current piece of the batch (par_plan_piece)
 		int small_streak;                          // consecutive small batches (sparse phase detection)
-		u64 dbg_key;
+		u64 dbg_key, dbg_key2, dbg_hub, dbg_hub_end, dbg_hub_sum;            // profiling builds: slowest chain / table-driven group / hub CTA of the segment
 		u64 tot_ins; unsigned tot_rec, tot_tr;
 		u64 lc[LC_N];
 	} *ctl;

@@ -106,6 +106,9 @@ struct Sim {
 	uint8_t *rec; ns_trace_row32 *tr;
 	// host core only (k_exec_ops / k_run_seq in host-callback mode): resource->auto_delete (data.h:34), null otherwise
 	uint8_t *s_autodel;
+	// batch engine: groups with more events than this skip the one-thread-per-group pass and get a warp (NS_E1_MAX, default 32)
+	int e1_max;
+	int hub_min_deg;              // sender groups with at least this many flows run their chain on a whole CTA (NS_HUB_MIN_DEG, default HUB_MIN_DEG)
 };
 
 // Replica ensembles: a replica whose bounded record buffer fills up folds it on the spot — the analyzer reductions take

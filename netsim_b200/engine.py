@@ -237,7 +237,9 @@ class Engine:
         out = {n: a[i] / 1e6 for i, n in enumerate(ms)}
         # profiling aid of the warp pass: the slowest (node,dir) group seen in one segment
         out.update({"slowest_group_ms": a[10] / 1e6, "slowest_group_degree": int(a[11]), "slowest_group_events": int(a[12]),
-                    "sum_slowest_ms": a[13] / 1e6, "deferred_groups": int(a[14])})
+                    "sum_slowest_ms": a[13] / 1e6, "deferred_groups": int(a[14]),
+                    "sum_slowest_table_ms": a[9] / 1e6, "sum_slowest_hub_ms": a[15] / 1e6,
+                    "hub_jobs": int(a[11]), "sum_last_hub_end_ms": a[12] / 1e6, "hub_cta_total_ms": a[6] / 1e6})
         return out
 
     def pick_live(self, mode: int, metric: int, off, cand_node, cand_tz, client_tz, k=None, usable=None):

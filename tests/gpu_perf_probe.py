@@ -117,7 +117,7 @@ if __name__ == "__main__":
             e.run(i * 2000000)
             w = time.time() - t0
             ph = e.phase_ms()
-            print(f"window {i}: device {e.device_ms:.1f} ms", {k: (round(ph[k] - last[k], 1) if k.endswith('_ms') or k in ('argmin', 'extract', 'group', 'solve_warp', 'solve_thread', 'commit', 'kernel') else ph[k]) for k in ph if k not in ('sequential', 'tail')}, flush=True)
+            print(f"window {i}: device {e.device_ms:.1f} ms", {k: (round(ph[k] - last[k], 1) if k.endswith('_ms') or k in ('argmin', 'extract', 'group', 'solve_warp', 'solve_thread', 'commit', 'kernel') else ph[k]) for k in ph if k not in ('sequential', 'tail', 'slowest_group_ms', 'slowest_group_degree', 'slowest_group_events')}, flush=True)
             last = ph
         e.close()
     elif which == "big":
