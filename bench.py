@@ -400,7 +400,7 @@ def main():
     traffic = None                       # dram bytes per launch from the committed ncu --set full capture
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tr.get("peers") == args.peers and tr.get("events_per_step") == eps:
+        if args.workload == "swarm100k" and tr.get("peers") == args.peers and tr.get("events_per_step") == eps:   # (the capture is of this workload's kernel)
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass

@@ -125,20 +125,25 @@ int  ns_dev_node_state(ns_dev *d, double *out4, size_t max_nodes, size_t *n);
  * ns_dev_run_host: run until such an event, the end of the queue or sim_end; for FLOW_DONE the flow is
  *   still alive when the host sees it (flow_done_cleaner runs on the next call), like HNDR_USER
  *   between HNDR_DEFAULT and HNDR_CLEANER (data.h:126-130).
- * ns_dev_exec: what a handler may do to the core — NS_OP_CREATE (sim_establish_flow; on return .a is the
+ * ns_dev_exec: what a handler may do to the core — NS_OP_CREATE / NS_OP_CREATE_RID (sim_establish_flow; on return .a is the
  *   flow's creation ordinal or -1), NS_OP_SCHED (event_add of a USER event; .a is a host token that
- *   comes back in ns_host_event.token), NS_OP_CLOSE (flow_close), NS_OP_END (sim_end). */
+ *   comes back in ns_host_event.token), NS_OP_CANCEL (event_remove), NS_OP_CLOSE (flow_close), NS_OP_END (sim_end), and what
+ *   the host core needs for modules that create things while the simulation runs (p2p.c): NS_OP_NEWNODE (sim_create_node),
+ *   NS_OP_NEWRES (sim_node_new_resource / sim_node_add_resource), NS_OP_DELRES / NS_OP_AUTODEL (node_del_resource,
+ *   resource->auto_delete), NS_OP_RANGE_SET (a module-side _range_update written back); include/ns_scenario.h has the operands. */
 struct ns_host_event { int32_t type, flow_ord, dir, token; double time, speed, now; int32_t stopped, status, exited, pad; };
 struct ns_flow_info { int32_t alive, src, dst; uint32_t flow_id, resource_id; int32_t pad; double ub, delay, speed[2]; int64_t drng_start; double drng_len; };
 struct ns_range_info { int64_t start, total_len; double len; int32_t producer_ord, pad; };
 struct ns_sc_op;
 struct ns_rand_state;
-/* the whole mutable state a module handler may read, for the host core's mirrors (netsim_b200/host/core.c): every live flow and
- * every range, as the device has them now.  done_t / drain_t = +inf when the event is not pending (event.h:76-88 is_active). */
+/* the whole mutable state a module handler may read, for the host core's mirrors (netsim_b200/host/core.c): node usage, every
+ * flow slot and every range slot below the high-water marks, written by one kernel straight into pinned host memory the library
+ * owns (valid until the next call).  Dead slots have slot == -1.  done_t / drain_t = +inf when the event is not pending
+ * (event.h:76-88 is_active).  nodes4[4*i..] = {bandwidth_usage[0], [1], total_bwupbound[0], [1]} of node i. */
+struct ns_view_hdr   { int32_t hi_flow, hi_range, n_nodes, pad; };
 struct ns_view_flow  { int32_t ord, slot, src, dst, srng, drng, drain_type, pad; uint32_t flow_id, pad2; double speed[2], done_t, drain_t; };
 struct ns_view_range { int32_t slot, res, producer_ord, next, prev, pad; int64_t start, total_len; double len, lenc, last_update; };
-/* fills at most max_flows / max_ranges entries (unordered) and reports how many there are */
-int  ns_dev_host_view(ns_dev *d, struct ns_view_flow *flows, int max_flows, int *n_flows, struct ns_view_range *ranges, int max_ranges, int *n_ranges);
+int  ns_dev_host_view(ns_dev *d, const struct ns_view_hdr **hdr, const double **nodes4, const struct ns_view_flow **flows, const struct ns_view_range **ranges);
 /* the simulation's random() stream (sim.c:117,132, flow.c:327, skiplist.h:34-40 share ONE generator with the module's own
  * random() calls): get applies the pending burns and returns the state, set installs a state (after the host drew from it) */
 int  ns_dev_rng_get(ns_dev *d, struct ns_rand_state *g);

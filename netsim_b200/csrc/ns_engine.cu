@@ -754,54 +754,55 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 }
 
 // ---- the host core's view of the mutable state (every live flow, every range) and the shared random() stream ----
-__global__ void k_host_view(const Sim *sp, ns_view_flow *fl, int max_f, ns_view_range *rg, int max_r, int *cnt){
+__global__ void k_host_view(const Sim *sp, ns_view_hdr *hdr, double *nodes4, ns_view_flow *fl, int max_f, ns_view_range *rg, int max_r, int max_n){
 	const Sim &S = *sp;
-	const int hf = S.st->hi_flow, hr = S.st->hi_range;
+	const int hf = min(S.st->hi_flow, max_f), hr = min(S.st->hi_range, max_r), nn = min(S.n_nodes, max_n);
 	const int gt = blockIdx.x*blockDim.x+threadIdx.x, gn = gridDim.x*blockDim.x;
+	if (gt == 0) { hdr->hi_flow = S.st->hi_flow; hdr->hi_range = S.st->hi_range; hdr->n_nodes = S.n_nodes; hdr->pad = 0; }
+	for (int n = gt; n < nn; n += gn) { nodes4[4*n] = S.n_usage[0][n]; nodes4[4*n+1] = S.n_usage[1][n]; nodes4[4*n+2] = S.n_total[0][n]; nodes4[4*n+3] = S.n_total[1][n]; }
 	for (int f = gt; f < hf; f += gn) {
-		if (!S.f_alive[f]) continue;
-		const int k = atomicAdd(&cnt[0], 1);
-		if (k >= max_f) continue;
 		ns_view_flow v;
-		v.ord = S.f_ord[f]; v.slot = f; v.src = S.f_peer[0][f]; v.dst = S.f_peer[1][f]; v.srng = S.f_srng[f]; v.drng = S.f_drng[f];
-		v.drain_type = S.f_drain_type[f]; v.pad = 0; v.flow_id = S.f_id[f]; v.pad2 = 0;
-		v.speed[0] = S.f_speed[0][f]; v.speed[1] = S.f_speed[1][f]; v.done_t = S.l_time[2*f]; v.drain_t = S.l_time[2*f+1];
-		fl[k] = v;
+		memset(&v, 0, sizeof v);
+		v.slot = -1;
+		if (S.f_alive[f]) {
+			v.ord = S.f_ord[f]; v.slot = f; v.src = S.f_peer[0][f]; v.dst = S.f_peer[1][f]; v.srng = S.f_srng[f]; v.drng = S.f_drng[f];
+			v.drain_type = S.f_drain_type[f]; v.flow_id = S.f_id[f];
+			v.speed[0] = S.f_speed[0][f]; v.speed[1] = S.f_speed[1][f]; v.done_t = S.l_time[2*f]; v.drain_t = S.l_time[2*f+1];
+		}
+		fl[f] = v;
 	}
 	for (int r = gt; r < hr; r += gn) {
-		if (S.r_res[r] < 0) continue;                                    // a free slot (range_merge_with_next)
-		const int k = atomicAdd(&cnt[1], 1);
-		if (k >= max_r) continue;
 		ns_view_range v;
-		v.slot = r; v.res = S.r_res[r]; v.producer_ord = S.r_prod[r] >= 0 ? S.f_ord[S.r_prod[r]] : -1; v.next = S.r_next[r]; v.prev = S.r_prev[r]; v.pad = 0;
-		v.start = S.r_start[r]; v.total_len = S.r_total[r]; v.len = S.r_len[r]; v.lenc = S.r_lenc[r]; v.last_update = S.r_last[r];
-		rg[k] = v;
+		memset(&v, 0, sizeof v);
+		v.slot = -1;
+		if (S.r_res[r] >= 0) {                                           // (-1: a free slot, range_merge_with_next / res_delete)
+			v.slot = r; v.res = S.r_res[r]; v.producer_ord = S.r_prod[r] >= 0 ? S.f_ord[S.r_prod[r]] : -1; v.next = S.r_next[r]; v.prev = S.r_prev[r];
+			v.start = S.r_start[r]; v.total_len = S.r_total[r]; v.len = S.r_len[r]; v.lenc = S.r_lenc[r]; v.last_update = S.r_last[r];
+		}
+		rg[r] = v;
 	}
 }
-extern "C" int ns_dev_host_view(ns_dev *d, ns_view_flow *flows, int max_flows, int *n_flows, ns_view_range *ranges, int max_ranges, int *n_ranges){
-	if (!d || !flows || !ranges || !n_flows || !n_ranges || max_flows < 0 || max_ranges < 0) return NS_E_ARG;
+extern "C" int ns_dev_host_view(ns_dev *d, const ns_view_hdr **hdr, const double **nodes4, const ns_view_flow **flows, const ns_view_range **ranges){
+	if (!d || !hdr || !nodes4 || !flows || !ranges) return NS_E_ARG;
 	CK(cudaSetDevice(d->device));
-	// called once per event in host-callback mode: the device buffers stay with the handle
-	const size_t need = 16+sizeof(ns_view_flow)*(size_t)std::max(1, max_flows)+sizeof(ns_view_range)*(size_t)std::max(1, max_ranges);
-	if (need > d->view_cap) {
-		if (d->view_buf) cudaFree(d->view_buf);
-		d->view_buf = nullptr; d->view_cap = 0;
-		CK(cudaMalloc(&d->view_buf, need));
-		d->view_cap = need;
+	// called once per event in host-callback mode: one pinned, device-mapped buffer for the life of the handle, sized for the
+	// tables' capacities; the kernel writes it over PCIe, the host reads it after one stream synchronisation
+	const size_t o_nodes = 64, o_flows = o_nodes+sizeof(double)*4*(size_t)d->h.cap_nodes;
+	const size_t o_ranges = o_flows+sizeof(ns_view_flow)*(size_t)d->h.S.cap_flows, total = o_ranges+sizeof(ns_view_range)*(size_t)d->h.S.cap_ranges;
+	if (!d->view_buf) {
+		CK(cudaHostAlloc(&d->view_buf, total, cudaHostAllocMapped));
+		d->view_cap = total;
 	}
-	int *dc = (int *)d->view_buf;
-	ns_view_flow *df = (ns_view_flow *)((char *)d->view_buf+16);
-	ns_view_range *dr = (ns_view_range *)((char *)df+sizeof(ns_view_flow)*(size_t)std::max(1, max_flows));
-	CK(cudaMemsetAsync(dc, 0, 8, d->stream));
-	k_host_view<<<64, 256, 0, d->stream>>>(d->d_sim, df, max_flows, dr, max_ranges, dc); d->launches++;
-	int hc[2];
-	CK(cudaMemcpyAsync(hc, dc, 8, cudaMemcpyDeviceToHost, d->stream));
+	char *base = (char *)d->view_buf;
+	void *dbase = nullptr;
+	CK(cudaHostGetDevicePointer(&dbase, d->view_buf, 0));
+	char *db = (char *)dbase;
+	k_host_view<<<64, 256, 0, d->stream>>>(d->d_sim, (ns_view_hdr *)db, (double *)(db+o_nodes), (ns_view_flow *)(db+o_flows), d->h.S.cap_flows,
+	                                        (ns_view_range *)(db+o_ranges), d->h.S.cap_ranges, d->h.cap_nodes);
+	d->launches++;
+	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(d->stream));
-	*n_flows = hc[0]; *n_ranges = hc[1];
-	const int cf = std::min(hc[0], max_flows), cr = std::min(hc[1], max_ranges);
-	if (cf) CK(cudaMemcpyAsync(flows, df, sizeof(ns_view_flow)*(size_t)cf, cudaMemcpyDeviceToHost, d->stream));
-	if (cr) CK(cudaMemcpyAsync(ranges, dr, sizeof(ns_view_range)*(size_t)cr, cudaMemcpyDeviceToHost, d->stream));
-	CK(cudaStreamSynchronize(d->stream));
+	*hdr = (const ns_view_hdr *)base; *nodes4 = (const double *)(base+o_nodes); *flows = (const ns_view_flow *)(base+o_flows); *ranges = (const ns_view_range *)(base+o_ranges);
 	return 0;
 }
 extern "C" int ns_dev_rng_get(ns_dev *d, ns_rand_state *g){
@@ -878,7 +879,7 @@ extern "C" void ns_dev_destroy(ns_dev *d){
 	if (!d) return;
 	cudaSetDevice(d->device);
 	free_sim(d->h);
-	if (d->view_buf) cudaFree(d->view_buf);
+	if (d->view_buf) cudaFreeHost(d->view_buf);
 	if (d->d_sim) cudaFree(d->d_sim);
 	if (d->d_scr) cudaFree(d->d_scr);
 	if (d->d_hash) cudaFree(d->d_hash);

@@ -81,6 +81,7 @@ def lib():
         L.ns_dev_flow_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_node_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ns_dev_phase_ns.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ns_dev_host_view.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.ns_dev_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ns_ens_check.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ns_dev_launches.restype = C.c_uint64
@@ -213,6 +214,24 @@ class Engine:
         if rc:
             raise NsError(rc, "ns_dev_flow_state")
         return out[:n.value]
+
+    VIEW_FLOW = np.dtype([("ord", "<i4"), ("slot", "<i4"), ("src", "<i4"), ("dst", "<i4"), ("srng", "<i4"), ("drng", "<i4"), ("drain_type", "<i4"), ("pad", "<i4"),
+                          ("flow_id", "<u4"), ("pad2", "<u4"), ("speed", "<f8", 2), ("done_t", "<f8"), ("drain_t", "<f8")])
+    VIEW_RANGE = np.dtype([("slot", "<i4"), ("res", "<i4"), ("producer_ord", "<i4"), ("next", "<i4"), ("prev", "<i4"), ("pad", "<i4"),
+                           ("start", "<i8"), ("total_len", "<i8"), ("len", "<f8"), ("lenc", "<f8"), ("last_update", "<f8")])
+
+    def host_view(self) -> dict:
+        """ns_dev_host_view: what the host core's mirrors are refreshed from (live flows, live ranges, node usage)"""
+        hdr, nd, fl, rg = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = self.L.ns_dev_host_view(self.h, C.byref(hdr), C.byref(nd), C.byref(fl), C.byref(rg))
+        if rc:
+            raise NsError(rc, "ns_dev_host_view")
+        h = np.ctypeslib.as_array((C.c_int32 * 4).from_address(hdr.value)).copy()
+        hi_flow, hi_range, n_nodes = int(h[0]), int(h[1]), int(h[2])
+        flows = np.frombuffer((C.c_char * (self.VIEW_FLOW.itemsize * hi_flow)).from_address(fl.value), dtype=self.VIEW_FLOW).copy() if hi_flow else np.zeros(0, self.VIEW_FLOW)
+        ranges = np.frombuffer((C.c_char * (self.VIEW_RANGE.itemsize * hi_range)).from_address(rg.value), dtype=self.VIEW_RANGE).copy() if hi_range else np.zeros(0, self.VIEW_RANGE)
+        nodes = np.frombuffer((C.c_char * (32 * n_nodes)).from_address(nd.value), dtype="<f8").reshape(n_nodes, 4).copy() if n_nodes else np.zeros((0, 4))
+        return {"flows": flows[flows["slot"] >= 0], "ranges": ranges[ranges["slot"] >= 0], "nodes": nodes}
 
     def node_state(self, n_nodes: int) -> np.ndarray:
         out = np.zeros((max(1, n_nodes), 4), dtype="<f8")

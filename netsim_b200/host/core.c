@@ -60,7 +60,6 @@ struct ns_host_core {
 	char *record_path; int want_records;
 	uint8_t *rec; size_t rec_len, rec_cap;                 /* record stream pulled from the device so far (+ module records) */
 	size_t dev_off;                                        /* device stream offset already pulled */
-	struct ns_view_flow *vf; struct ns_view_range *vr; int vf_cap, vr_cap;
 	unsigned epoch;
 	struct sim_state *s;
 	int device;
@@ -224,29 +223,17 @@ static struct range *range_mirror_new(struct ns_host_core *c, struct resource *r
 static void refresh(struct ns_host_core *c){
 	if (!c->dev) return;
 	struct sim_state *s = c->s;
-	{
-		static double *st; static int st_cap;
-		if (st_cap < c->n_nodes) { st_cap = c->n_nodes*2; st = realloc(st, (size_t)st_cap*32); }
-		size_t k = 0;
-		if (!ns_dev_node_state(c->dev, st, (size_t)c->nodes_pushed, &k))
-			for (size_t i = 0; i < k; i++) {
-				c->nodes[i]->bandwidth_usage[0] = st[4*i]; c->nodes[i]->bandwidth_usage[1] = st[4*i+1];
-				c->nodes[i]->total_bwupbound[0] = st[4*i+2]; c->nodes[i]->total_bwupbound[1] = st[4*i+3];
-			}
-	}
-	int nf = 0, nr = 0;
-	for (;;) {
-		if (!c->vf_cap) { c->vf_cap = 256; c->vr_cap = 512; c->vf = malloc(sizeof *c->vf*(size_t)c->vf_cap); c->vr = malloc(sizeof *c->vr*(size_t)c->vr_cap); }
-		int rc = ns_dev_host_view(c->dev, c->vf, c->vf_cap, &nf, c->vr, c->vr_cap, &nr);
-		if (rc) die(rc, "ns_dev_host_view");
-		if (nf <= c->vf_cap && nr <= c->vr_cap) break;
-		while (c->vf_cap < nf) c->vf_cap *= 2;
-		while (c->vr_cap < nr) c->vr_cap *= 2;
-		c->vf = realloc(c->vf, sizeof *c->vf*(size_t)c->vf_cap); c->vr = realloc(c->vr, sizeof *c->vr*(size_t)c->vr_cap);
+	const struct ns_view_hdr *vh; const double *nd; const struct ns_view_flow *vf; const struct ns_view_range *vr;
+	int rc = ns_dev_host_view(c->dev, &vh, &nd, &vf, &vr);
+	if (rc) die(rc, "ns_dev_host_view");
+	for (int i = 0; i < vh->n_nodes && i < c->n_nodes; i++) {
+		c->nodes[i]->bandwidth_usage[0] = nd[4*i]; c->nodes[i]->bandwidth_usage[1] = nd[4*i+1];
+		c->nodes[i]->total_bwupbound[0] = nd[4*i+2]; c->nodes[i]->total_bwupbound[1] = nd[4*i+3];
 	}
 	const unsigned ep = ++c->epoch;
-	for (int i = 0; i < nr; i++) {
-		const struct ns_view_range *v = &c->vr[i];
+	for (int i = 0; i < vh->hi_range; i++) {
+		const struct ns_view_range *v = &vr[i];
+		if (v->slot < 0) continue;
 		struct resource *r = v->res < c->cap_res ? c->res_by_slot[v->res] : NULL;
 		if (!r) continue;                                   /* a resource the host never saw cannot exist: every resource is created here */
 		struct range *g = v->slot < c->cap_rng ? c->rng_by_slot[v->slot] : NULL;
@@ -264,8 +251,9 @@ static void refresh(struct ns_host_core *c){
 		if (g->ranges.next) skip_list_delete(&g->ranges);
 		c->rng_by_slot[k] = NULL;
 	}
-	for (int i = 0; i < nf; i++) {
-		const struct ns_view_flow *v = &c->vf[i];
+	for (int i = 0; i < vh->hi_flow; i++) {
+		const struct ns_view_flow *v = &vf[i];
+		if (v->slot < 0) continue;
 		struct flow *f = (v->ord >= 0 && v->ord < c->n_flows) ? c->flows[v->ord] : NULL;
 		if (!f || f->closed) continue;
 		f->seen = ep;

@@ -431,3 +431,28 @@ def test_pick_small_tables_one_request_per_thread(built):
             continue
         j = int(np.argmin(v[lo:hi]))
         assert oc2[i] == 1 and on2[lo] == nd[lo + j] and ov2[lo] == v[lo + j]
+
+
+@pytest.mark.gpu
+def test_host_view_matches_the_table_read_backs(built):
+    """ns_dev_host_view (what the host core's mirrors are refreshed from, one kernel into pinned host memory) against the oracle-checked
+    read-backs: live flows with their speeds by creation ordinal, node usage / total_bwupbound, one destination range per live flow."""
+    sc = S.swarm(300, 3, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b, trace=False)
+    assert o.run(20000) == 0
+    e = E.Engine(b, mode=E.MODE_SEQ, records=True)
+    assert e.run(20000) == 0
+    v = e.host_view()
+    fs = o.flow_state(sc.n_creates())                       # per ordinal {alive, speed0, speed1, drng len}
+    alive = np.nonzero(fs[:, 0] != 0)[0]
+    fl = v["flows"][np.argsort(v["flows"]["ord"])]
+    assert fl["ord"].tolist() == alive.tolist()
+    assert fl["speed"].tobytes() == np.ascontiguousarray(fs[alive, 1:3]).tobytes()
+    assert v["nodes"].tobytes() == o.node_state(sc.n_nodes).tobytes()
+    rg = {int(r["slot"]): r for r in v["ranges"]}
+    for f in fl:
+        r = rg[int(f["drng"])]
+        assert int(r["producer_ord"]) == int(f["ord"]) and float(r["len"]) == float(fs[int(f["ord"]), 3])
+    e.close()
+    o.close()
