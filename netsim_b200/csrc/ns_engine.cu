@@ -712,10 +712,7 @@ extern "C" int ns_dev_set_host_mask(ns_dev *d, uint32_t mask){
 extern "C" int ns_dev_run_host(ns_dev *d, ns_host_event *ev){
 	if (!d || !ev) return NS_E_ARG;
 	CK(cudaSetDevice(d->device));
-	int zero = 0; uint64_t nomax = 0;
-	CK(cudaMemcpyAsync(&d->h.S.st->host_stop, &zero, 4, cudaMemcpyHostToDevice, d->stream));
-	CK(cudaMemcpyAsync(&d->h.S.st->max_events, &nomax, 8, cudaMemcpyHostToDevice, d->stream));
-	int rc = seq_launch_run(d->d_sim, d->d_scr, 1, d->stream);       // callbacks serialise the run anyway
+	int rc = seq_launch_run(d->d_sim, d->d_scr, 1, d->stream, -1);   // callbacks serialise the run anyway; -1: the kernel clears host_stop / max_events itself
 	if (rc) return rc;
 	d->launches++;
 	SimState st; rc = read_state(d, &st); if (rc) return rc;
@@ -725,14 +722,14 @@ extern "C" int ns_dev_run_host(ns_dev *d, ns_host_event *ev){
 	return st.status;
 }
 extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
-	if (!d || !ops || n < 0 || n > d->h.S.host_ops_cap) return NS_E_ARG;
+	if (!d || !ops || n < 0 || n >= d->h.S.host_ops_cap) return NS_E_ARG;   // (one slot carries the status back)
 	if (n == 0) return 0;
 	int new_nodes = 0;
 	for (int i = 0; i < n; i++) {                                        // the device indexes its tables with these
 		const ns_sc_op &op = ops[i];
 		if (op.kind == NS_OP_CREATE) { if (op.a < 0 || op.a >= d->h.S.n_nodes || op.b < 0 || op.b >= d->h.S.n_nodes || op.c < 0 || op.c >= d->h.S.n_rids) return NS_E_ARG; }
 		else if (op.kind == NS_OP_CLOSE) { if (op.a < 0) return NS_E_ARG; }
-		else if (op.kind == NS_OP_CANCEL) { if (op.a < 0 || op.a >= d->h.S.cap_users) return NS_E_ARG; }
+		else if (op.kind == NS_OP_CANCEL) { if (op.a >= d->h.S.cap_users || (op.a < 0 && (-op.a-1 >= i || ops[-op.a-1].kind != NS_OP_SCHED))) return NS_E_ARG; }
 		else if (op.kind == NS_OP_NEWNODE) { if (op.a != d->h.S.n_nodes+new_nodes || op.a >= d->h.cap_nodes) return op.a >= d->h.cap_nodes ? NS_E_TABLE_FULL : NS_E_ARG; new_nodes++; }
 		else if (op.kind == NS_OP_NEWRES) { if (op.a < 0 || op.a >= d->h.S.n_nodes+new_nodes || op.start < 0) return NS_E_ARG; }
 		else if (op.kind == NS_OP_CREATE_RID) { if (op.a < 0 || op.a >= d->h.S.n_nodes+new_nodes || op.b < 0 || op.b >= d->h.S.n_nodes+new_nodes) return NS_E_ARG; }
@@ -744,13 +741,15 @@ extern "C" int ns_dev_exec(ns_dev *d, ns_sc_op *ops, int n){
 	CK(cudaMemcpyAsync(d->h.S.host_ops, ops, (size_t)n*sizeof *ops, cudaMemcpyHostToDevice, d->stream));
 	{ int rc = seq_launch_exec_ops(d->d_sim, n, d->stream); if (rc) return rc; }
 	d->launches++;
-	CK(cudaMemcpyAsync(ops, d->h.S.host_ops, (size_t)n*sizeof *ops, cudaMemcpyDeviceToHost, d->stream));
+	std::vector<ns_sc_op> back((size_t)n+1);
+	CK(cudaMemcpyAsync(back.data(), d->h.S.host_ops, ((size_t)n+1)*sizeof *ops, cudaMemcpyDeviceToHost, d->stream));
 	if (new_nodes) {                                                     // the node count is part of the device's Sim
 		d->h.S.n_nodes += new_nodes;
 		CK(cudaMemcpyAsync(&d->d_sim->n_nodes, &d->h.S.n_nodes, sizeof(int), cudaMemcpyHostToDevice, d->stream));
 	}
 	CK(cudaStreamSynchronize(d->stream));
-	return ns_dev_status(d);
+	memcpy(ops, back.data(), (size_t)n*sizeof *ops);
+	return back[n].kind;                                                 // the simulation's status after the ops (host_ops_status)
 }
 
 // ---- the host core's view of the mutable state (every live flow, every range) and the shared random() stream ----

@@ -1263,7 +1263,7 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 			WSYNC();
 			break; }
 		case NS_OP_CANCEL: {                                           // event_remove of a module-owned event: the slot is free again
-			const int u = op.a;
+			const int u = op.a >= 0 ? op.a : S.host_ops[-op.a-1].b;   // (a < 0: the slot an NS_OP_SCHED earlier in this batch got)
 			if (S.l_time[2*S.cap_flows+u] != NS_INF && S.u_group[u] < 0) {
 				WSYNC();
 				L0 { S.l_time[2*S.cap_flows+u] = NS_INF; S.u_next_free[u] = c.st->free_user; c.st->free_user = u; }
@@ -1317,6 +1317,11 @@ __device__ __noinline__ void run_host_ops(Ctx &c, int n){
 			break; }
 		}
 	}
+}
+// the status travels back with the ops (slot n of the batch), so the host needs no second read
+__device__ __forceinline__ void host_ops_status(Ctx &c, int n){
+	L0 { if (n < c.S->host_ops_cap) c.S->host_ops[n].kind = c.st->status; }
+	WSYNC();
 }
 
 // ---------------------------------------------------------------- register-resident event chains

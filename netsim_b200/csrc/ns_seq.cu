@@ -24,12 +24,18 @@ __global__ void __launch_bounds__(32) k_exec_ops(const Sim *sp, int n_ops){
 	run_host_ops(c, n_ops);
 	L0 c.st->cnt[NS_CNT_SEQ] = c.tail;
 	ctx_flush(c);
+	host_ops_status(c, n_ops);
 }
 
 // one warp per simulation, strictly sequential event handling
 __global__ void __launch_bounds__(32) k_run_seq(const Sim *sims, const SeqScratch *scr, int n, int ens_phase, EnsAcc *acc, AnaStream *ana){
 	int s = blockIdx.x;
 	if (s >= n) return;
+	if (ens_phase < 0) {                                                 // host-callback mode (ns_dev_run_host): a fresh run to the next stop
+		if (threadIdx.x == 0) { sims[s].st->host_stop = 0; sims[s].st->max_events = 0; }
+		__syncwarp();
+		ens_phase = 0;
+	}
 	__shared__ WideSmem W;
 	__shared__ FoldSmem Fs;
 	EnsFold F;

@@ -46,6 +46,7 @@
 #include "../../include/netsim_b200.h"
 
 const double eps = 1e-4;            /* sim.c:11 */
+#define NS_QMAX 192
 
 struct ns_host_core {
 	ns_dev *dev;
@@ -61,6 +62,9 @@ struct ns_host_core {
 	uint8_t *rec; size_t rec_len, rec_cap;                 /* record stream pulled from the device so far (+ module records) */
 	size_t dev_off;                                        /* device stream offset already pulled */
 	unsigned epoch;
+	/* operations that only touch the event queue or a range's progress state (event_add / event_remove of module-owned events,
+	 * range write-backs) wait here and travel in ONE ns_dev_exec, in call order, before anything else talks to the device */
+	struct ns_sc_op q[NS_QMAX]; struct event *q_ev[NS_QMAX]; int nq;
 	struct sim_state *s;
 	int device;
 };
@@ -82,8 +86,10 @@ static void die(int rc, const char *what){ log_err("device core: %s: %s\n", what
 	(arr) = realloc((arr), (size_t)c_*sizeof *(arr)); memset((arr)+(cap), 0, (size_t)(c_-(cap))*sizeof *(arr)); (cap) = c_; } } while (0)
 
 /* ---------------------------------------------------------------- the shared random() stream */
+static void q_flush(struct ns_host_core *c);
 static uint32_t core_random(struct ns_host_core *c){
 	if (!c->dev) return ns_rand_next_host(&c->rng);
+	q_flush(c);                                             /* a queued event_add burns its draw first */
 	struct ns_rand_state g;
 	int rc = ns_dev_rng_get(c->dev, &g);
 	if (rc) die(rc, "random");
@@ -115,10 +121,26 @@ struct sim_state *ns_host_state_new(int device){
 
 /* ---------------------------------------------------------------- device calls */
 static void dev_exec(struct ns_host_core *c, struct ns_sc_op *ops, int n, const char *what){
+	if (ops != c->q) q_flush(c);
 	int rc = ns_dev_exec(c->dev, ops, n);
 	if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time\n"); abort(); }
 	if (rc == NS_E_NAN_TIME) { log_err("Add event at nan\n"); abort(); }
 	if (rc) die(rc, what);
+}
+static void q_flush(struct ns_host_core *c){
+	if (!c->nq || !c->dev) return;
+	const int n = c->nq;
+	c->nq = 0;
+	dev_exec(c, c->q, n, "event_add / event_remove");
+	for (int i = 0; i < n; i++)
+		if (c->q[i].kind == NS_OP_SCHED && c->q_ev[i] && c->q_ev[i]->q_idx == i) { c->q_ev[i]->dev_slot = c->q[i].b; c->q_ev[i]->q_idx = -1; }
+}
+static struct ns_sc_op *q_push(struct ns_host_core *c, struct event *e){
+	if (c->nq == NS_QMAX) q_flush(c);
+	struct ns_sc_op *op = &c->q[c->nq];
+	memset(op, 0, sizeof *op);
+	c->q_ev[c->nq++] = e;
+	return op;
 }
 /* nodes and resources the module has created since the last call, in creation order.  Pushed lazily: a module sets
  * maximum_bandwidth / bit_rate on the struct AFTER sim_create_node / sim_node_new_resource returned (p2p.c:144-170). */
@@ -222,6 +244,7 @@ static struct range *range_mirror_new(struct ns_host_core *c, struct resource *r
 /* every number a handler may read, as the device has it now */
 static void refresh(struct ns_host_core *c){
 	if (!c->dev) return;
+	q_flush(c);
 	struct sim_state *s = c->s;
 	const struct ns_view_hdr *vh; const double *nd; const struct ns_view_flow *vf; const struct ns_view_range *vr;
 	int rc = ns_dev_host_view(c->dev, &vh, &nd, &vf, &vr);
@@ -278,17 +301,13 @@ static void refresh(struct ns_host_core *c){
 /* a handler advanced a range itself (_range_update): the device takes the new state over */
 static void push_range_updates(struct ns_host_core *c){
 	if (!c->dev) return;
-	struct ns_sc_op ops[64]; int n = 0;
 	for (int k = 0; k < c->cap_rng; k++) {
 		struct range *g = c->rng_by_slot[k];
 		if (!g || (g->len == g->dev_len && g->lenc == g->dev_lenc && g->last_update == g->dev_last)) continue;
-		struct ns_sc_op *op = &ops[n++];
-		memset(op, 0, sizeof *op);
+		struct ns_sc_op *op = q_push(c, NULL);
 		op->kind = NS_OP_RANGE_SET; op->a = k; op->x = g->len; op->y = g->lenc; memcpy(&op->start, &g->last_update, 8);
 		g->dev_len = g->len; g->dev_lenc = g->lenc; g->dev_last = g->last_update;
-		if (n == 64) { dev_exec(c, ops, n, "range update"); n = 0; }
 	}
-	if (n) dev_exec(c, ops, n, "range update");
 }
 
 /* ---------------------------------------------------------------- the module API */
@@ -451,23 +470,29 @@ void event_add(struct event *e, struct sim_state *s){
 	if (isnan(e->time)) { log_err("Add event at nan\n"); abort(); }
 	materialize(c);
 	if (e->token < 0) { GROW(c->uev, c->n_uev, c->cap_uev); e->token = c->n_uev; c->uev[c->n_uev++] = e; }
-	struct ns_sc_op op;
-	memset(&op, 0, sizeof op);
-	op.kind = NS_OP_SCHED; op.a = e->token; op.c = 0; op.x = e->time;
-	dev_exec(c, &op, 1, "event_add");
+	struct ns_sc_op *op = q_push(c, e);
+	op->kind = NS_OP_SCHED; op->a = e->token; op->c = 0; op->x = e->time;
+	e->q_idx = c->nq-1;
 	e->active = true;
-	e->dev_slot = op.b;
+	e->dev_slot = -1;                                       /* known when the queue has been executed */
 }
 /* event_remove, event.h:13-18, of a module-owned event */
 void event_remove(struct event *e){
 	struct ns_host_core *c = the_core;
 	if (!e || !e->active) return;
 	e->active = false;
-	if (!c || !c->dev || e->dev_slot < 0) return;
-	struct ns_sc_op op;
-	memset(&op, 0, sizeof op);
-	op.kind = NS_OP_CANCEL; op.a = e->dev_slot;
-	dev_exec(c, &op, 1, "event_remove");
+	if (!c || !c->dev) return;
+	if (c->nq == NS_QMAX) q_flush(c);                       /* (room first: afterwards q_idx / dev_slot are final) */
+	struct ns_sc_op *op;
+	if (e->q_idx >= 0) {                                    /* its event_add is still in the queue: cancel the slot that one will get */
+		op = q_push(c, NULL);
+		op->kind = NS_OP_CANCEL; op->a = -(e->q_idx+1);
+		e->q_idx = -1;
+		return;
+	}
+	if (e->dev_slot < 0) return;
+	op = q_push(c, NULL);
+	op->kind = NS_OP_CANCEL; op->a = e->dev_slot;
 	e->dev_slot = -1;
 }
 
@@ -564,6 +589,7 @@ int ns_host_run(struct sim_state *s){
 	int rc = 0;
 	while (!s->exit) {
 		struct ns_host_event ev;
+		q_flush(c);
 		rc = ns_dev_run_host(c->dev, &ev);
 		if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time\n"); abort(); }
 		if (rc) { log_err("device core: %s\n", ns_strerror(rc)); break; }
@@ -583,7 +609,7 @@ int ns_host_run(struct sim_state *s){
 		struct spd_event se;
 		struct flow *f = (ev.flow_ord >= 0 && ev.flow_ord < c->n_flows) ? c->flows[ev.flow_ord] : NULL;
 		memset(&tmp, 0, sizeof tmp);
-		tmp.type = ev.type; tmp.time = ev.time; tmp.token = -1;
+		tmp.type = ev.type; tmp.time = ev.time; tmp.token = -1; tmp.dev_slot = -1; tmp.q_idx = -1;
 		bool need_free = false;
 		refresh(c);
 		switch (ev.type) {
@@ -610,9 +636,10 @@ int ns_host_run(struct sim_state *s){
 		struct event_handler *eh;
 		list_for_each_entry(eh, &s->handlers[ev.type], handlers) eh->f(e, s);
 		if (ev.type == FLOW_DONE && f) flow_unlink(c, f);   /* flow_done_cleaner (flow.c:403-406) runs on the device next */
-		if (need_free) { c->uev[ev.token] = NULL; free(e); }   /* main.c:65-66 */
 		flush_pending(c);
 		push_range_updates(c);
+		q_flush(c);                                         /* (nothing queued refers to the event freed next) */
+		if (need_free) { c->uev[ev.token] = NULL; free(e); }   /* main.c:65-66 */
 		if (s->exit) {
 			struct ns_sc_op op;
 			memset(&op, 0, sizeof op);

@@ -115,6 +115,7 @@ struct event {
 	/* host core */
 	int token;                    /* host-owned USER events: handle on the device */
 	int dev_slot;                 /* ... and the device slot of its pending instance (event_remove) */
+	int q_idx;                    /* ... or, while its event_add waits in the host core's queue, its position there */
 };
 
 #define SND 0
@@ -143,7 +144,7 @@ static inline struct store *store_new(void){ return talloc(1, struct store); }
 static inline struct event *event_new(double time, enum event_type t, void *d){
 	struct event *e = talloc(1, struct event);
 	e->time = time; e->type = t; e->data = d;
-	e->token = -1; e->dev_slot = -1;
+	e->token = -1; e->dev_slot = -1; e->q_idx = -1;
 	return e;
 }
 static inline void event_free(struct event *e){ free(e); }
