@@ -80,6 +80,12 @@ void ns_host_log(int level, const char *domain, const char *fmt, ...){
 	vfprintf(stderr, fmt, ap);
 	va_end(ap);
 }
+/* NS_HOST_PROF=1: where the wall time of a run goes (printed to stdout at the end) */
+#include <time.h>
+static double prof_t[8]; static unsigned long prof_n[8]; static int prof_on = -1;
+static inline double prof_now(void){ struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec+1e-9*ts.tv_nsec; }
+#define PROF_BEGIN double pt0_ = prof_on > 0 ? prof_now() : 0
+#define PROF_END(k) do { if (prof_on > 0) { prof_t[k] += prof_now()-pt0_; prof_n[k]++; } } while (0)
 static void die(int rc, const char *what){ log_err("device core: %s: %s\n", what, ns_strerror(rc)); exit(3); }
 
 #define GROW(arr, n, cap) do { if ((n) >= (cap)) { int c_ = (cap) ? (cap) : 16; while (c_ <= (n)) c_ *= 2; \
@@ -122,7 +128,9 @@ struct sim_state *ns_host_state_new(int device){
 /* ---------------------------------------------------------------- device calls */
 static void dev_exec(struct ns_host_core *c, struct ns_sc_op *ops, int n, const char *what){
 	if (ops != c->q) q_flush(c);
+	PROF_BEGIN;
 	int rc = ns_dev_exec(c->dev, ops, n);
+	PROF_END(2);
 	if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time\n"); abort(); }
 	if (rc == NS_E_NAN_TIME) { log_err("Add event at nan\n"); abort(); }
 	if (rc) die(rc, what);
@@ -247,8 +255,11 @@ static void refresh(struct ns_host_core *c){
 	q_flush(c);
 	struct sim_state *s = c->s;
 	const struct ns_view_hdr *vh; const double *nd; const struct ns_view_flow *vf; const struct ns_view_range *vr;
+	PROF_BEGIN;
 	int rc = ns_dev_host_view(c->dev, &vh, &nd, &vf, &vr);
+	PROF_END(1);
 	if (rc) die(rc, "ns_dev_host_view");
+	double pt1_ = prof_on > 0 ? prof_now() : 0;
 	for (int i = 0; i < vh->n_nodes && i < c->n_nodes; i++) {
 		c->nodes[i]->bandwidth_usage[0] = nd[4*i]; c->nodes[i]->bandwidth_usage[1] = nd[4*i+1];
 		c->nodes[i]->total_bwupbound[0] = nd[4*i+2]; c->nodes[i]->total_bwupbound[1] = nd[4*i+3];
@@ -297,6 +308,7 @@ static void refresh(struct ns_host_core *c){
 		struct flow *f = c->live[k];
 		if (f->seen != ep) flow_unlink(c, f);
 	}
+	if (prof_on > 0) { prof_t[3] += prof_now()-pt1_; prof_n[3]++; }
 }
 /* a handler advanced a range itself (_range_update): the device takes the new state over */
 static void push_range_updates(struct ns_host_core *c){
@@ -580,6 +592,7 @@ static void save_records(struct ns_host_core *c){
 /* ---------------------------------------------------------------- the event loop, main.c:50-67, with the default handlers (main.c:44-48) on the device */
 int ns_host_run(struct sim_state *s){
 	struct ns_host_core *c = core_of(s);
+	if (prof_on < 0) { const char *pe = getenv("NS_HOST_PROF"); prof_on = pe && *pe && *pe != '0'; }
 	materialize(c);
 	flush_pending(c);
 	push_range_updates(c);
@@ -590,7 +603,7 @@ int ns_host_run(struct sim_state *s){
 	while (!s->exit) {
 		struct ns_host_event ev;
 		q_flush(c);
-		rc = ns_dev_run_host(c->dev, &ev);
+		{ PROF_BEGIN; rc = ns_dev_run_host(c->dev, &ev); PROF_END(0); }
 		if (rc == NS_E_BACK_IN_TIME) { log_err("Add event back in time\n"); abort(); }
 		if (rc) { log_err("device core: %s\n", ns_strerror(rc)); break; }
 		if (!ev.stopped) break;                             /* queue empty */
@@ -634,10 +647,9 @@ int ns_host_run(struct sim_state *s){
 			tmp.data = f;
 		}
 		struct event_handler *eh;
-		list_for_each_entry(eh, &s->handlers[ev.type], handlers) eh->f(e, s);
+		{ PROF_BEGIN; list_for_each_entry(eh, &s->handlers[ev.type], handlers) eh->f(e, s); PROF_END(4); }
 		if (ev.type == FLOW_DONE && f) flow_unlink(c, f);   /* flow_done_cleaner (flow.c:403-406) runs on the device next */
-		flush_pending(c);
-		push_range_updates(c);
+		{ PROF_BEGIN; flush_pending(c); push_range_updates(c); PROF_END(5); }
 		q_flush(c);                                         /* (nothing queued refers to the event freed next) */
 		if (need_free) { c->uev[ev.token] = NULL; free(e); }   /* main.c:65-66 */
 		if (s->exit) {
@@ -648,6 +660,10 @@ int ns_host_run(struct sim_state *s){
 		}
 	}
 	save_records(c);
+	if (prof_on > 0) {
+		static const char *nm[] = { "ns_dev_run_host", "ns_dev_host_view", "ns_dev_exec", "mirror update", "module handlers (incl. their device calls)", "pending scans" };
+		for (int k = 0; k < 6; k++) printf("host core: %-44s %9.3f s  %9lu calls  %7.1f us/call\n", nm[k], prof_t[k], prof_n[k], prof_n[k] ? 1e6*prof_t[k]/prof_n[k] : 0.0);
+	}
 	return rc;
 }
 
