@@ -546,7 +546,10 @@ def ensemble_main(args, rank, local_rank, world):
         scs = [ens_script(args, base + i).to_bytes() for i in mine]
         t_gen = time.perf_counter() - t0
         t1 = time.perf_counter()
-        ens = E.Ensemble(scs, device=local_rank, records=True, ring_cap=1 << (17 if args.ens_kind == "p2p1k" else 20), record_cap=(2 if args.ens_kind == "p2p1k" else 8) << 20, mode=E.MODE_AUTO)
+        # per-replica capacities (overridable for experiments): the event ring and the record buffer are cyclic / folded in place
+        ring_log2 = int(os.environ.get("NS_ENS_RING_LOG2", 17 if args.ens_kind == "p2p1k" else 20))
+        rec_kb = int(os.environ.get("NS_ENS_REC_KB", (2 if args.ens_kind == "p2p1k" else 8) << 10))
+        ens = E.Ensemble(scs, device=local_rank, records=True, ring_cap=1 << ring_log2, record_cap=rec_kb << 10, mode=E.MODE_AUTO)
         if args.ens_kind == "p2p1k":
             ens.analysis_begin(3600.0)                       # analyzer reductions on the device, from the records while they are produced
         ens.run(0)
