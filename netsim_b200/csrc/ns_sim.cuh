@@ -168,7 +168,9 @@ __host__ __device__ inline void ns_poly_mulmod(const uint32_t *a, const uint32_t
 }
 
 __host__ __device__ inline void ns_rand_jump(int32_t *st, int32_t &f, int32_t &r, u64 n){
-	if (n < 96) { for (u64 i = 0; i < n; i++) ns_rand_step(st, f, r); return; }
+	// stepping costs ~10 instructions per draw, the polynomial jump ~13 000 whatever n is (measured: 12 % of all instructions of a
+	// p2p replica were jumps over a few hundred burned draws, profiles/README.md r2-p): jump only over long stretches
+	if (n < 1024) { for (u64 i = 0; i < n; i++) ns_rand_step(st, f, r); return; }
 	// chronological window s_0..s_30 (oldest first): the next draw overwrites the oldest word
 	// st[f] with st[f]+st[r], r = f+28 (mod 31), i.e. s_31 = s_0 + s_28.
 	uint32_t s[61];

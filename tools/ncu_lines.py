@@ -16,6 +16,7 @@ top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 45
 cur_file = None
 idx = {}
 agg = collections.Counter()
+inst = collections.Counter()
 stall = collections.defaultdict(collections.Counter)
 src = {}
 key = None
@@ -40,11 +41,26 @@ for r in rows:
     if key is None:
         continue
     agg[key] += num(r[idx['# Samples']])
+    for n in ('Instructions Executed', 'inst_executed'):
+        if n in idx:
+            inst[key] += num(r[idx[n]])
+            break
     for n in ('stall_barrier', 'stall_long_sb', 'stall_no_inst', 'stall_wait', 'stall_short_sb', 'stall_math', 'stall_lg', 'stall_branch_resolving', 'stall_mio', 'stall_membar'):
         if n in idx:
             stall[key][n] += num(r[idx[n]])
 tot = sum(agg.values())
-print('total samples', tot)
+print('columns:', sorted(idx))
+print('total samples', tot, 'total warp instructions executed', sum(inst.values()))
+if inst:
+    ti = sum(inst.values())
+    print('--- by executed warp instructions')
+    for key, s in inst.most_common(top_n):
+        print(f"{key[0]}:{key[1]:5d} {s:12d} {100 * s / ti:5.1f}%  {src[key][:110]}")
+    byfile = collections.Counter()
+    for key, s in inst.items():
+        byfile[key[0]] += s
+    print('--- by file', {k: f"{100 * v / ti:.1f}%" for k, v in byfile.most_common()})
+    print('--- by stall samples')
 for key, s in agg.most_common(top_n):
     st = stall[key]
     top = ', '.join(f"{k[6:]}:{v}" for k, v in st.most_common(3) if v)
