@@ -26,7 +26,7 @@ struct ParScratch {
 	ParStage *d_stage;
 	// per-timestamp
 	int *tile_cnt, *tile_off;     // per ring-window tile: matches, exclusive offset
-	unsigned *tile_mask; int *cta_tile;   // ... the match bits of a tile (32 words), per-CTA totals of the count scan
+	unsigned *tile_mask; int *cta_tile;   // ... the match bits of a tile (NS_TILE_ROWS words), per-CTA totals of the count scan
 	// grouping
 	int *grp_cnt, *grp_off, *grp_fill, *active, *grp_items, *b_grp;
 	int *deferred, *defer_pos;     // groups handed from the per-thread pass to the per-warp pass
@@ -72,7 +72,7 @@ template <typename A> static int par_alloc(ParScratch &p, const Sim &S, bool ena
 	PA(st.ev_nins, p.seg_cap); PA(st.ev_ovf, p.seg_cap); PA(st.ev_nrec, p.seg_cap); PA(st.ev_ntr, p.seg_cap); PA(st.ev_idpos, p.seg_cap);
 	PA(p.d_stage, 1);
 	PA(p.tile_cnt, S.n_ring_tiles+1); PA(p.tile_off, S.n_ring_tiles+1);
-	PA(p.tile_mask, (size_t)(S.n_ring_tiles+1)*32); PA(p.cta_tile, z.grid_max);
+	PA(p.tile_mask, (size_t)(S.n_ring_tiles+1)*NS_TILE_ROWS); PA(p.cta_tile, z.grid_max);
 	PA(p.grp_cnt, 2*S.n_nodes+1); PA(p.grp_off, 2*S.n_nodes+1); PA(p.grp_fill, 2*S.n_nodes+1);
 	PA(p.active, p.seg_cap); PA(p.grp_items, p.seg_cap); PA(p.b_grp, p.seg_cap);
 	PA(p.deferred, p.seg_cap); PA(p.defer_pos, 2*S.n_nodes+1); PA(p.defer_long, p.seg_cap/128+2);

@@ -481,8 +481,8 @@ __device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &
 	}
 }
 
-#define NS_SPARSE_MAX_HIT_TILES 4
-#define NS_ENS_MAX_HIT_TILES 64
+#define NS_SPARSE_MAX_HIT_TILES (4*1024/NS_TILE)
+#define NS_ENS_MAX_HIT_TILES (64*1024/NS_TILE)
 __device__ void seq_run(const Sim *Sp, const SeqScratch &sc, int lane, WideSmem *W, int ens_phase = 0, const EnsFold *fold = nullptr, FoldSmem *Fs = nullptr){
 	Ctx c;
 	ctx_load(c, Sp, lane);

@@ -20,8 +20,9 @@
 #include "../../include/ns_scenario.h"
 #include "../../include/netsim_b200.h"
 
-#define NS_TILE 1024
-#define NS_TILE_SHIFT 10
+#define NS_TILE 256              // entries per tile of the event stores (one minimum per tile): 8 rows of 32 lanes = one 8-deep batch of loads
+#define NS_TILE_SHIFT 8
+#define NS_TILE_ROWS (NS_TILE/32)
 #define NS_EPS 1e-4                       /* sim.c:11 */
 #define NS_INF (__longlong_as_double(0x7ff0000000000000LL))
 #define FULLMASK 0xffffffffu
