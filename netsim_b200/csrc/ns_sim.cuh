@@ -12,7 +12,7 @@
 //            equal timestamps (event.h:27-31) and an equal-time batch is an ordered compaction.
 //   L table  long-lived events: FLOW_DONE (slot 2f) / FLOW_DRAIN|THROTTLE (slot 2f+1) of each flow
 //            (flow->done, flow->drain, data.h:84) and USER events, with explicit seq.
-// Both event stores keep a per-1024-entry lower bound of their minimum time (q_tmin/l_tmin): the
+// Both event stores keep a per-tile (NS_TILE entries) lower bound of their minimum time (q_tmin/l_tmin): the
 // next-completion argmin reads only those, the batch extraction only the tiles that hit.
 #pragma once
 #include <stdint.h>
