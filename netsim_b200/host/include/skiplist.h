@@ -66,12 +66,14 @@ static inline void ns_skip_link_after(struct skip_list_head *n, struct skip_list
 /* smallest element >= key */
 static inline struct skip_list_head *skip_list_find_ge(struct skip_list_head *h, void *key, skip_list_cmp cmp){
 	struct skip_list_head *before[MAX_HEIGHT];
+	before[0] = h;
 	skip_list_previous(h, key, cmp, before);
 	return before[0]->next[0];
 }
 /* largest element <= key */
 static inline struct skip_list_head *skip_list_find_le(struct skip_list_head *h, void *key, skip_list_cmp cmp){
 	struct skip_list_head *before[MAX_HEIGHT];
+	before[0] = h;
 	skip_list_previous(h, key, cmp, before);
 	if (before[0]->next[0] && cmp(before[0]->next[0], key) == 0) return before[0]->next[0];
 	return before[0] == h ? NULL : before[0];

@@ -92,3 +92,15 @@ def test_host_core_containers():
         p = subprocess.run([exe], capture_output=True, text=True)
         assert p.returncode == 0, p.stdout
         assert "iter in order 1, left 500" in p.stdout and "skip sorted 1 n 200 ge 18 le 17" in p.stdout and "list 31 13 empty 0" in p.stdout
+
+
+def test_host_core_containers_randomized():
+    """CPU: 60 000 random operations each on the hash (adds / finds / deletes, deletion inside HASH_ITER, iteration == insertion order)
+    and on the skip list (inserts / deletes / find_ge / find_le, level-0 next / prev walks) against plain arrays."""
+    import subprocess, tempfile
+    inc = os.path.join(ROOT, "netsim_b200", "host", "include")
+    with tempfile.TemporaryDirectory(prefix="nsfuzz") as d:
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-O2", "-I" + inc, os.path.join(ROOT, "tests", "modules", "t_containers_fuzz.c"), "-o", exe], check=True)
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0 and "containers fuzz: ok" in p.stdout, p.stdout
