@@ -454,7 +454,7 @@ __device__ __noinline__ void seq_restore(Ctx &c, double m, int i, int nr, int j,
 
 // process batch entries [i,nr) x [j,nl) in sequence order, strictly sequentially; stops early on
 // status / sim_end / max_events / host stop and reports how far it got
-#define NS_WIDE_MIN_RUN 1
+#define NS_WIDE_MIN_RUN 1      // every run: one handler path for all speed events is what many one-warp simulations per GPU need (profiles/README.md r2-o, r2-q)
 __device__ __noinline__ void seq_process(Ctx &c, double m, int &i, int nr, int &j, int nl, const SeqScratch &sc, WideSmem *W){
 	const Sim &S = *c.S;
 #ifdef NS_NO_WIDE      // the grid engine's translation unit: its sparse phases go to k_run_seq anyway, and k_run_par's code layout is touchy (profiles/README.md r1-f)
