@@ -460,7 +460,7 @@ def ens_config(args, world):
                             f"metric) and runs the water-mark state machine of modules/client_behaviour.c ON THE DEVICE (node-state records included) until DONE_PLAY; "
                             f"~313k events in ~41k timestamps per replica (mean batch 7.6: the reference's real regime); replica i -> rank i mod N; the reference arm "
                             f"runs the reference's own client_behaviour.c through the replay module",
-                "replicas": args.replicas, "clients_per_replica": 1000, "engine": "one CTA per replica in dense phases, one warp per replica in sparse phases (k_run_ens / k_run_seq)",
+                "replicas": args.replicas, "clients_per_replica": 1000, "engine": "one warp per replica (k_run_seq; NS_ENS_MODE=auto adds the one-CTA-per-replica engine for dense phases, which these replicas do not have)",
                 "working_set": "per replica ~2 MB of tables; the ensemble's tables + event rings exceed the 126 MB L2; no explicit L2 flush"}
     return {"workload": f"BASELINE.json configs[4]: ensemble of {args.replicas} seeded replicas of a {args.ens_peers}-peer swarm script (20 seeders, ~3 flows "
                         f"per peer, file distribution to completion: every flow runs to FLOW_DONE and is closed), replica i -> rank i mod N; "
@@ -549,7 +549,9 @@ def ensemble_main(args, rank, local_rank, world):
         # per-replica capacities (overridable for experiments): the event ring and the record buffer are cyclic / folded in place
         ring_log2 = int(os.environ.get("NS_ENS_RING_LOG2", 17 if args.ens_kind == "p2p1k" else 20))
         rec_kb = int(os.environ.get("NS_ENS_REC_KB", (2 if args.ens_kind == "p2p1k" else 8) << 10))
-        ens = E.Ensemble(scs, device=local_rank, records=True, ring_cap=1 << ring_log2, record_cap=rec_kb << 10, mode=E.MODE_AUTO)
+        # config-2-shaped replicas never see a batch that is worth a CTA (mean 7.6 events per timestamp): the one-warp engine alone, no rounds
+        ens_mode = {"auto": E.MODE_AUTO, "seq": E.MODE_SEQ}[os.environ.get("NS_ENS_MODE", "seq" if args.ens_kind == "p2p1k" else "auto")]
+        ens = E.Ensemble(scs, device=local_rank, records=True, ring_cap=1 << ring_log2, record_cap=rec_kb << 10, mode=ens_mode)
         if args.ens_kind == "p2p1k":
             ens.analysis_begin(3600.0)                       # analyzer reductions on the device, from the records while they are produced
         ens.run(0)
