@@ -41,6 +41,7 @@
 #include "user.h"
 #include "record.h"
 #include "core.h"
+#include "recfile.h"
 
 #include "../../include/ns_scenario.h"
 #include "../../include/netsim_b200.h"
@@ -574,19 +575,8 @@ void open_record(const char *filename, int create, struct sim_state *s){
 static void save_records(struct ns_host_core *c){
 	if (!c->record_path) return;
 	pull_records(c);
-	size_t total = c->rec_len;
-	uint8_t *buf = malloc(total+4);
-	memcpy(buf+4, c->rec, total);
-	buf[0] = total >> 24; buf[1] = total >> 16; buf[2] = total >> 8; buf[3] = total;   /* record.c:111-115 */
-	size_t size = 1024*1024;                                /* record.c:133 initial size, doubled at :38-51 */
-	while (4+total+19 >= size) size <<= 1;
-	FILE *f = fopen(c->record_path, "wb");
-	if (f) {
-		fwrite(buf, 1, total+4, f);
-		if (ftruncate(fileno(f), (off_t)size)) { }
-		fclose(f);
-	}
-	free(buf);
+	int rc = ns_recfile_save(c->record_path, c->rec, c->rec_len, ns_recfile_split_from_env(), ns_recfile_flags_from_env(), NULL);   /* recfile.c */
+	if (rc < 0) log_err("Can't write record file %s (%d)\n", c->record_path, rc);
 }
 
 /* ---------------------------------------------------------------- the event loop, main.c:50-67, with the default handlers (main.c:44-48) on the device */
