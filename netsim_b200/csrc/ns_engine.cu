@@ -57,7 +57,7 @@ __global__ void k_node_ranges(const Sim *sp, int node, unsigned rid, RangeInfoDe
 }
 
 // order-sensitive, parallel digest of a byte stream: sum over little-endian 64-bit words w_j of
-// mix64(w_j + K*(j+1)), finalised with the length (see netsim_b200/digest.py for the host mirror).
+// mix64(w_j + K*(j+1)), finalised with the length (host mirror: stream_hash in netsim_b200/engine.py).
 __global__ void k_stream_hash(const uint8_t *p, u64 len, u64 *out){
 	u64 nw = (len+7)/8;
 	u64 acc = 0;
@@ -227,14 +227,14 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	if (H.magic != NS_SC_MAGIC || H.version != NS_SC_VERSION || H.n_groups < 1 || H.n_nodes < 0) return NS_E_BAD_SCENARIO;
 	if (H.n_resources < 0 || H.n_copies < 0 || H.n_ops < 0 || H.n_ondone < 0) return NS_E_BAD_SCENARIO;
 	size_t need = sizeof H+(size_t)H.n_nodes*16+(size_t)H.n_resources*sizeof(ns_sc_resource)+(size_t)H.n_copies*sizeof(ns_sc_copy)+
-		(size_t)(H.n_groups+1)*4+(size_t)H.n_ops*sizeof(ns_sc_op)+(size_t)H.n_ondone*sizeof(ns_sc_ondone);
+		((size_t)H.n_groups+1)*4+(size_t)H.n_ops*sizeof(ns_sc_op)+(size_t)H.n_ondone*sizeof(ns_sc_ondone);
 	if (len < need) return NS_E_BAD_SCENARIO;
 	const char *p = (const char *)scenario+sizeof H;
 	const double *max_up = (const double *)p; p += (size_t)H.n_nodes*8;
 	const double *max_down = (const double *)p; p += (size_t)H.n_nodes*8;
 	const ns_sc_resource *rs = (const ns_sc_resource *)p; p += (size_t)H.n_resources*sizeof *rs;
 	const ns_sc_copy *cp = (const ns_sc_copy *)p; p += (size_t)H.n_copies*sizeof *cp;
-	const int32_t *goff = (const int32_t *)p; p += (size_t)(H.n_groups+1)*4;
+	const int32_t *goff = (const int32_t *)p; p += ((size_t)H.n_groups+1)*4;
 	const ns_sc_op *ops = (const ns_sc_op *)p; p += (size_t)H.n_ops*sizeof *ops;
 	const ns_sc_ondone *od = (const ns_sc_ondone *)p; p += (size_t)H.n_ondone*sizeof *od;
 	const bool has_clients = (H.flags & NS_SC_F_CLIENTS) != 0;
@@ -671,8 +671,11 @@ extern "C" int ns_dev_pick_live(ns_dev *d, int mode, int metric, int n_req, cons
 		int32_t *out_val, int32_t *out_node, int32_t *out_cnt, float *device_ms){
 	if (!d || n_req < 0 || !off || (mode != 1 && mode != 2) || (metric != 0 && metric != 1)) return NS_E_ARG;
 	if (n_req == 0) return 0;
-	CK(cudaSetDevice(d->device));
+	if (!client_tz || !out_cnt || off[0] < 0) return NS_E_ARG;
+	for (int q = 0; q < n_req; q++) if (off[q+1] < off[q]) return NS_E_ARG;
 	const int total = off[n_req];
+	if (total > 0 && (!cand_node || !cand_tz || !out_val || !out_node)) return NS_E_ARG;
+	CK(cudaSetDevice(d->device));
 	for (int i = 0; i < total; i++) if (cand_node[i] < 0 || cand_node[i] >= d->h.S.n_nodes) return NS_E_ARG;
 	const size_t tb = (size_t)std::max(total, 1)*4;
 	int32_t *d_off, *d_node, *d_tz, *d_ctz, *d_val, *d_k, *d_ov, *d_on, *d_oc; uint8_t *d_us = nullptr;
@@ -1085,7 +1088,7 @@ extern "C" int ns_ens_digests(ns_ens *e, ns_digest *out, int n){
 }
 // ---- analyzer reductions over every replica's record stream (ns_ana.cu)
 extern "C" int ns_ens_analysis_begin(ns_ens *e, double period){
-	if (!e || !(period > 0) || e->ana_on) return NS_E_ARG;
+	if (!e || !(period > 0) || e->ana_on || !S_rec_ok(e)) return NS_E_ARG;   // (the analysis reads the record stream)
 	CK(cudaSetDevice(e->device));
 	const int n = e->n;
 	auto al = [](size_t b){ return (b+255) & ~(size_t)255; };
@@ -1129,7 +1132,6 @@ extern "C" int ns_ens_analysis_begin(ns_ens *e, double period){
 		if (N) { CK(cudaMemset(A.ntype, 2, N)); CK(cudaMemset(A.n_state, 0xff, N)); }     // everything is a client until a state record says otherwise; no state yet
 	}
 	CK(cudaMemcpy(e->d_ana, hs.data(), sizeof(AnaStream)*n, cudaMemcpyHostToDevice));
-	if (!S_rec_ok(e)) return NS_E_ARG;
 	e->ana_on = true;
 	return 0;
 }
