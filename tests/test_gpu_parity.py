@@ -456,3 +456,22 @@ def test_host_view_matches_the_table_read_backs(built):
         assert int(r["producer_ord"]) == int(f["ord"]) and float(r["len"]) == float(fs[int(f["ord"]), 3])
     e.close()
     o.close()
+
+
+def test_malformed_scenarios_are_rejected_before_use(built):
+    """ns_dev_create / ns_ens_create answer NS_E_BAD_SCENARIO for every malformed script of tests/malformed.py (counts, offsets, operands
+    and tables the device would index with) and the library is unharmed afterwards."""
+    import malformed as M
+    z = dict(CASES)["test04"]
+    base = z["scenario"].tobytes()
+    for rule, m in M.mutations(base):
+        for mode in (E.MODE_SEQ, E.MODE_AUTO):
+            with pytest.raises(E.NsError) as ei:
+                E.Engine(m, mode=mode)
+            assert ei.value.code == -1, rule
+        with pytest.raises(E.NsError) as ei:
+            E.Ensemble([base, m], record_cap=1 << 16, ring_cap=1 << 12)
+        assert ei.value.code == -1, rule
+    e, st = run_engine(base, E.MODE_AUTO)
+    assert st == 0 and e.records() == z["records"].tobytes()
+    e.close()

@@ -206,3 +206,23 @@ def test_record_file_split_at_record_boundaries():
             assert len(nodes) == 92
             last = run(pre + ".%d" % (len(pp) - 1), "list_nodes")
             assert last.returncode == 0 and sorted(last.stdout.splitlines()) == sorted(nodes)
+
+
+def test_malformed_scenarios_break_the_rule_they_name():
+    """CPU: the byte surgery of tests/malformed.py does what it says (the GPU suite feeds the same scripts to ns_dev_create), and
+    the numpy restatement of build_sim's rules accepts every valid script of the test suite."""
+    import malformed as M
+    from conftest import golden_cases
+    base = S.reference_tests()["test04"].to_bytes()
+    assert M.violations(base) == []
+    muts = M.mutations(base)
+    assert len(muts) >= 18 and len({m for _, m in muts}) == len(muts)
+    for rule, m in muts:
+        assert rule in M.violations(m), rule
+    for name, sc in S.reference_tests().items():
+        assert M.violations(sc.to_bytes()) == [], name
+    for name, z in golden_cases():
+        b = z["scenario"].tobytes()
+        if np.frombuffer(b[:48], dtype=M.HDR)[0]["flags"] == 0:
+            assert M.violations(b) == [], name
+    assert M.violations(S.swarm(60, 2, n_catalogue=4, seeds_per_peer=2, mean_strips=2.0).to_bytes()) == []
