@@ -475,3 +475,36 @@ def test_malformed_scenarios_are_rejected_before_use(built):
     e, st = run_engine(base, E.MODE_AUTO)
     assert st == 0 and e.records() == z["records"].tobytes()
     e.close()
+
+
+def test_c_abi_argument_checks(built):
+    """what the host hands to ns_dev_pick_live / ns_dev_pick_batch / ns_dev_exec is checked before a kernel indexes with it
+    (NS_E_ARG), and a refused call leaves the simulation usable"""
+    import ctypes as C
+    import malformed as M
+    sc = S.reference_tests()["test04"]
+    z = dict(CASES)["test04"]
+    e = E.Engine(sc.to_bytes(), mode=E.MODE_SEQ, records=True, trace=True)
+    good = dict(off=[0, 2, 3], cand_node=[0, 1, 2], cand_tz=[1, 2, 3], client_tz=[0, 5])
+    ov, on, oc, _ = e.pick_live(1, 0, k=[1, 1], **good)
+    assert oc.tolist() == [1, 1] and sorted(on[:2].tolist()) == [0, 1] and on[2] == 2
+    for kw, mode, metric in ((dict(good, off=[0, 3, 2]), 1, 0), (dict(good, off=[-1, 2, 3]), 1, 0), (dict(good, cand_node=[0, 1, sc.n_nodes]), 1, 0),
+                             (dict(good, cand_node=[0, -1, 2]), 1, 0), (good, 3, 0), (good, 1, 2)):
+        with pytest.raises(E.NsError) as ei:
+            e.pick_live(mode, metric, **kw)
+        assert ei.value.code == -10
+    for mode, off in ((1, [0, 3, 2]), (3, [0, 2, 3])):
+        with pytest.raises(E.NsError) as ei:
+            E.pick_batch(mode, off, [5, 1, 3], [0, 1, 2], k=[1, 1])
+        assert ei.value.code == -10
+    L = E.lib()
+    L.ns_dev_exec.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.ns_dev_exec.restype = C.c_int
+    for kind, a in ((1, 99), (1, -1), (3, -1), (9, 99), (10, -1), (11, 0), (12, 0), (99, 0), (0, 0)):   # CREATE, CLOSE, CREATE_RID, RANGE_SET, DELRES / AUTODEL without a host core, unknown kinds
+        op = np.zeros(1, dtype=M.OP)
+        op["kind"], op["a"] = kind, a
+        assert L.ns_dev_exec(e.h, op.ctypes.data, 1) == -10, (kind, a)
+    op = np.zeros(1, dtype=M.OP)
+    assert L.ns_dev_exec(e.h, op.ctypes.data, -1) == -10 and L.ns_dev_exec(e.h, None, 1) == -10 and L.ns_dev_exec(e.h, op.ctypes.data, 0) == 0
+    assert e.run(0) == 0 and e.records() == z["records"].tobytes()
+    e.close()
