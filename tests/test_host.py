@@ -62,11 +62,12 @@ def test_no_cpu_fallback(built):
         E.pick_batch(1, np.array([0, 2]), np.array([1, 2]), np.array([0, 1]), np.array([1]))
 
 
+@pytest.mark.gpu
 def test_bad_scenario_rejected(built):
-    if E.device_count() == 0:
-        pytest.skip("needs a device to get past the device check")
-    with pytest.raises(E.NsError):
+    """(the device check comes first, so this needs a GPU; the full set of malformed scripts is in tests/test_gpu_parity.py)"""
+    with pytest.raises(E.NsError) as ei:
         E.Engine(b"\0" * 64)
+    assert ei.value.code == -1
 
 
 def test_swarm_generator_is_valid_script():
