@@ -1,0 +1,200 @@
+// tests/emul/emu.cpp — TEST INFRASTRUCTURE: the runtime behind tests/emul/cuda_runtime.h (see there).
+#include "cuda_runtime.h"
+#include <stdio.h>
+#include <ucontext.h>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+
+namespace emu {
+// One CUDA thread = one fiber (ucontext) of the calling OS thread; the threads of a block are scheduled one at a time, highest
+// thread index first, each running until it finishes or reaches a rendezvous (a warp collective, __syncthreads).  So between two
+// rendezvous lane 31 runs first and lane 0 last: what lane 0 writes after every lane has read it — the pattern of the engine's
+// `L0 { table[i] = v; }` updates, which a converged warp executes as read-by-all, then write-by-one — is seen by no other lane
+// before the next rendezvous, as on the GPU.  The schedule is deterministic.
+struct Rendezvous {
+	int expected = 0, arrived = 0; unsigned gen = 0;
+	const char *what = "";
+	// the threads that meet must come from the same call site after the same number of rendezvous
+	uint64_t tag = 0; bool tag_set = false; int t_line = 0; const char *t_file = "";
+};
+struct Fiber {
+	ucontext_t ctx; void *stack = nullptr; size_t stack_size = 0;
+	bool done = false;
+	Rendezvous *waiting = nullptr; unsigned wait_gen = 0; int w_line = 0; const char *w_file = "";
+	unsigned tid = 0; uint64_t n_warp = 0, n_block = 0;
+	void *fake = nullptr;                                   // AddressSanitizer's fake-stack handle across a switch
+};
+struct Warp { Rendezvous bar; uint64_t slots[32]; unsigned live = 0; };
+struct Block {
+	Rendezvous bar; std::vector<Warp> warps; std::vector<uint64_t> dyn; std::vector<Fiber> fibers;
+	ucontext_t sched; void *sched_fake = nullptr;
+	const void *sched_bottom = nullptr; size_t sched_size = 0;
+	const std::function<void()> *body = nullptr; dim3 block, grid; unsigned bidx = 0; const char *kernel = "";
+	Fiber *cur = nullptr;
+};
+static thread_local Block *B = nullptr;                     // the block the calling OS thread is running (nullptr: sequential mode)
+static thread_local const char *seq_kernel = "";
+
+static void need_threads(const char *what){
+	if (B && B->cur) return;
+	fprintf(stderr, "emu: kernel %s calls %s but is launched in sequential mode: add it to the threaded set in emu.cpp\n", seq_kernel, what);
+	abort();
+}
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define SWITCH_BEGIN(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define SWITCH_END(fake, ob, os) __sanitizer_finish_switch_fiber(fake, ob, os)
+#else
+#define SWITCH_BEGIN(save, bottom, size) do { } while (0)
+#define SWITCH_END(fake, ob, os) do { } while (0)
+#endif
+static void to_scheduler(bool dying){
+	Fiber *f = B->cur;
+	SWITCH_BEGIN(dying ? nullptr : &f->fake, B->sched_bottom, B->sched_size);
+	swapcontext(&f->ctx, &B->sched);
+	SWITCH_END(f->fake, nullptr, nullptr);
+}
+static void set_ids(const Fiber *f){
+	threadIdx = { f->tid, 0, 0 }; blockIdx = { B->bidx, 0, 0 }; blockDim = B->block; gridDim = B->grid;
+}
+static void fiber_main(void){
+	SWITCH_END(nullptr, &B->sched_bottom, &B->sched_size);
+	Fiber *f = B->cur;
+	set_ids(f);
+	(*B->body)();
+	f->done = true;
+	Warp &w = B->warps[f->tid >> 5];
+	w.live &= ~(1u << (f->tid & 31));
+	for (Rendezvous *r : { &w.bar, &B->bar }) { r->expected--; if (r->expected > 0 && r->arrived >= r->expected) { r->arrived = 0; r->gen++; r->tag_set = false; } }
+	to_scheduler(true);
+}
+static void meet(Rendezvous &r, uint64_t my_tag, int line, const char *file){
+	Fiber *f = B->cur;
+	if (!r.tag_set) { r.tag = my_tag; r.t_line = line; r.t_file = file; r.tag_set = true; }
+	else if (r.tag != my_tag || line != r.t_line || strcmp(file, r.t_file)) {
+		fprintf(stderr, "emu: %s: divergent %s collective: one thread is at %s:%d after %llu rendezvous, thread %u at %s:%d after %llu\n",
+			B->kernel, r.what, r.t_file, r.t_line, (unsigned long long)r.tag, f->tid, file, line, (unsigned long long)my_tag);
+		abort();
+	}
+	const unsigned g = r.gen;
+	if (++r.arrived >= r.expected) { r.arrived = 0; r.gen++; r.tag_set = false; }
+	f->waiting = &r; f->wait_gen = g; f->w_line = line; f->w_file = file;
+	to_scheduler(false);                                     // (also the last one to arrive: the next stretch starts with the highest lane again)
+	set_ids(f);
+}
+void warp_sync(int line, const char *file){ need_threads("a warp collective"); Fiber *f = B->cur; meet(B->warps[f->tid >> 5].bar, ++f->n_warp, line, file); }
+void block_sync(void){ need_threads("__syncthreads"); Fiber *f = B->cur; meet(B->bar, ++f->n_block, 0, "__syncthreads"); }
+uint64_t *warp_slots(void){ need_threads("a warp collective"); return B->warps[B->cur->tid >> 5].slots; }
+unsigned warp_live(void){ return B->warps[B->cur->tid >> 5].live; }
+int lane_id(void){ return B && B->cur ? (int)(B->cur->tid & 31) : (int)(threadIdx.x & 31); }
+void *dyn_smem(void){ need_threads("dynamic shared memory"); return B->dyn.data(); }
+
+// kernels whose threads meet (warp collectives, __syncthreads, shared memory): one fiber per CUDA thread, blocks one after the
+// other.  Everything else is plain data-parallel code and runs its threads one after the other as plain calls.
+static const std::set<std::string> threaded = { "k_run_seq", "k_init_groups", "k_exec_ops", "k_stream_hash", "k_ens_drain", "k_ens_digest",
+	"k_pick", "k_pick_small", "k_ana" };
+// grid-stride kernels whose result does not depend on the grid: fewer blocks, same answer
+static unsigned clamp_grid(const std::string &k, unsigned g){ if (k == "k_stream_hash") return 1; return g; }
+#define EMU_STACK (4u << 20)
+
+void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body){
+	const std::string name(kernel);
+	grid.x = clamp_grid(name, grid.x);
+	const unsigned nt = block.x*block.y*block.z;
+	if (B) { fprintf(stderr, "emu: launch of %s from inside a kernel\n", kernel); abort(); }
+	if (!threaded.count(name)) {
+		seq_kernel = kernel;
+		blockDim = block; gridDim = grid;
+		for (unsigned b = 0; b < grid.x; b++) for (unsigned t = 0; t < nt; t++) { blockIdx = { b, 0, 0 }; threadIdx = { t, 0, 0 }; body(); }
+		return;
+	}
+	for (unsigned b = 0; b < grid.x; b++) {
+		Block blk;
+		const unsigned nw = (nt+31)/32;
+		blk.warps = std::vector<Warp>(nw);
+		blk.dyn.assign((dyn_smem+7)/8+1, 0xCDCDCDCDCDCDCDCDull);
+		blk.bar.expected = (int)nt; blk.bar.what = "__syncthreads";
+		blk.body = &body; blk.block = block; blk.grid = grid; blk.bidx = b; blk.kernel = kernel;
+		for (unsigned w = 0; w < nw; w++) {
+			const unsigned n = std::min(32u, nt-32*w);
+			blk.warps[w].bar.expected = (int)n; blk.warps[w].bar.what = "warp";
+			blk.warps[w].live = n == 32 ? 0xffffffffu : ((1u << n)-1u);
+			memset(blk.warps[w].slots, 0, sizeof blk.warps[w].slots);
+		}
+		blk.fibers = std::vector<Fiber>(nt);
+		B = &blk;
+		for (unsigned t = 0; t < nt; t++) {
+			Fiber &f = blk.fibers[t];
+			f.tid = t; f.stack_size = EMU_STACK; f.stack = malloc(f.stack_size);
+			getcontext(&f.ctx);
+			f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = f.stack_size; f.ctx.uc_link = nullptr;
+			makecontext(&f.ctx, fiber_main, 0);
+		}
+		unsigned left = nt;
+		while (left) {
+			bool progress = false;
+			for (int t = (int)nt-1; t >= 0; t--) {
+				Fiber &f = blk.fibers[t];
+				if (f.done) continue;
+				if (f.waiting) { if (f.waiting->gen == f.wait_gen) continue; f.waiting = nullptr; }
+				blk.cur = &f;
+				SWITCH_BEGIN(&blk.sched_fake, f.stack, f.stack_size);
+				swapcontext(&blk.sched, &f.ctx);
+				SWITCH_END(blk.sched_fake, nullptr, nullptr);
+				blk.cur = nullptr;
+				progress = true;
+				if (f.done) { left--; free(f.stack); f.stack = nullptr; }
+			}
+			if (!progress) {
+				fprintf(stderr, "emu: %s block %u: dead-lock, %u threads wait for a rendezvous the others never reach:\n", kernel, b, left);
+				for (auto &f : blk.fibers) if (!f.done) fprintf(stderr, "  thread %u waits at %s:%d (%s)\n", f.tid, f.w_file, f.w_line, f.waiting ? f.waiting->what : "?");
+				abort();
+			}
+		}
+		B = nullptr;
+	}
+}
+}   // namespace emu
+
+// ---------------------------------------------------------------- runtime API
+struct emu_stream { int id; };
+struct emu_event { std::chrono::steady_clock::time_point t; };
+const char *cudaGetErrorString(cudaError_t e){ return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "error"; }
+static bool zero_fill(void){ static int z = -1; if (z < 0) { const char *e = getenv("EMU_ZERO"); z = e && *e && *e != '0'; } return z != 0; }
+cudaError_t cudaMalloc(void **p, size_t n){
+	*p = malloc(n ? n : 1);
+	if (!*p) return cudaErrorMemoryAllocation;
+	memset(*p, zero_fill() ? 0 : 0xCD, n);                  // cudaMalloc does not clear: make a read of never-written memory visible
+	return cudaSuccess;
+}
+cudaError_t cudaFree(void *p){ free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned){ *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void *p){ free(p); return cudaSuccess; }
+cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned){ *d = h; return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind){ if (n) memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t){ if (n) memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *p, int v, size_t n){ if (n) memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t){ if (n) memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t *s){ *s = new emu_stream{ 0 }; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned){ *s = new emu_stream{ 1 }; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t){ return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s){ delete s; return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e){ *e = new emu_event{ std::chrono::steady_clock::now() }; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned){ return cudaEventCreate(e); }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t){ e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b){ *ms = std::chrono::duration<float, std::milli>(b->t-a->t).count(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e){ delete e; return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void){ return cudaSuccess; }
+cudaError_t cudaGetLastError(void){ return cudaSuccess; }
+cudaError_t cudaSetDevice(int){ return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d){ *d = 0; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n){ *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int){ memset(p, 0, sizeof *p); p->multiProcessorCount = 1; strcpy(p->name, "lock-step warp model (tests/emul)"); return cudaSuccess; }
