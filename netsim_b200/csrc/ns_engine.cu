@@ -235,7 +235,10 @@ static int build_sim(HostSim &h, const void *scenario, size_t len, const ns_dev_
 	const ns_sc_resource *rs = (const ns_sc_resource *)p; p += (size_t)H.n_resources*sizeof *rs;
 	const ns_sc_copy *cp = (const ns_sc_copy *)p; p += (size_t)H.n_copies*sizeof *cp;
 	const int32_t *goff = (const int32_t *)p; p += ((size_t)H.n_groups+1)*4;
-	const ns_sc_op *ops = (const ns_sc_op *)p; p += (size_t)H.n_ops*sizeof *ops;
+	// (the op table follows 4-byte offsets, so where it lies it may not be aligned for its 8-byte members: read it from a copy)
+	std::vector<ns_sc_op> ops_copy((size_t)H.n_ops);
+	if (H.n_ops) memcpy(ops_copy.data(), p, (size_t)H.n_ops*sizeof(ns_sc_op));
+	const ns_sc_op *ops = ops_copy.data(); p += (size_t)H.n_ops*sizeof *ops;
 	const ns_sc_ondone *od = (const ns_sc_ondone *)p; p += (size_t)H.n_ondone*sizeof *od;
 	const bool has_clients = (H.flags & NS_SC_F_CLIENTS) != 0;
 	const ns_sc_client *cl = (const ns_sc_client *)p;

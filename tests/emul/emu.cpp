@@ -14,11 +14,10 @@ thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 
 namespace emu {
-// One CUDA thread = one fiber (ucontext) of the calling OS thread; the threads of a block are scheduled one at a time, highest
-// thread index first, each running until it finishes or reaches a rendezvous (a warp collective, __syncthreads).  So between two
-// rendezvous lane 31 runs first and lane 0 last: what lane 0 writes after every lane has read it — the pattern of the engine's
-// `L0 { table[i] = v; }` updates, which a converged warp executes as read-by-all, then write-by-one — is seen by no other lane
-// before the next rendezvous, as on the GPU.  The schedule is deterministic.
+// One CUDA thread = one fiber (ucontext) of the calling OS thread; the threads of a block are scheduled one at a time, each
+// running until it finishes or reaches a rendezvous (a warp collective, __syncthreads, the two ends of an `L0 { }` block).  The
+// schedule is deterministic: between two rendezvous the threads take their turn in index order (EMU_ORDER=rev: highest first).
+// Code whose lanes only communicate through rendezvous gives the same answer in both orders; the goldens are run in both.
 struct Rendezvous {
 	int expected = 0, arrived = 0; unsigned gen = 0;
 	const char *what = "";
@@ -103,6 +102,14 @@ static const std::set<std::string> threaded = { "k_run_seq", "k_init_groups", "k
 	"k_pick", "k_pick_small", "k_ana" };
 // grid-stride kernels whose result does not depend on the grid: fewer blocks, same answer
 static unsigned clamp_grid(const std::string &k, unsigned g){ if (k == "k_stream_hash") return 1; return g; }
+// The order in which the threads of a block take their turn between two rendezvous: lowest first, or EMU_ORDER=rev.
+// One place is known to depend on it (tests/emul/README.md): ana_process (ns_ana_dev.cuh) gathers each node's previous record from
+// a table and lets the LAST record of that node in the tile — a higher lane — write the table back with no __syncwarp in between;
+// a converged warp does all the reads first, which lowest-first reproduces and highest-first does not.
+static bool lanes_forward(const std::string &){
+	const char *e = getenv("EMU_ORDER");
+	return !(e && !strcmp(e, "rev"));
+}
 #define EMU_STACK (4u << 20)
 
 void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body){
@@ -116,6 +123,7 @@ void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const st
 		for (unsigned b = 0; b < grid.x; b++) for (unsigned t = 0; t < nt; t++) { blockIdx = { b, 0, 0 }; threadIdx = { t, 0, 0 }; body(); }
 		return;
 	}
+	const bool forward = lanes_forward(name);
 	for (unsigned b = 0; b < grid.x; b++) {
 		Block blk;
 		const unsigned nw = (nt+31)/32;
@@ -141,8 +149,8 @@ void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const st
 		unsigned left = nt;
 		while (left) {
 			bool progress = false;
-			for (int t = (int)nt-1; t >= 0; t--) {
-				Fiber &f = blk.fibers[t];
+			for (unsigned k = 0; k < nt; k++) {
+				Fiber &f = blk.fibers[forward ? k : nt-1-k];
 				if (f.done) continue;
 				if (f.waiting) { if (f.waiting->gen == f.wait_gen) continue; f.waiting = nullptr; }
 				blk.cur = &f;

@@ -1,0 +1,215 @@
+"""tests/emul/run_checks.py — TEST INFRASTRUCTURE.  Runs inside a process that has loaded tests/emul/_build/libnetsim_emul.so in
+place of the CUDA library (NS_LIB) with the AddressSanitizer runtime preloaded: the device code of the single-warp engine, the
+pickers, the analyzer kernel and the host layer, compiled for the lock-step warp model (cuda_runtime.h here), against the
+committed goldens of the compiled reference and against the CPU oracle.  Prints one JSON line per check; any sanitizer report
+aborts the process.
+
+    python run_checks.py goldens:test00,test05 random:0,1 windows ensemble picks malformed args"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+from netsim_b200 import engine as E  # noqa: E402
+from netsim_b200 import scenario as S  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+
+KEYS = ("events", "solves", "full_spreads", "flow_visits", "speed_change", "flow_done", "drain", "throttle", "user",
+        "creates", "closes", "draws", "seq")
+
+
+def out(name, ok, t0, **kw):
+    print(json.dumps(dict(check=name, ok=bool(ok), sec=round(time.time() - t0, 1), **kw)), flush=True)
+
+
+def goldens(names):
+    for n in names:
+        t0 = time.time()
+        z = np.load(os.path.join(ROOT, "tests", "golden", n + ".npz"))
+        e = E.Engine(z["scenario"].tobytes(), mode=E.MODE_SEQ, records=True, trace=True)
+        st = e.run(0)
+        ok = st == 0 and e.records() == z["records"].tobytes() and ("trace" not in z.files or e.trace().tobytes() == z["trace"].tobytes())
+        ok = ok and ("events" not in z.files or e.counters()["events"] == int(z["events"]))
+        out("golden " + n, ok, t0, events=e.counters()["events"])
+        e.close()
+
+
+def random_scripts(seeds):
+    """tests/test_gpu_parity.py::test_engine_matches_oracle_random, one-warp engine, on the model"""
+    for seed in seeds:
+        for relay in (False, True):
+            t0 = time.time()
+            sc = S.random_small(200 + seed, n_nodes=6 + seed % 7, n_flows=8 + seed % 17, relay=relay)
+            b = sc.to_bytes()
+            o = pyoracle.Oracle(b)
+            so = o.run(0)
+            e = E.Engine(b, mode=E.MODE_SEQ, records=True, trace=True)
+            se = e.run(0)
+            ok = se == -so
+            if so == 0:
+                ce, co = e.counters(), o.counters()
+                ok = (ok and e.records() == o.records() and e.trace().tobytes() == o.trace().tobytes() and all(ce[k] == co[k] for k in KEYS)
+                      and e.flow_state(sc.n_creates()).tobytes() == o.flow_state(sc.n_creates()).tobytes()
+                      and e.node_state(sc.n_nodes).tobytes() == o.node_state(sc.n_nodes).tobytes()
+                      and e.digest()["record_hash"] == E.stream_hash(o.records()))
+            out(f"random {seed} relay={int(relay)}", ok, t0, status=se)
+            e.close()
+            o.close()
+
+
+def windows():
+    """stop / resume in the middle of an equal-timestamp batch (max_events), and a record buffer far smaller than the stream
+    (soft stop before a batch, drain, resume): the paths through seq_restore"""
+    t0 = time.time()
+    sc = S.swarm(60, 2, n_catalogue=4, seeds_per_peer=2, mean_strips=2.0)
+    b = sc.to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(900) == 0
+    e = E.Engine(b, mode=E.MODE_SEQ, records=True, trace=True)
+    ok = e.run(307) == 0 and e.counters()["events"] == 307 and e.run(601) == 0 and e.run(900) == 0
+    ce, co = e.counters(), o.counters()
+    ok = ok and e.records() == o.records() and e.trace().tobytes() == o.trace().tobytes() and all(ce[k] == co[k] for k in KEYS)
+    out("windows: three instalments", ok, t0, events=ce["events"])
+    e.close()
+    t0 = time.time()
+    e = E.Engine(b, mode=E.MODE_SEQ, records=True, record_cap=24 << 10)
+    stream = e.run_draining(900)
+    ok = stream == o.records() and len(stream) > (24 << 10) and e.counters()["events"] == o.counters()["events"]
+    out("windows: bounded record buffer drained", ok, t0, stream=len(stream))
+    e.close()
+    o.close()
+
+
+def ensemble():
+    """replicas on the one-warp engine: digests from the device against single runs of the oracle; the client-behaviour fixture
+    as replicas with a record buffer that is folded in place, analysed on the device (k_ana) against the numpy restatement"""
+    from oracle import pyanalyze
+    t0 = time.time()
+    scs = [S.random_small(300 + i, n_nodes=7, n_flows=10).to_bytes() for i in range(4)]
+    ens = E.Ensemble(scs, mode=E.MODE_SEQ)
+    ens.run(0)
+    ok = True
+    for d, b in zip(ens.digests(), scs):
+        o = pyoracle.Oracle(b)
+        so = o.run(0)
+        ok = ok and d["status"] == -so
+        if so == 0:
+            ok = ok and d["events"] == o.counters()["events"] and d["solves"] == o.counters()["solves"] and d["record_bytes"] == len(o.records()) \
+                and d["record_hash"] == E.stream_hash(o.records())
+        o.close()
+    cs = ens.counters_sum()
+    out("ensemble: digests of 4 replicas", ok, t0, events=cs["events"])
+    ens.close()
+    t0 = time.time()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "clients_play40.npz"))
+    b, rec = z["scenario"].tobytes(), z["records"].tobytes()
+    ens = E.Ensemble([b, b], mode=E.MODE_SEQ, record_cap=1 << 12, ring_cap=1 << 12)
+    ens.analysis_begin(7.5)
+    ens.run(0)
+    dg, an = ens.digests(), ens.analysis()
+    s = pyanalyze.summarize(rec, 7.5)
+    ok = True
+    for d, a in zip(dg, an):
+        ok = ok and d["status"] == 0 and d["record_hash"] == E.stream_hash(rec) and d["record_bytes"] == len(rec)
+        ok = ok and all(a[k] == s[k] for k in ("records", "usage_records", "state_records", "stale_now", "stale_max")) and a["t_last"] == s["t_last"]
+        ok = ok and np.allclose(a["usage"], s["usage"], rtol=1e-9, atol=1e-6) and np.allclose(a["stale"], s["stale"], rtol=1e-9, atol=1e-9)
+    out("ensemble: client fixture folded + analysed on the device", ok, t0, records=int(an[0]["records"]))
+    ens.close()
+
+
+def picks():
+    from conftest import pick_golden
+    t0 = time.time()
+    z = pick_golden()
+    ov, on, oc, _ = E.pick_batch(1, z["off"], z["val"], z["node"], z["k"])
+    out("picks: reference golden (k_pick / k_pick_small)", (oc == z["out_cnt"]).all() and (ov == z["out_val"]).all() and (on == z["out_node"]).all(), t0,
+        requests=int(len(z["k"])))
+    t0 = time.time()
+    rng = np.random.default_rng(5)
+    L = pyoracle.lib()
+    ok = True
+    for lo_c, hi_c, n in ((0, 70, 40), (65, 140, 6)):          # one request per thread (<= 64 entries, >= 32 requests) and one warp per request
+        offs, vals, nodes, ks = [0], [], [], []
+        for _ in range(n):
+            c = int(rng.integers(lo_c, hi_c))
+            offs.append(offs[-1] + c)
+            vals.extend(rng.integers(-30, 30, c).tolist())
+            nodes.extend(rng.permutation(1000)[:c].tolist())
+            ks.append(int(rng.integers(0, 40)))
+        off, val, node, k = (np.array(x, dtype=np.int32) for x in (offs, vals, nodes, ks))
+        for mode in (1, 2):
+            ov, on, oc, _ = E.pick_batch(mode, off, val, node, k)
+            for q in range(n):
+                lo, hi = off[q], off[q + 1]
+                v, nd = val[lo:hi].copy(), node[lo:hi].copy()
+                if mode == 1:
+                    cnt = L.ns_oracle_pick_opt1(v.ctypes.data, nd.ctypes.data, hi - lo, int(k[q]))
+                    ok = ok and oc[q] == cnt and (ov[lo:hi] == v).all() and (on[lo:hi] == nd).all()
+                else:
+                    u = np.ones(hi - lo, dtype=np.uint8)
+                    i = L.ns_oracle_pick_opt2(v.ctypes.data, u.ctypes.data, hi - lo)
+                    ok = ok and oc[q] == (1 if i >= 0 else 0) and (i < 0 or on[lo] == nd[i])
+    out("picks: random tables against the oracle", ok, t0)
+
+
+def malformed():
+    import malformed as M
+    t0 = time.time()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "test04.npz"))
+    base = z["scenario"].tobytes()
+    ok, n = True, 0
+    for rule, m in M.mutations(base):
+        for make in (lambda: E.Engine(m, mode=E.MODE_SEQ), lambda: E.Ensemble([base, m], mode=E.MODE_SEQ, record_cap=1 << 16, ring_cap=1 << 12)):
+            try:
+                make()
+                ok = False
+            except E.NsError as ex:
+                ok = ok and ex.code == -1
+            n += 1
+    out("malformed scripts refused", ok, t0, cases=n)
+
+
+def args():
+    """tests/test_gpu_parity.py::test_c_abi_argument_checks on the model"""
+    import ctypes as C
+    import malformed as M
+    t0 = time.time()
+    sc = S.reference_tests()["test04"]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "test04.npz"))
+    e = E.Engine(sc.to_bytes(), mode=E.MODE_SEQ, records=True, trace=True)
+    good = dict(off=[0, 2, 3], cand_node=[0, 1, 2], cand_tz=[1, 2, 3], client_tz=[0, 5])
+    ov, on, oc, _ = e.pick_live(1, 0, k=[1, 1], **good)
+    ok = oc.tolist() == [1, 1] and sorted(on[:2].tolist()) == [0, 1] and on[2] == 2
+    for kw, mode, metric in ((dict(good, off=[0, 3, 2]), 1, 0), (dict(good, off=[-1, 2, 3]), 1, 0), (dict(good, cand_node=[0, 1, sc.n_nodes]), 1, 0), (good, 3, 0), (good, 1, 2)):
+        try:
+            e.pick_live(mode, metric, **kw)
+            ok = False
+        except E.NsError as ex:
+            ok = ok and ex.code == -10
+    L = E.lib()
+    L.ns_dev_exec.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.ns_dev_exec.restype = C.c_int
+    for kind, a in ((1, 99), (1, -1), (3, -1), (9, 99), (10, -1), (11, 0), (12, 0), (99, 0), (0, 0)):
+        op = np.zeros(1, dtype=M.OP)
+        op["kind"], op["a"] = kind, a
+        ok = ok and L.ns_dev_exec(e.h, op.ctypes.data, 1) == -10
+    ok = ok and e.run(0) == 0 and e.records() == z["records"].tobytes()
+    out("C ABI argument checks", ok, t0)
+    e.close()
+
+
+if __name__ == "__main__":
+    assert "emul" in E.LIB_PATH, "run_checks.py is for the lock-step model only (NS_LIB=tests/emul/_build/libnetsim_emul.so)"
+    for a in sys.argv[1:]:
+        name, _, arg = a.partition(":")
+        if name == "goldens":
+            goldens(arg.split(","))
+        elif name == "random":
+            random_scripts([int(x) for x in arg.split(",")])
+        else:
+            {"windows": windows, "ensemble": ensemble, "picks": picks, "malformed": malformed, "args": args}[name]()

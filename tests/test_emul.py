@@ -1,0 +1,72 @@
+"""CPU: the DEVICE code of the single-warp engine (ns_seq.cu + ns_model.cuh), of the pickers (ns_pick.cu), of the analyzer kernel
+(ns_ana.cu) and the host layer (ns_engine.cu), compiled as plain C++ against a deterministic lock-step warp model (tests/emul) and run
+under AddressSanitizer + UBSan with poisoned "device memory": byte-identical to the goldens of the compiled reference and to the CPU
+oracle.  compute-sanitizer is closed on the GPU pool; this is the memory-safety and collective-discipline pass the device code
+gets instead (out-of-bounds reads and writes, reads of never-written memory that matter, collectives not every lane reaches or
+that lanes reach from different call sites).  TEST INFRASTRUCTURE: the model is not a fallback of the product — the product
+library fails with NS_E_NO_DEVICE without a GPU (tests/test_host.py::test_no_cpu_fallback) — and is ~10^4 times slower than a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+LIB = os.path.join(EMUL, "_build", "libnetsim_emul.so")
+
+
+@pytest.fixture(scope="module")
+def model(built):
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("no AddressSanitizer runtime next to gcc")
+    subprocess.run(["make", "-s", "-C", EMUL], check=True)
+    return dict(os.environ, NS_LIB=LIB, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
+
+
+def run(env, *checks, order=None, timeout=900):
+    env = dict(env)
+    if order:
+        env["EMU_ORDER"] = order
+    p = subprocess.run([sys.executable, os.path.join(EMUL, "run_checks.py"), *checks], env=env, capture_output=True, text=True, timeout=timeout)
+    err = "\n".join(ln for ln in p.stderr.splitlines() if "doesn't fully support makecontext" not in ln)
+    assert p.returncode == 0 and "AddressSanitizer" not in err and "runtime error" not in err and "emu:" not in err, err[-3000:]
+    res = [json.loads(ln) for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert res and all(r["ok"] for r in res), [r for r in res if not r["ok"]]
+    return res
+
+
+def parallel(env, jobs, **kw):
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        return [r for rs in ex.map(lambda j: run(env, *j, **kw), jobs) for r in rs]
+
+
+def test_goldens_on_the_lockstep_model(model):
+    """the reference's own test00-05, the edge cases, random scripts, relay topologies (throttles, merges), churn and the client
+    behaviour fixture: records, fp64 traces and event counts of the compiled reference, from the device code under ASan + UBSan"""
+    jobs = [["goldens:test00,test01,test02,test03,test04,test05,edge_empty,edge_end_and_closes,edge_existing_range,edge_missing_resource,edge_zero_capacity,rand1,rand21,rand34"],
+            ["goldens:rand11,rand13,rand2,rand3"], ["goldens:rand55,rand7,rand89,relay1,relay16"], ["goldens:relay12,relay4,relay6,relay9"],
+            ["goldens:churn150"], ["goldens:clients_play40"]]
+    res = parallel(model, jobs)
+    assert len(res) == 33 - 4            # all but swarm200 and the three long client fixtures (NS_SLOW below)
+
+
+def test_lane_schedule_does_not_matter(model):
+    """the same device code with the lanes taking their turn highest-first instead of lowest-first between two rendezvous: code
+    whose lanes only communicate through collectives / __syncwarp gives the same bytes (the fp64 traces included)"""
+    parallel(model, [["goldens:test04,test05,rand2,rand7"], ["goldens:rand55,relay9,relay1"], ["random:1,4"]], order="rev")
+
+
+def test_engine_paths_on_the_lockstep_model(model):
+    """stop / resume inside a batch, soft stop + drain of a small record buffer, ensembles with in-kernel record folding and the
+    analyzer kernel, the pickers against the reference's own qselect tables, random scripts (relays included, and the scripts on
+    which the reference aborts) against the oracle, the C ABI's refusals"""
+    parallel(model, [["windows"], ["ensemble"], ["picks", "malformed", "args"], ["random:0,3,7"], ["random:12,20,29"]])
+
+
+@pytest.mark.skipif(not os.environ.get("NS_SLOW"), reason="minutes: NS_SLOW=1")
+def test_long_goldens_on_the_lockstep_model(model):
+    parallel(model, [["goldens:swarm200"], ["goldens:clients_cut"], ["goldens:clients_distance"], ["goldens:clients_saturated"]], timeout=3000)
