@@ -70,3 +70,59 @@ def test_engine_paths_on_the_lockstep_model(model):
 @pytest.mark.skipif(not os.environ.get("NS_SLOW"), reason="minutes: NS_SLOW=1")
 def test_long_goldens_on_the_lockstep_model(model):
     parallel(model, [["goldens:swarm200"], ["goldens:clients_cut"], ["goldens:clients_distance"], ["goldens:clients_saturated"]], timeout=3000)
+
+
+HOST = os.path.join(ROOT, "netsim_b200", "host", "_build")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _netsim_dev(model, module, cwd, extra_preload=(), env_extra=None, timeout=900):
+    """netsim_dev (the host core, linked against the CUDA library) with the model's C ABI preloaded in front of it"""
+    env = dict(model, **(env_extra or {}))
+    env.pop("NS_LIB")
+    env["LD_PRELOAD"] = " ".join([model["LD_PRELOAD"], *extra_preload, LIB])
+    p = subprocess.run([os.path.join(HOST, "netsim_dev"), os.path.join(HOST, "modules", module)], cwd=cwd, env=env, capture_output=True, timeout=timeout)
+    err = b"".join(ln for ln in p.stderr.splitlines(True) if b"doesn't fully support makecontext" not in ln)
+    assert p.returncode == 0 and b"AddressSanitizer" not in err and b"runtime error" not in err and b"emu:" not in err, err[-3000:].decode(errors="replace")
+    return err
+
+
+def test_unmodified_reference_modules_through_the_host_core_on_the_model(model):
+    """the reference's own test00-05.c, test_client2/3.c + client_behaviour.c and p2p.c + cloud_behaviour.c (tests/golden/p2p/small50),
+    compiled unchanged against netsim_b200/host/include, with every device call of the host core (k_exec_ops, k_run_seq in
+    host-callback mode, the mirror view, the shared random() stream) answered by the device code on the lock-step model under
+    ASan + UBSan: stderr and record files byte-identical to the reference's"""
+    import hashlib
+    import shutil
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    mods = ["test00", "test01", "test02", "test03", "test04", "test05", "tc2", "tc3"]
+    if not all(os.path.exists(os.path.join(HOST, "modules", m + ".so")) for m in mods + ["p2p"]) or not os.path.exists(os.path.join(HOST, "netsim_dev")):
+        pytest.skip("reference modules were not built against the host core (needs /root/reference at build time)")
+
+    def one(mod):
+        with tempfile.TemporaryDirectory(prefix="nsemu") as d:
+            err = _netsim_dev(model, mod, d)
+            assert err == open(os.path.join(GOLD, mod + ".stderr.txt"), "rb").read(), mod
+            if mod == "test05":
+                assert hashlib.sha256(open(os.path.join(d, "R"), "rb").read()).hexdigest() == "8180090a224a219634a6004be53879144c5edb2a4951c91c691039aab3135d8f"
+        return mod
+
+    def p2p(cfg):
+        exp = json.load(open(os.path.join(GOLD, "p2p", "expected.json")))[cfg]
+        shim = os.path.join(ROOT, "oracle", "_ref", "timeshim.so")
+        with tempfile.TemporaryDirectory(prefix="nsemu") as d:
+            shutil.copy(os.path.join(GOLD, "p2p", cfg, "p2p.cfg"), d)
+            err = _netsim_dev(model, "p2p", d, extra_preload=(shim,), env_extra={"NS_FAKE_TIME": str(exp["seed"])}, timeout=3000)
+            data = open(os.path.join(d, "p2p_record"), "rb").read()
+            n = int.from_bytes(data[:4], "big")
+            assert n == exp["record_bytes"] and hashlib.sha256(data[4:4 + n]).hexdigest() == exp["record_sha256"], cfg
+            assert hashlib.sha256(err).hexdigest() == exp["stderr_sha256"], cfg
+        return cfg
+
+    cfgs = ["small50"] + (["evict3", "play2c", "cloudc", "push2"] if os.environ.get("NS_SLOW") else [])
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "timeshim.so")):
+        cfgs = []
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        done = list(ex.map(one, mods)) + list(ex.map(p2p, cfgs))
+    assert len(done) == len(mods) + len(cfgs)
