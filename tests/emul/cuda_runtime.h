@@ -41,6 +41,9 @@
 #define __restrict__
 
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
@@ -142,10 +145,34 @@ template <typename T> inline unsigned __match_any_sync(unsigned, T v, EMU_SITE){
 	emu::warp_sync(line, file);
 	return r;
 }
+template <typename T, typename F> inline T emu_reduce(T v, F f, int line, const char *file){
+	uint64_t *s = emu::warp_slots();
+	s[emu::lane_id()] = emu::to_bits(v);
+	emu::warp_sync(line, file);
+	const unsigned live = emu::warp_live();
+	bool first = true; T r = v;
+	for (int i = 0; i < 32; i++) if ((live >> i) & 1u) { T x = emu::from_bits<T>(s[i]); r = first ? x : f(r, x); first = false; }
+	emu::warp_sync(line, file);
+	return r;
+}
+inline unsigned __reduce_or_sync(unsigned, unsigned v, EMU_SITE){ return emu_reduce(v, [](unsigned a, unsigned b){ return a | b; }, line, file); }
+inline unsigned __reduce_and_sync(unsigned, unsigned v, EMU_SITE){ return emu_reduce(v, [](unsigned a, unsigned b){ return a & b; }, line, file); }
+inline unsigned __reduce_add_sync(unsigned, unsigned v, EMU_SITE){ return emu_reduce(v, [](unsigned a, unsigned b){ return a+b; }, line, file); }
+inline int __reduce_add_sync(unsigned, int v, EMU_SITE){ return emu_reduce(v, [](int a, int b){ return a+b; }, line, file); }
+inline unsigned __reduce_min_sync(unsigned, unsigned v, EMU_SITE){ return emu_reduce(v, [](unsigned a, unsigned b){ return a < b ? a : b; }, line, file); }
+inline int __reduce_min_sync(unsigned, int v, EMU_SITE){ return emu_reduce(v, [](int a, int b){ return a < b ? a : b; }, line, file); }
+inline unsigned __reduce_max_sync(unsigned, unsigned v, EMU_SITE){ return emu_reduce(v, [](unsigned a, unsigned b){ return a > b ? a : b; }, line, file); }
+inline int __reduce_max_sync(unsigned, int v, EMU_SITE){ return emu_reduce(v, [](int a, int b){ return a > b ? a : b; }, line, file); }
 inline void __threadfence(void){ __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block(void){ __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 /* ---------------------------------------------------------------- scalar intrinsics */
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel){
+	const uint64_t src = ((uint64_t)y << 32) | x;
+	unsigned r = 0;
+	for (int i = 0; i < 4; i++) { const unsigned n = (sel >> (4*i)) & 0xF; unsigned b = (unsigned)(src >> (8*(n & 7))) & 0xFF; if (n & 8) b = (b & 0x80) ? 0xFF : 0; r |= b << (8*i); }
+	return r;
+}
 inline int __popc(unsigned v){ return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v){ return __builtin_popcountll(v); }
 inline int __ffs(int v){ return __builtin_ffs(v); }

@@ -1,7 +1,6 @@
 // tests/emul/emu.cpp — TEST INFRASTRUCTURE: the runtime behind tests/emul/cuda_runtime.h (see there).
 #include "cuda_runtime.h"
 #include <stdio.h>
-#include <ucontext.h>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -13,8 +12,38 @@
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 
+// The context switch between fibers: the callee-saved registers and the stack pointer (x86-64 System V).  swapcontext would do,
+// but it saves and restores the signal mask with two system calls per switch, and a collective of one warp is 128 switches.
+#if defined(__x86_64__)
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+	pushq %rbp
+	pushq %rbx
+	pushq %r12
+	pushq %r13
+	pushq %r14
+	pushq %r15
+	movq %rsp, (%rdi)
+	movq %rsi, %rsp
+	popq %r15
+	popq %r14
+	popq %r13
+	popq %r12
+	popq %rbx
+	popq %rbp
+	ret
+.size emu_switch,.-emu_switch
+)");
+#else
+#error "tests/emul needs an x86-64 host (emu_switch)"
+#endif
+
 namespace emu {
-// One CUDA thread = one fiber (ucontext) of the calling OS thread; the threads of a block are scheduled one at a time, each
+// One CUDA thread = one fiber of the calling OS thread; the threads of a block are scheduled one at a time, each
 // running until it finishes or reaches a rendezvous (a warp collective, __syncthreads, the two ends of an `L0 { }` block).  The
 // schedule is deterministic: between two rendezvous the threads take their turn in index order (EMU_ORDER=rev: highest first).
 // Code whose lanes only communicate through rendezvous gives the same answer in both orders; the goldens are run in both.
@@ -25,7 +54,7 @@ struct Rendezvous {
 	uint64_t tag = 0; bool tag_set = false; int t_line = 0; const char *t_file = "";
 };
 struct Fiber {
-	ucontext_t ctx; void *stack = nullptr; size_t stack_size = 0;
+	void *sp = nullptr; void *stack = nullptr; size_t stack_size = 0;
 	bool done = false;
 	Rendezvous *waiting = nullptr; unsigned wait_gen = 0; int w_line = 0; const char *w_file = "";
 	unsigned tid = 0; uint64_t n_warp = 0, n_block = 0;
@@ -34,7 +63,7 @@ struct Fiber {
 struct Warp { Rendezvous bar; uint64_t slots[32]; unsigned live = 0; };
 struct Block {
 	Rendezvous bar; std::vector<Warp> warps; std::vector<uint64_t> dyn; std::vector<Fiber> fibers;
-	ucontext_t sched; void *sched_fake = nullptr;
+	void *sched_sp = nullptr; void *sched_fake = nullptr;
 	const void *sched_bottom = nullptr; size_t sched_size = 0;
 	const std::function<void()> *body = nullptr; dim3 block, grid; unsigned bidx = 0; const char *kernel = "";
 	Fiber *cur = nullptr;
@@ -58,7 +87,7 @@ static void need_threads(const char *what){
 static void to_scheduler(bool dying){
 	Fiber *f = B->cur;
 	SWITCH_BEGIN(dying ? nullptr : &f->fake, B->sched_bottom, B->sched_size);
-	swapcontext(&f->ctx, &B->sched);
+	emu_switch(&f->sp, B->sched_sp);
 	SWITCH_END(f->fake, nullptr, nullptr);
 }
 static void set_ids(const Fiber *f){
@@ -99,7 +128,7 @@ void *dyn_smem(void){ need_threads("dynamic shared memory"); return B->dyn.data(
 // kernels whose threads meet (warp collectives, __syncthreads, shared memory): one fiber per CUDA thread, blocks one after the
 // other.  Everything else is plain data-parallel code and runs its threads one after the other as plain calls.
 static const std::set<std::string> threaded = { "k_run_seq", "k_init_groups", "k_exec_ops", "k_stream_hash", "k_ens_drain", "k_ens_digest",
-	"k_pick", "k_pick_small", "k_ana" };
+	"k_pick", "k_pick_small", "k_ana", "k_run_ens" };
 // grid-stride kernels whose result does not depend on the grid: fewer blocks, same answer
 static unsigned clamp_grid(const std::string &k, unsigned g){ if (k == "k_stream_hash") return 1; return g; }
 // The order in which the threads of a block take their turn between two rendezvous: lowest first, or EMU_ORDER=rev.
@@ -111,6 +140,10 @@ static bool lanes_forward(const std::string &){
 	return !(e && !strcmp(e, "rev"));
 }
 #define EMU_STACK (4u << 20)
+// fiber stacks are reused from launch to launch (the host core launches a kernel per event)
+static thread_local std::vector<void *> stack_pool;
+static void *stack_get(void){ if (stack_pool.empty()) return malloc(EMU_STACK); void *p = stack_pool.back(); stack_pool.pop_back(); return p; }
+static void stack_put(void *p){ if (stack_pool.size() < 512) stack_pool.push_back(p); else free(p); }
 
 void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body){
 	const std::string name(kernel);
@@ -141,10 +174,13 @@ void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const st
 		B = &blk;
 		for (unsigned t = 0; t < nt; t++) {
 			Fiber &f = blk.fibers[t];
-			f.tid = t; f.stack_size = EMU_STACK; f.stack = malloc(f.stack_size);
-			getcontext(&f.ctx);
-			f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = f.stack_size; f.ctx.uc_link = nullptr;
-			makecontext(&f.ctx, fiber_main, 0);
+			f.tid = t; f.stack_size = EMU_STACK; f.stack = stack_get();
+			// a fresh fiber "returns" from emu_switch into fiber_main: six zeroed registers, the entry point, a null return address
+			uintptr_t top = ((uintptr_t)f.stack+f.stack_size) & ~(uintptr_t)15;
+			void **sp = (void **)(top-64);
+			for (int k = 0; k < 6; k++) sp[k] = nullptr;
+			sp[6] = (void *)fiber_main; sp[7] = nullptr;
+			f.sp = sp;
 		}
 		unsigned left = nt;
 		while (left) {
@@ -155,11 +191,11 @@ void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const st
 				if (f.waiting) { if (f.waiting->gen == f.wait_gen) continue; f.waiting = nullptr; }
 				blk.cur = &f;
 				SWITCH_BEGIN(&blk.sched_fake, f.stack, f.stack_size);
-				swapcontext(&blk.sched, &f.ctx);
+				emu_switch(&blk.sched_sp, f.sp);
 				SWITCH_END(blk.sched_fake, nullptr, nullptr);
 				blk.cur = nullptr;
 				progress = true;
-				if (f.done) { left--; free(f.stack); f.stack = nullptr; }
+				if (f.done) { left--; stack_put(f.stack); f.stack = nullptr; }
 			}
 			if (!progress) {
 				fprintf(stderr, "emu: %s block %u: dead-lock, %u threads wait for a rendezvous the others never reach:\n", kernel, b, left);

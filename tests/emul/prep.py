@@ -52,12 +52,14 @@ def rewrite(src: str) -> str:
         at = end + 1
     out += src[at:]
     # dynamic shared memory: `extern __shared__ T name[];` -> a pointer into the block's buffer
+    out = re.sub(r"extern\s+__shared__\s+__align__\(\d+\)\s+unsigned char\s+(\w+)\s*\[\s*\]\s*;", r"unsigned char *\1 = (unsigned char *)emu::dyn_smem();", out)
     return re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"\1 *\2 = (\1 *)emu::dyn_smem();", out)
 
 
 def no_ptx(src: str) -> str:
     """inline PTX has no meaning here: the prefetch hint of ns_model.cuh becomes a no-op (its address computations stay)"""
     src = src.replace('asm volatile("prefetch.global.L1 [%0];" :: "l"(p));', "(void)p;")
+    src = src.replace('asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));', "t = 0;")          # (profiling builds only)
     # lane 0 acting for the warp: rendezvous around the block (cuda_runtime.h, L0Guard)
     return src.replace("#define L0 if (c.scalar || c.lane == 0)", "#define L0 EMU_L0")
 

@@ -4,7 +4,7 @@ pickers, the analyzer kernel and the host layer, compiled for the lock-step warp
 committed goldens of the compiled reference and against the CPU oracle.  Prints one JSON line per check; any sanitizer report
 aborts the process.
 
-    python run_checks.py goldens:test00,test05 random:0,1 windows ensemble picks malformed args"""
+    python run_checks.py goldens:test00,test05 random:0,1 windows ensemble ensemble_cta picks malformed args"""
 import json
 import os
 import sys
@@ -122,6 +122,36 @@ def ensemble():
     ens.close()
 
 
+def ensemble_cta(n_events=1500):
+    """the batch engine at CTA scope (k_run_ens = ns_par_kernel.inc with __syncthreads barriers: ordered extraction, radix partition by
+    (node, dir) group, one thread / one warp / the whole CTA per group, staged event_adds and records, ordered commit): small replicas,
+    and a 300-peer swarm whose first timestamps are batches of hundreds of events with hub spreads"""
+    t0 = time.time()
+    scs = [S.random_small(300 + i, n_nodes=7, n_flows=10).to_bytes() for i in range(3)]
+    ens = E.Ensemble(scs, mode=E.MODE_AUTO)
+    ens.run(0)
+    ok = True
+    for d, b in zip(ens.digests(), scs):
+        o = pyoracle.Oracle(b)
+        so = o.run(0)
+        ok = ok and d["status"] == -so and (so != 0 or (d["events"] == o.counters()["events"] and d["record_hash"] == E.stream_hash(o.records())))
+        o.close()
+    out("ensemble (CTA engine): small replicas", ok, t0)
+    ens.close()
+    t0 = time.time()
+    b = S.swarm(300, 3, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0, res_len=30000, seed=50).to_bytes()
+    ens = E.Ensemble([b], mode=E.MODE_AUTO, record_cap=1 << 18, ring_cap=1 << 18)
+    ens.run(n_events)
+    d, cs = ens.digests()[0], ens.counters_sum()
+    o = pyoracle.Oracle(b, trace=False)
+    ok = o.run(n_events) == 0 and d["status"] == 0 and d["events"] == o.counters()["events"] == n_events and d["record_bytes"] == len(o.records()) \
+        and d["record_hash"] == E.stream_hash(o.records()) and all(cs[k] == o.counters()[k] for k in ("solves", "full_spreads", "flow_visits", "draws", "seq"))
+    ok = ok and cs["par_events"] == n_events and cs["max_batch"] > 256 and cs["full_spreads"] > 100      # it really went through the parallel pieces
+    out("ensemble (CTA engine): swarm batches of hundreds of events", ok, t0, max_batch=cs["max_batch"], full_spreads=cs["full_spreads"])
+    ens.close()
+    o.close()
+
+
 def picks():
     from conftest import pick_golden
     t0 = time.time()
@@ -212,4 +242,4 @@ if __name__ == "__main__":
         elif name == "random":
             random_scripts([int(x) for x in arg.split(",")])
         else:
-            {"windows": windows, "ensemble": ensemble, "picks": picks, "malformed": malformed, "args": args}[name]()
+            {"windows": windows, "ensemble": ensemble, "ensemble_cta": ensemble_cta, "picks": picks, "malformed": malformed, "args": args}[name]()

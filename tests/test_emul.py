@@ -51,7 +51,7 @@ def test_goldens_on_the_lockstep_model(model):
             ["goldens:rand11,rand13,rand2,rand3"], ["goldens:rand55,rand7,rand89,relay1,relay16"], ["goldens:relay12,relay4,relay6,relay9"],
             ["goldens:churn150"], ["goldens:clients_play40"]]
     res = parallel(model, jobs)
-    assert len(res) == 33 - 4            # all but swarm200 and the three long client fixtures (NS_SLOW below)
+    assert len(res) == 33 - 4            # all but swarm200 and the three long client fixtures (next test)
 
 
 def test_lane_schedule_does_not_matter(model):
@@ -67,8 +67,17 @@ def test_engine_paths_on_the_lockstep_model(model):
     parallel(model, [["windows"], ["ensemble"], ["picks", "malformed", "args"], ["random:0,3,7"], ["random:12,20,29"]])
 
 
-@pytest.mark.skipif(not os.environ.get("NS_SLOW"), reason="minutes: NS_SLOW=1")
+def test_batch_engine_at_cta_scope_on_the_lockstep_model(model):
+    """k_run_ens — the batch engine of ns_par_kernel.inc with one CTA per replica (the code the grid-scope k_run_par shares: ordered
+    extraction, radix partition by (node, dir) group, thread / warp / CTA solves, staged event_adds and records, ordered commit) —
+    with 256 fibers per CTA under ASan + UBSan: a 300-peer swarm whose first timestamps are batches of up to 552 events with 789
+    full spreads, digest and counters equal to the oracle's"""
+    run(model, "ensemble_cta")
+
+
 def test_long_goldens_on_the_lockstep_model(model):
+    """swarm200 (3 933 events, the one-event-per-lane path on batches of dozens of events) and the three long client-behaviour
+    fixtures (client_new_play1 with the picker in the loop, the water-mark machine, node-state records): 1.3 - 3.9 k events each"""
     parallel(model, [["goldens:swarm200"], ["goldens:clients_cut"], ["goldens:clients_distance"], ["goldens:clients_saturated"]], timeout=3000)
 
 
@@ -88,8 +97,8 @@ def _netsim_dev(model, module, cwd, extra_preload=(), env_extra=None, timeout=90
 
 
 def test_unmodified_reference_modules_through_the_host_core_on_the_model(model):
-    """the reference's own test00-05.c, test_client2/3.c + client_behaviour.c and p2p.c + cloud_behaviour.c (tests/golden/p2p/small50),
-    compiled unchanged against netsim_b200/host/include, with every device call of the host core (k_exec_ops, k_run_seq in
+    """the reference's own test00-05.c, test_client2/3.c + client_behaviour.c and p2p.c + cloud_behaviour.c (tests/golden/p2p: servers only,
+    resource eviction, client-to-client relays, smart cloud, cloud pushes), compiled unchanged against netsim_b200/host/include, with every device call of the host core (k_exec_ops, k_run_seq in
     host-callback mode, the mirror view, the shared random() stream) answered by the device code on the lock-step model under
     ASan + UBSan: stderr and record files byte-identical to the reference's"""
     import hashlib
@@ -120,7 +129,7 @@ def test_unmodified_reference_modules_through_the_host_core_on_the_model(model):
             assert hashlib.sha256(err).hexdigest() == exp["stderr_sha256"], cfg
         return cfg
 
-    cfgs = ["small50"] + (["evict3", "play2c", "cloudc", "push2"] if os.environ.get("NS_SLOW") else [])
+    cfgs = ["small50", "evict3", "play2c", "cloudc", "push2"]
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "timeshim.so")):
         cfgs = []
     with ThreadPoolExecutor(max_workers=8) as ex:
