@@ -1,4 +1,8 @@
-/* tests/emul/cooperative_groups.h — TEST INFRASTRUCTURE: ns_par_dev.cuh includes <cooperative_groups.h> for the grid-scope engine's
- * grid_group; the lock-step model only compiles the CTA scope (NS_SCOPE_CTA), where the type is never used. */
+/* tests/emul/cooperative_groups.h — TEST INFRASTRUCTURE: the grid group of a cooperative launch on the lock-step model
+ * (cuda_runtime.h, emu.cpp): sync() is a rendezvous of every live thread of every block. */
 #pragma once
-namespace cooperative_groups { struct grid_group { void sync(); }; }
+#include "cuda_runtime.h"
+namespace cooperative_groups {
+struct grid_group { void sync() const { emu::grid_sync(); } };
+inline grid_group this_grid(){ return grid_group(); }
+}

@@ -37,7 +37,7 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local      /* one OS thread runs one block at a time (emu.cpp): per-block storage */
 #define __restrict__
 
 struct uint3 { unsigned x, y, z; };
@@ -85,11 +85,17 @@ cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d);
 template <typename F> cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, F){ a->numRegs = 0; return cudaSuccess; }
 template <typename F> cudaError_t cudaFuncSetAttribute(F, int, int){ return cudaSuccess; }
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, const void *, int, size_t){ *n = 1; return cudaSuccess; }
+/* cooperative launches: the kernel arrives as a bare pointer, so the kernels that are launched this way register an invoker (coop.cpp) */
+cudaError_t cudaLaunchCooperativeKernel(const void *kernel, dim3 grid, dim3 block, void **args, size_t dyn_smem, cudaStream_t s);
 cudaError_t cudaGetDevice(int *d);
 
 /* ---------------------------------------------------------------- launches and rendezvous */
 namespace emu {
 void launch(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body);
+void launch_coop(const char *kernel, dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body);   /* every block alive at once: one OS thread per block */
+void register_coop(const void *kernel, const char *name, std::function<void(void **)> invoke);
+void grid_sync(void);                       /* every live thread of every block of a cooperative launch */
 void *dyn_smem(void);                       /* `extern __shared__ T x[];` of the calling thread's block */
 void warp_sync(int line = 0, const char *file = "");   /* every live lane of the calling thread's warp; (line, file) = the call site, which must be the same for all of them */
 void block_sync(void);                      /* every live thread of the block */

@@ -1,10 +1,10 @@
 """tests/emul/run_checks.py — TEST INFRASTRUCTURE.  Runs inside a process that has loaded tests/emul/_build/libnetsim_emul.so in
 place of the CUDA library (NS_LIB) with the AddressSanitizer runtime preloaded: the device code of the single-warp engine, the
-pickers, the analyzer kernel and the host layer, compiled for the lock-step warp model (cuda_runtime.h here), against the
+pickers, the analyzer kernel and the host layer, and both scopes of the batch engine, compiled for the lock-step warp model (cuda_runtime.h here), against the
 committed goldens of the compiled reference and against the CPU oracle.  Prints one JSON line per check; any sanitizer report
 aborts the process.
 
-    python run_checks.py goldens:test00,test05 random:0,1 windows ensemble ensemble_cta picks malformed args"""
+    python run_checks.py goldens:test00,test05 random:0,1 windows ensemble ensemble_cta grid picks malformed args      (EMU_SMS=3: CTAs of the grid engine)"""
 import json
 import os
 import sys
@@ -152,6 +152,31 @@ def ensemble_cta(n_events=1500):
     o.close()
 
 
+def grid(n_events=0):
+    """the grid-scope batch engine (k_run_par / k_run_par_cl: cooperative launch, grid barriers, EMU_SMS CTAs of 256 threads) and the
+    parallel module init (k_init_par: CREATE ops in conflict-free waves): goldens with NS_MODE_AUTO, and a 300-peer swarm run to
+    completion — batches of up to 552 events, hub spreads, then FLOW_DONE / close / merge pieces and the hand-over to k_run_seq"""
+    for n in ("test04", "test05", "rand2", "rand55", "relay9", "edge_end_and_closes", "churn150", "clients_play40"):
+        t0 = time.time()
+        z = np.load(os.path.join(ROOT, "tests", "golden", n + ".npz"))
+        e = E.Engine(z["scenario"].tobytes(), mode=E.MODE_AUTO, records=True, trace=True)
+        ok = e.run(0) == 0 and e.records() == z["records"].tobytes() and e.trace().tobytes() == z["trace"].tobytes()
+        out("grid engine: golden " + n, ok, t0)
+        e.close()
+    t0 = time.time()
+    b = S.swarm(300, 3, n_catalogue=6, seeds_per_peer=3, mean_strips=4.0, res_len=30000, seed=50).to_bytes()
+    o = pyoracle.Oracle(b)
+    assert o.run(n_events) == 0
+    e = E.Engine(b, mode=E.MODE_AUTO, records=True, trace=True, trace_cap=100000)
+    ok = e.run(n_events) == 0
+    ce, co = e.counters(), o.counters()
+    ok = ok and e.records() == o.records() and e.trace().tobytes() == o.trace().tobytes() and all(ce[k] == co[k] for k in KEYS)
+    ok = ok and ce["waves"] > 0 and ce["par_events"] > 5000 and ce["max_batch"] > 256 and ce["flow_done"] > 500        # parallel init, parallel pieces, completions
+    out("grid engine: 300-peer swarm to completion", ok, t0, events=ce["events"], par_events=ce["par_events"], max_batch=ce["max_batch"], launches=e.launches)
+    e.close()
+    o.close()
+
+
 def picks():
     from conftest import pick_golden
     t0 = time.time()
@@ -242,4 +267,4 @@ if __name__ == "__main__":
         elif name == "random":
             random_scripts([int(x) for x in arg.split(",")])
         else:
-            {"windows": windows, "ensemble": ensemble, "ensemble_cta": ensemble_cta, "picks": picks, "malformed": malformed, "args": args}[name]()
+            {"windows": windows, "ensemble": ensemble, "ensemble_cta": ensemble_cta, "grid": grid, "picks": picks, "malformed": malformed, "args": args}[name]()

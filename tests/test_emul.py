@@ -26,10 +26,12 @@ def model(built):
     return dict(os.environ, NS_LIB=LIB, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
 
 
-def run(env, *checks, order=None, timeout=900):
+def run(env, *checks, order=None, sms=None, timeout=900):
     env = dict(env)
     if order:
         env["EMU_ORDER"] = order
+    if sms:
+        env["EMU_SMS"] = str(sms)
     p = subprocess.run([sys.executable, os.path.join(EMUL, "run_checks.py"), *checks], env=env, capture_output=True, text=True, timeout=timeout)
     err = "\n".join(ln for ln in p.stderr.splitlines() if "doesn't fully support makecontext" not in ln)
     assert p.returncode == 0 and "AddressSanitizer" not in err and "runtime error" not in err and "emu:" not in err, err[-3000:]
@@ -79,6 +81,17 @@ def test_long_goldens_on_the_lockstep_model(model):
     """swarm200 (3 933 events, the one-event-per-lane path on batches of dozens of events) and the three long client-behaviour
     fixtures (client_new_play1 with the picker in the loop, the water-mark machine, node-state records): 1.3 - 3.9 k events each"""
     parallel(model, [["goldens:swarm200"], ["goldens:clients_cut"], ["goldens:clients_distance"], ["goldens:clients_saturated"]], timeout=3000)
+
+
+def test_grid_engine_on_the_lockstep_model(model):
+    """k_run_par / k_run_par_cl (cooperative launch, grid barriers) and k_init_par (the parallel module init) with 1, 3 and 4 CTAs of 256
+    threads — one OS thread per CTA, so the CTAs really run side by side and only meet at grid.sync() — under ASan + UBSan: goldens
+    with NS_MODE_AUTO, and a 300-peer swarm to completion (parallel init in waves, batches of up to 552 events through the radix
+    partition / thread, warp and CTA solves / ordered commit, then completions, closes, merges and the hand-over to the one-warp
+    engine): records, fp64 traces and counters equal to the oracle's, whatever the number of CTAs and the lane order"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=3) as ex:
+        list(ex.map(lambda kw: run(model, "grid", **kw), [dict(sms=3), dict(sms=1), dict(sms=4, order="rev")]))
 
 
 HOST = os.path.join(ROOT, "netsim_b200", "host", "_build")
