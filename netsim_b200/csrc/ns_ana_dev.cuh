@@ -80,9 +80,10 @@ __device__ __noinline__ void ana_process(AnaStream &A, uint8_t *tile, int *start
 			const unsigned before = peers & ((1u << lane)-1u);
 			const int pl = before ? 31-__clz(before) : -1;            // previous record of the same (node, dir) in this tile
 			const double pt_l = __shfl_sync(FULL, t, pl < 0 ? lane : pl), pv_l = __shfl_sync(FULL, val, pl < 0 ? lane : pl);
+			double pt = pt_l, pv = pv_l;
+			if (us && pl < 0) { pt = A.u_time[dir][node]; pv = A.u_val[dir][node]; }   // first of its (node, dir) in the tile: the table
+			__syncwarp();                                             // every lane has read the table before any lane writes it back
 			if (us) {
-				double pt, pv;
-				if (pl >= 0) { pt = pt_l; pv = pv_l; } else { pt = A.u_time[dir][node]; pv = A.u_val[dir][node]; }
 				const int cls = A.ntype[node];
 				ana_spread(A.st->usage[cls][dir], nb, period, pt, t, pv);
 				if (!(peers & ~((2u << lane)-1u))) { A.u_time[dir][node] = t; A.u_val[dir][node] = val; }   // last of its (node, dir) in the tile
@@ -97,9 +98,10 @@ __device__ __noinline__ void ana_process(AnaStream &A, uint8_t *tile, int *start
 			const int ps_l = __shfl_sync(FULL, u8v, pl < 0 ? lane : pl);
 			const double pt_l = __shfl_sync(FULL, t, pl < 0 ? lane : pl);
 			int delta = 0;
+			int ps = ps_l; double pt = pt_l;
+			if (sr && pl < 0) { ps = A.n_state[node]; pt = A.n_since[node]; }
+			__syncwarp();                                             // (as above: gather, then update)
 			if (sr) {
-				int ps; double pt;
-				if (pl >= 0) { ps = ps_l; pt = pt_l; } else { ps = A.n_state[node]; pt = A.n_since[node]; }
 				if (ps == 1) ana_spread(A.st->stale, nb, period, pt, t, 1.0);          // was N_STALE since pt
 				if (ps != u8v) delta = (u8v == 1) - (ps == 1);                            // analyzers.c:411-424
 				if (!(peers & ~((2u << lane)-1u))) { A.n_state[node] = (int8_t)u8v; A.n_since[node] = t; }

@@ -143,10 +143,9 @@ static const std::set<std::string> threaded = { "k_run_seq", "k_init_groups", "k
 	"k_pick", "k_pick_small", "k_ana", "k_run_ens" };
 // grid-stride kernels whose result does not depend on the grid: fewer blocks, same answer
 static unsigned clamp_grid(const std::string &k, unsigned g){ if (k == "k_stream_hash") return 1; return g; }
-// The order in which the threads of a block take their turn between two rendezvous: lowest first, or EMU_ORDER=rev.
-// One place is known to depend on it (tests/emul/README.md): ana_process (ns_ana_dev.cuh) gathers each node's previous record from
-// a table and lets the LAST record of that node in the tile — a higher lane — write the table back with no __syncwarp in between;
-// a converged warp does all the reads first, which lowest-first reproduces and highest-first does not.
+// The order in which the threads of a block take their turn between two rendezvous: lowest first, or EMU_ORDER=rev.  (It found one
+// place that depended on it — ana_process read a per-node table and wrote it back with no __syncwarp in between — since fixed;
+// tests/emul/README.md.)
 static bool lanes_forward(const std::string &){
 	const char *e = getenv("EMU_ORDER");
 	return !(e && !strcmp(e, "rev"));

@@ -122,6 +122,30 @@ def ensemble():
     ens.close()
 
 
+def analysis():
+    """tests/test_analysis.py::test_device_reductions_match_the_restatement on the model: the four client-behaviour fixtures as replicas
+    of one ensemble with small record buffers (folded in the kernel many times), two periods, one-warp and CTA engines"""
+    from oracle import pyanalyze
+    names = ("clients_cut", "clients_distance", "clients_play40", "clients_saturated")
+    zs = [np.load(os.path.join(ROOT, "tests", "golden", n + ".npz")) for n in names]
+    scs, recs = [z["scenario"].tobytes() for z in zs], [z["records"].tobytes() for z in zs]
+    for mode, mname in ((E.MODE_SEQ, "one warp per replica"), (E.MODE_AUTO, "one CTA per replica")):
+        for period in (3600.0, 7.5):
+            t0 = time.time()
+            ens = E.Ensemble(scs, mode=mode, record_cap=1 << 14, ring_cap=1 << 14)
+            ens.analysis_begin(period)
+            ens.run(0)
+            dg, an = ens.digests(), ens.analysis()
+            ok = True
+            for d, a, rec in zip(dg, an, recs):
+                s = pyanalyze.summarize(rec, period)
+                ok = ok and d["status"] == 0 and d["record_hash"] == E.stream_hash(rec)
+                ok = ok and all(a[k] == s[k] for k in ("records", "usage_records", "state_records", "stale_now", "stale_max")) and a["t_last"] == s["t_last"]
+                ok = ok and np.allclose(a["usage"], s["usage"], rtol=1e-9, atol=1e-6) and np.allclose(a["stale"], s["stale"], rtol=1e-9, atol=1e-9)
+            out(f"analysis on the device: {mname}, period {period}", ok, t0, records=int(sum(a["records"] for a in an)))
+            ens.close()
+
+
 def ensemble_cta(n_events=1500):
     """the batch engine at CTA scope (k_run_ens = ns_par_kernel.inc with __syncthreads barriers: ordered extraction, radix partition by
     (node, dir) group, one thread / one warp / the whole CTA per group, staged event_adds and records, ordered commit): small replicas,
@@ -267,4 +291,4 @@ if __name__ == "__main__":
         elif name == "random":
             random_scripts([int(x) for x in arg.split(",")])
         else:
-            {"windows": windows, "ensemble": ensemble, "ensemble_cta": ensemble_cta, "grid": grid, "picks": picks, "malformed": malformed, "args": args}[name]()
+            {"windows": windows, "ensemble": ensemble, "ensemble_cta": ensemble_cta, "analysis": analysis, "grid": grid, "picks": picks, "malformed": malformed, "args": args}[name]()

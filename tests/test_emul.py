@@ -59,14 +59,14 @@ def test_goldens_on_the_lockstep_model(model):
 def test_lane_schedule_does_not_matter(model):
     """the same device code with the lanes taking their turn highest-first instead of lowest-first between two rendezvous: code
     whose lanes only communicate through collectives / __syncwarp gives the same bytes (the fp64 traces included)"""
-    parallel(model, [["goldens:test04,test05,rand2,rand7"], ["goldens:rand55,relay9,relay1"], ["random:1,4"]], order="rev")
+    parallel(model, [["goldens:test04,test05,rand2,rand7"], ["goldens:rand55,relay9,relay1"], ["random:1,4"], ["ensemble", "analysis"]], order="rev")
 
 
 def test_engine_paths_on_the_lockstep_model(model):
     """stop / resume inside a batch, soft stop + drain of a small record buffer, ensembles with in-kernel record folding and the
     analyzer kernel, the pickers against the reference's own qselect tables, random scripts (relays included, and the scripts on
     which the reference aborts) against the oracle, the C ABI's refusals"""
-    parallel(model, [["windows"], ["ensemble"], ["picks", "malformed", "args"], ["random:0,3,7"], ["random:12,20,29"]])
+    parallel(model, [["windows"], ["ensemble"], ["analysis"], ["picks", "malformed", "args"], ["random:0,3,7"], ["random:12,20,29"]])
 
 
 def test_batch_engine_at_cta_scope_on_the_lockstep_model(model):
