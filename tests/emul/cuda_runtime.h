@@ -37,7 +37,11 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#ifdef EMU_THREADS
+#define __shared__ static                   /* emu_threads.cpp: one OS thread per CUDA thread, one block at a time */
+#else
 #define __shared__ static thread_local      /* one OS thread runs one block at a time (emu.cpp): per-block storage */
+#endif
 #define __restrict__
 
 struct uint3 { unsigned x, y, z; };
