@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128) k_pick(int mode, int n_req, const int32_t
 		// first strict minimum == minimum of (val, index) pairs
 		long long best = 0x7fffffffffffffffLL;
 		for (int i = lane; i < c; i += 32) {
-			long long key = ((long long)val[lo+i] << 32) | (unsigned)i;
+			long long key = (long long)val[lo+i]*4294967296LL | (unsigned)i;   // (value, index) as one key; a multiplication, not << 32: the value may be negative
 			if (val[lo+i] != INT32_MAX && key < best) best = key;
 		}
 		for (int d = 16; d; d >>= 1) { long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
