@@ -4,7 +4,8 @@ pickers, the analyzer kernel and the host layer, and both scopes of the batch en
 committed goldens of the compiled reference and against the CPU oracle.  Prints one JSON line per check; any sanitizer report
 aborts the process.
 
-    python run_checks.py goldens:test00,test05 random:0,1 windows ensemble ensemble_cta grid picks malformed args      (EMU_SMS=3: CTAs of the grid engine)"""
+    python run_checks.py goldens:test00,test05 random:0,1 live:2,5 windows ensemble ensemble_cta analysis grid picks malformed args
+    (EMU_SMS=3: CTAs of the grid engine; EMU_MODE=auto: random / live on the grid engine; EMU_ORDER=rev: lanes highest-first)"""
 import json
 import os
 import sys
@@ -48,7 +49,7 @@ def random_scripts(seeds):
             b = sc.to_bytes()
             o = pyoracle.Oracle(b)
             so = o.run(0)
-            e = E.Engine(b, mode=E.MODE_SEQ, records=True, trace=True)
+            e = E.Engine(b, mode=E.MODE_AUTO if os.environ.get("EMU_MODE") == "auto" else E.MODE_SEQ, records=True, trace=True)   # EMU_MODE=auto: the grid engine
             se = e.run(0)
             ok = se == -so
             if so == 0:
@@ -60,6 +61,37 @@ def random_scripts(seeds):
             out(f"random {seed} relay={int(relay)}", ok, t0, status=se)
             e.close()
             o.close()
+
+
+def live(seeds):
+    """fresh scripts — client behaviour (client_new_play1 + the water-mark machine), churn, swarms to completion — with the COMPILED
+    REFERENCE run live beside the device code on the model (EMU_MODE=auto: the grid engine): records and event counts"""
+    from oracle import refrun
+    if not refrun.available():
+        out("live reference: oracle/_ref not built", True, time.time())
+        return
+    mode = E.MODE_AUTO if os.environ.get("EMU_MODE") == "auto" else E.MODE_SEQ
+    for seed in seeds:
+        cases = {
+            "p2p_clients": S.p2p_clients(40 + 7 * seed, 2 + seed % 5, n_catalogue=3 + seed % 4, play_seconds=60.0 + 10 * seed, arrival_window=8.0,
+                                         arrival_quantum=0.05 * (1 + seed % 3), metric=seed % 2, seed=100 + seed, rand_seed=1 + seed),
+            "churn": S.churn(n_users=120 + 10 * seed, n_servers=3 + seed % 3, rate=200.0, mean_session=0.4, quantum=0.01, res_len=200000, seed=2024 + seed, sim_end=1.5),
+            "swarm": S.swarm(50 + 5 * seed, 2, n_catalogue=4, seeds_per_peer=2, mean_strips=2.0 + seed % 3, res_len=20000, seed=77 + seed),
+        }
+        for name, sc in cases.items():
+            t0 = time.time()
+            b = sc.to_bytes()
+            saved = os.environ.pop("LD_PRELOAD", None)          # the reference runs without the sanitizer runtime
+            try:
+                r = refrun.run_reference(b, trace=False, record=True)
+            finally:
+                if saved is not None:
+                    os.environ["LD_PRELOAD"] = saved
+            e = E.Engine(b, mode=mode, records=True)
+            st = e.run(0)
+            ok = r["returncode"] == 0 and st == 0 and e.records() == r["records"] and e.counters()["events"] == r["stats"]["events"]
+            out(f"live reference: {name} seed {seed}", ok, t0, events=e.counters()["events"])
+            e.close()
 
 
 def windows():
@@ -290,5 +322,7 @@ if __name__ == "__main__":
             goldens(arg.split(","))
         elif name == "random":
             random_scripts([int(x) for x in arg.split(",")])
+        elif name == "live":
+            live([int(x) for x in arg.split(",")])
         else:
             {"windows": windows, "ensemble": ensemble, "ensemble_cta": ensemble_cta, "analysis": analysis, "grid": grid, "picks": picks, "malformed": malformed, "args": args}[name]()

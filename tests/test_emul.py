@@ -26,12 +26,14 @@ def model(built):
     return dict(os.environ, NS_LIB=LIB, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
 
 
-def run(env, *checks, order=None, sms=None, timeout=900):
+def run(env, *checks, order=None, sms=None, auto=False, timeout=900):
     env = dict(env)
     if order:
         env["EMU_ORDER"] = order
     if sms:
         env["EMU_SMS"] = str(sms)
+    if auto:
+        env["EMU_MODE"] = "auto"
     p = subprocess.run([sys.executable, os.path.join(EMUL, "run_checks.py"), *checks], env=env, capture_output=True, text=True, timeout=timeout)
     err = "\n".join(ln for ln in p.stderr.splitlines() if "doesn't fully support makecontext" not in ln)
     assert p.returncode == 0 and "AddressSanitizer" not in err and "runtime error" not in err and "emu:" not in err, err[-3000:]
@@ -52,6 +54,7 @@ JOBS = {
               (["ensemble", "analysis"], dict(order="rev"))],
     "paths": [(["windows"], {}), (["ensemble"], {}), (["analysis"], {}), (["picks", "malformed", "args"], {}), (["random:0,3,7"], {}), (["random:12,20,29"], {})],
     "cta": [(["ensemble_cta"], {})],
+    "live": [(["live:2,5,9"], {}), (["live:3,6,10", "random:2,9,17"], dict(auto=True, sms=3))],
     "grid": [(["grid"], dict(sms=3)), (["grid"], dict(sms=1)), (["grid"], dict(sms=4, order="rev"))],
 }
 HOST = os.path.join(ROOT, "netsim_b200", "host", "_build")
@@ -111,7 +114,7 @@ def started(model):
     # longest first: the pool is never left waiting for one late straggler
     if _host_ready():
         fut["host"] = [ex.submit(_host_p2p, model, c) for c in reversed(HOST_CFGS)] + [ex.submit(_host_module, model, m) for m in HOST_MODS]
-    for k in ("grid", "lanes", "paths", "long", "cta", "goldens"):
+    for k in ("grid", "lanes", "paths", "long", "cta", "live", "goldens"):
         fut[k] = [ex.submit(run, model, *c, **kw) for c, kw in JOBS[k]]
     yield fut
     ex.shutdown(wait=False, cancel_futures=True)
@@ -145,6 +148,12 @@ def test_engine_paths_on_the_lockstep_model(started):
     analyzer kernel, the pickers against the reference's own qselect tables, random scripts (relays included, and the scripts on
     which the reference aborts) against the oracle, the C ABI's refusals"""
     results(started, "paths")
+
+
+def test_fresh_scripts_against_the_live_reference_on_the_lockstep_model(started):
+    """scripts nobody has stored — client behaviour, churn, swarms to completion, random scripts — with the compiled reference
+    (oracle/_ref) run live beside the device code: the one-warp engine and the grid engine with 3 CTAs"""
+    assert len(results(started, "live")) == 9 + 9 + 6
 
 
 def test_batch_engine_at_cta_scope_on_the_lockstep_model(started):
