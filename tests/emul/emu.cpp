@@ -153,7 +153,12 @@ static bool lanes_forward(const std::string &){
 #define EMU_STACK (4u << 20)
 // fiber stacks are reused from launch to launch (the host core launches a kernel per event)
 static thread_local std::vector<void *> stack_pool;
-static void *stack_get(void){ if (stack_pool.empty()) return malloc(EMU_STACK); void *p = stack_pool.back(); stack_pool.pop_back(); return p; }
+static void *stack_get(void){
+	if (!stack_pool.empty()) { void *p = stack_pool.back(); stack_pool.pop_back(); return p; }
+	void *p = malloc(EMU_STACK);
+	if (!p) { fprintf(stderr, "emu: out of memory for a fiber stack\n"); abort(); }
+	return p;
+}
 static void stack_put(void *p){ if (stack_pool.size() < 512) stack_pool.push_back(p); else free(p); }
 
 // the blocks of a cooperative launch meet here: one OS thread per block, every block alive at once
